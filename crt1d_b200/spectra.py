@@ -1,0 +1,54 @@
+"""Band definitions and the fractional-overlap band weights used by the fused PAR/NIR reduction.
+
+Only the piece of the reference's `crt1d/spectra.py` that is on the hot path's epilogue:
+`BAND_DEFNS_UM` (ref spectra.py:22-27) and `_x_frac_in_bounds` (ref spectra.py:71-126), which
+`diagnostics.band` (ref diagnostics.py:56-81) multiplies into a Sum over wavelength bands.
+"""
+import warnings
+
+import numpy as np
+
+BAND_DEFNS_UM = {
+    "PAR": (0.4, 0.7),
+    "NIR": (0.7, 2.5),
+    "UV": (0.01, 0.4),
+    "solar": (0.3, 5.0),
+}
+
+
+def x_frac_in_bounds(xe, bounds):
+    """Weight in [0, 1] of every bin (edges `xe`) that falls inside `bounds`; partial bins get their
+    overlapped fraction.  Vectorised restatement of ref spectra.py:71-126 (identical results,
+    including the `>=`/`<=` edge-touching rule that yields weight 0 for a bin that only touches)."""
+    xe = np.asarray(xe, dtype=float)
+    lo, hi = xe[:-1], xe[1:]
+    b1, b2 = bounds
+    if (b1 < lo[0] or b2 > hi[-1]) and tuple(bounds) != BAND_DEFNS_UM["solar"]:
+        warnings.warn(
+            f"`bounds` ({b1:.3g}, {b2:.3g}) extend outside the data range "
+            f"defined by `xe` ({lo[0]:.3g}, {hi[-1]:.3g})"
+        )
+    inside = (hi >= b1) & (lo <= b2)
+    width = hi - lo
+    w = np.ones_like(lo)
+    left = lo < b1
+    right = (~left) & (hi > b2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        w = np.where(left, (hi - b1) / width, w)
+        w = np.where(right, (b2 - lo) / width, w)
+    return np.where(inside, w, 0.0)
+
+
+_x_frac_in_bounds = x_frac_in_bounds  # the reference's private name
+
+
+def band_weights(wle, band_name):
+    """Weights for a named band ("PAR", "NIR", ...) on bins with edges `wle` (micrometres)."""
+    return x_frac_in_bounds(wle, BAND_DEFNS_UM[band_name])
+
+
+def edges_from_centers_widths(wl, dwl):
+    """Band edges as `Model._check_inputs` builds them  (ref model.py:286-287)."""
+    wl = np.asarray(wl, dtype=float)
+    dwl = np.asarray(dwl, dtype=float)
+    return np.r_[wl[0] - 0.5 * dwl[0], wl + 0.5 * dwl]
