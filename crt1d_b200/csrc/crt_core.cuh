@@ -1,0 +1,822 @@
+// crt_core.cuh -- per-column arithmetic of every scheme, shared by the CUDA kernels (crt_kernels.cu)
+// and by the host-compiled unit-test harness (tests/_hostcheck).  A "column" is one (scenario, band):
+// all n_z interface levels of one wavelength band of one scenario.  VEC adjacent bands are processed
+// together so that the kernels can issue 16-byte stores and have two independent dependency chains.
+//
+// Every function cites the reference lines (zmoon/crt1d, paths relative to crt1d/solvers/) whose
+// arithmetic it reproduces.  Nothing here is copied: the reference loops over bands in Python and
+// evaluates whole-profile numpy expressions; this code is organised as  scenario prologue (level
+// tables) -> per-band coefficients -> level sweep, with level-independent factors folded.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CRT_HD __host__ __device__ __forceinline__
+#else
+#define CRT_HD inline
+#endif
+
+namespace crt {
+
+// Output field slots of the column accessors.
+enum Field : int { F_IDR = 0, F_DN = 1, F_UP = 2, F_F = 3, F_X0 = 4, F_X1 = 5, F_X2 = 6, N_FIELDS = 7 };
+
+#ifndef CRT_PI
+#define CRT_PI 3.14159265358979323846
+#endif
+
+// exp() hook: one place to swap the exponential used in the level sweeps.
+CRT_HD double exp_m(double x) { return exp(x); }
+
+// Band inputs of one column group.
+template <int VEC>
+struct BandIn {
+    double leaf_r[VEC], leaf_t[VEC], soil_r[VEC], Idr0[VEC], Idf0[VEC];
+};
+
+// Canopy-integrated absorbed irradiance of a column from its ground (0) and top (n_z-1) level values:
+// Sum over layers of  a = dI_dr + dI_df_d - dI_df_u  (ref ../model.py:606-609) telescopes to the ends.
+CRT_HD double absorbed_from_ends(double Idr_top, double Idr_gnd, double dn_top, double dn_gnd,
+                                 double up_top, double up_gnd) {
+    return (Idr_top - Idr_gnd) + (dn_top - dn_gnd) + (up_gnd - up_top);
+}
+
+// =================================================================================================
+// 2s  Dickinson-Sellers two-stream   (ref _solve_2s.py:11-163)
+// =================================================================================================
+struct Scen2s {
+    double K;        // K_b_fn(psi), black-leaf extinction          (ref :26, :40)
+    double inv_mu;   // 1/cos(psi)
+    double mu_bar;   // (ref :32)
+    double cos2_tl;  // cos^2(radians(mla))                         (ref :28, :68)
+    double as_fac;   // 1 - mu log((mu+1)/mu)                       (ref :73)
+    double L_T;      // total LAI = lai[0]                          (ref :38)
+    double S2;       // exp(-K L_T)                                 (ref :91)
+};
+
+CRT_HD Scen2s scen_2s(double psi, double K, double mu_bar, double mla_deg, double L_T) {
+    Scen2s s;
+    const double mu = cos(psi);
+    s.K = K;
+    s.inv_mu = 1.0 / mu;
+    s.mu_bar = mu_bar;
+    const double ct = cos(mla_deg * (CRT_PI / 180.0));
+    s.cos2_tl = ct * ct;
+    s.as_fac = 1.0 - mu * log((mu + 1.0) / mu);
+    s.L_T = L_T;
+    s.S2 = exp(-K * L_T);
+    return s;
+}
+
+// Folded per-band coefficients:  I_up(L) = Au eK(L) + Bu e^{-hL} + Cu e^{+hL},  I_dn likewise.
+struct Coef2s {
+    double h, Au, Bu, Cu, Ad, Bd, Cd, Idr0;
+};
+
+CRT_HD Coef2s coef_2s(const Scen2s& s, double alpha, double tau, double rho_s, double Idr0, double Idf0) {
+    const double mu_bar = s.mu_bar, K = s.K;
+    const double omega = alpha + tau;                                                   // ref :65
+    const double beta = (0.5 * (alpha + tau + (alpha - tau) * s.cos2_tl)) / omega;      // ref :68 (eq. 3)
+    const double a_s = omega / 2.0 * s.as_fac;                                          // ref :73
+    const double beta_0 = (1.0 + mu_bar * K) / (omega * mu_bar * K) * a_s;              // ref :76 (eq. 4)
+    const double b = 1.0 - (1.0 - beta) * omega;                                        // ref :80-85
+    const double c = omega * beta;
+    const double d = omega * mu_bar * K * beta_0;
+    const double f = omega * mu_bar * K * (1.0 - beta_0);
+    const double h = sqrt(b * b - c * c) / mu_bar;
+    const double sigma = (mu_bar * K) * (mu_bar * K) + c * c - b * b;
+    const double u1 = b - c / rho_s;                                                    // ref :87-97
+    const double u2 = b - c * rho_s;
+    const double u3 = f + c * rho_s;
+    const double S1 = exp(-h * s.L_T);
+    const double S2 = s.S2;
+    const double mh = mu_bar * h, mK = mu_bar * K;
+    const double p1 = b + mh, p2 = b - mh, p3 = b + mK, p4 = b - mK;
+    const double D1 = p1 * (u1 - mh) / S1 - p2 * (u1 + mh) * S1;
+    const double D2 = (u2 + mh) / S1 - (u2 - mh) * S1;
+    const double h1 = -d * p4 - c * f;                                                  // ref :99-120
+    const double h1s = h1 / sigma;
+    const double t1 = d - h1s * p3;
+    const double t2 = d - c - h1s * (u1 + mK);
+    const double h2 = 1.0 / D1 * (t1 * (u1 - mh) / S1 - p2 * t2 * S2);
+    const double h3 = -1.0 / D1 * (t1 * (u1 + mh) * S1 - p1 * t2 * S2);
+    const double h4 = -f * p3 - c * d;  // Sellers (1996) correction
+    const double h4s = h4 / sigma;
+    const double t3 = u3 - h4s * (u2 - mK);
+    const double h5 = -1.0 / D2 * (h4s * (u2 + mh) / S1 + t3 * S2);
+    const double h6 = 1.0 / D2 * (h4s * (u2 - mh) * S1 + t3 * S2);
+    const double h7 = c / D1 * (u1 - mh) / S1;
+    const double h8 = -c / D1 * (u1 + mh) * S1;
+    const double h9 = 1.0 / D2 * (u2 + mh) / S1;
+    const double h10 = -1.0 / D2 * (u2 - mh) * S1;
+    Coef2s k;  // fold  I_dr0 * (h1 eK/sigma + h2 em + h3 ep) + I_df0 * (h7 em + h8 ep)   (ref :125-135)
+    k.h = h;
+    k.Au = Idr0 * h1s;
+    k.Bu = Idr0 * h2 + Idf0 * h7;
+    k.Cu = Idr0 * h3 + Idf0 * h8;
+    k.Ad = Idr0 * h4s;
+    k.Bd = Idr0 * h5 + Idf0 * h9;
+    k.Cd = Idr0 * h6 + Idf0 * h10;
+    k.Idr0 = Idr0;
+    return k;
+}
+
+// Level sweep of VEC 2s columns.  `L`, `eK` are the scenario's level tables (eK[j] = exp(-K L[j])).
+template <int VEC, class Out>
+CRT_HD void column_2s(const Scen2s& s, const double* L, const double* eK, int n_z, const BandIn<VEC>& in,
+                      Out& out, double (&absorbed)[VEC]) {
+    Coef2s k[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) k[v] = coef_2s(s, in.leaf_r[v], in.leaf_t[v], in.soil_r[v], in.Idr0[v], in.Idf0[v]);
+    double gnd[VEC][3];
+    for (int j = 0; j < n_z; ++j) {
+        const double Lj = L[j], eKj = eK[j];
+        double Idr[VEC], dn[VEC], up[VEC], F[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const double em = exp_m(-k[v].h * Lj);
+            const double ep = 1.0 / em;  // exp(+hL) (ref :125-131 evaluates it directly; <= 1 ulp apart)
+            up[v] = k[v].Au * eKj + (k[v].Bu * em + k[v].Cu * ep);
+            dn[v] = k[v].Ad * eKj + (k[v].Bd * em + k[v].Cd * ep);
+            Idr[v] = k[v].Idr0 * eKj;                                   // ref :150
+            F[v] = Idr[v] * s.inv_mu + 2.0 * up[v] + 2.0 * dn[v];       // ref :156
+            if (j == 0) { gnd[v][0] = Idr[v]; gnd[v][1] = dn[v]; gnd[v][2] = up[v]; }
+            if (j == n_z - 1) absorbed[v] = absorbed_from_ends(Idr[v], gnd[v][0], dn[v], gnd[v][1], up[v], gnd[v][2]);
+        }
+        out.st(F_IDR, j, Idr);
+        out.st(F_DN, j, dn);
+        out.st(F_UP, j, up);
+        out.st(F_F, j, F);
+    }
+}
+
+// =================================================================================================
+// bl  Beer-Lambert   (ref _solve_bl.py:9-93)
+// =================================================================================================
+struct ScenBl {
+    double K_b, inv_mu;
+};
+
+// tables: tau_b[j] = exp(-K_b L[j]) (ref :31), tau_d[j] = tau_df_fn(K_b_fn, L[j]) (ref :35-37)
+template <int VEC, class Out>
+CRT_HD void column_bl(const ScenBl& s, const double* L, const double* tau_b, const double* tau_d, int n_z,
+                      const BandIn<VEC>& in, Out& out, double (&absorbed)[VEC]) {
+    double Kg[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) Kg[v] = s.K_b * sqrt(1.0 - (in.leaf_t[v] + in.leaf_r[v]));  // ref :58-62
+    double gnd[VEC][2];
+    for (int j = 0; j < n_z; ++j) {
+        const double Lj = L[j], tb = tau_b[j], td = tau_d[j];
+        double Idr[VEC], dn[VEC], up[VEC], F[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const double tau_g = exp_m(-Kg[v] * Lj);                                   // ref :65
+            Idr[v] = in.Idr0[v] * tb;                                                  // ref :69
+            dn[v] = in.Idf0[v] * td + 0.5 * (in.Idr0[v] * (tau_g - tb));               // ref :70-79
+            up[v] = 0.0;                                                               // ref :87
+            F[v] = Idr[v] * s.inv_mu + 2.0 * dn[v];                                    // ref :90
+            if (j == 0) { gnd[v][0] = Idr[v]; gnd[v][1] = dn[v]; }
+            if (j == n_z - 1) absorbed[v] = absorbed_from_ends(Idr[v], gnd[v][0], dn[v], gnd[v][1], 0.0, 0.0);
+        }
+        out.st(F_IDR, j, Idr);
+        out.st(F_DN, j, dn);
+        out.st(F_UP, j, up);
+        out.st(F_F, j, F);
+    }
+}
+
+// =================================================================================================
+// bf  Bodin & Franklin (2012)   (ref _solve_bf.py:7-154)
+// g77 Goudriaan (1977)          (ref _solve_g77.py:7-135)
+// =================================================================================================
+struct ScenBf {
+    double k_b, mu, inv_mu, L_T;
+    double eb0;  // exp(-k_b L_T) = A_sl at the ground
+};
+
+CRT_HD ScenBf scen_bf(double psi, double K_b, double L_T) {
+    ScenBf s;
+    s.k_b = K_b;
+    s.mu = cos(psi);
+    s.inv_mu = 1.0 / s.mu;
+    s.L_T = L_T;
+    s.eb0 = exp(-K_b * L_T);
+    return s;
+}
+
+struct CoefBf {
+    double r_l, t_l, k_prime, rho_c, k_d, c1, c2, c3, soil, Idr0, Idf0, one_m_sigma, ed0;
+};
+
+// band coefficients common to bf and g77 (ref _solve_bf.py:66-81 / _solve_g77.py:54-69)
+CRT_HD CoefBf coef_bf_common(const ScenBf& s, double r_l, double t_l, double Idr0, double Idf0) {
+    CoefBf k;
+    k.r_l = r_l;
+    k.t_l = t_l;
+    const double sigma = r_l + t_l;
+    k.one_m_sigma = 1.0 - sigma;
+    k.k_prime = sqrt(1.0 - sigma);
+    k.rho_c = ((1.0 - k.k_prime) / (1.0 + k.k_prime)) * (2.0 / (1.0 + 1.6 * s.mu));  // Spitters (1986) eq. 1
+    k.k_d = 0.8 * sqrt(1.0 - sigma);                                                  // B&F eq. 2
+    k.c1 = k.k_d / k.k_prime;                                                         // eq. 14/15 factors
+    k.c2 = k.k_d / sqrt(1.0 - r_l);
+    k.c3 = k.k_d / sqrt(1.0 - t_l);
+    k.Idr0 = Idr0;
+    k.Idf0 = Idf0;
+    k.ed0 = exp(-k.k_d * s.L_T);
+    k.soil = 0.0;
+    return k;
+}
+
+// eb[j] = exp(-k_b L[j]) is the scenario level table.
+template <int VEC, class Out>
+CRT_HD void column_bf(const ScenBf& s, const double* L, const double* eb, int n_z, const BandIn<VEC>& in, Out& out,
+                      double (&rho_c)[VEC], double (&absorbed)[VEC]) {
+    CoefBf k[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        k[v] = coef_bf_common(s, in.leaf_r[v], in.leaf_t[v], in.Idr0[v], in.Idf0[v]);
+        // ground-level values feeding the soil-reflection term (eq. 11, ref :114)
+        const double I_df_g = k[v].Idf0 * k[v].ed0;
+        const double I_sc_d_g = k[v].Idr0 * k[v].t_l * ((s.eb0 - k[v].ed0) / (k[v].k_d - s.k_b));
+        k[v].soil = in.soil_r[v] * (k[v].Idr0 * s.eb0 + I_df_g + I_sc_d_g);
+        rho_c[v] = k[v].rho_c;
+    }
+    double gnd[VEC][3];
+    for (int j = 0; j < n_z; ++j) {
+        const double Lj = L[j], ebj = eb[j];
+        double Idr[VEC], dn[VEC], up[VEC], F[VEC], sl[VEC], sh[VEC], tot[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const double ed = exp_m(-k[v].k_d * Lj);                     // exp(-k_d L)
+            const double e2 = exp_m(-k[v].k_d * (s.L_T - Lj));           // exp(-k_d (L_T - L))   (ref :114)
+            const double ex = e2 * s.eb0;                                // exp(k_d L - (k_b + k_d) L_T)  (ref :103)
+            const double I_df = k[v].Idf0 * ed;                                                    // ref :86
+            Idr[v] = k[v].Idr0 * ebj;                                                              // ref :90
+            const double I_sc_d = k[v].Idr0 * k[v].t_l * ((ebj - ed) / (k[v].k_d - s.k_b));        // eq. 8, ref :97
+            const double I_sc_u = k[v].Idr0 * k[v].r_l * ((ebj - ex) / (k[v].k_d + s.k_b));        // eq. 9, ref :101-105
+            const double I_sr = k[v].soil * e2;                                                    // eq. 11
+            const double diff = k[v].c1 * I_df + k[v].c2 * I_sc_u + k[v].c3 * I_sc_d;
+            sh[v] = (1.0 - ebj) * diff;                                                            // eq. 14, ref :118-120
+            sl[v] = ebj * (diff + s.k_b * k[v].Idr0);                                              // eq. 15, ref :125-130
+            tot[v] = sl[v] + sh[v];
+            dn[v] = I_sc_d + I_df;
+            up[v] = I_sc_u + I_sr;
+            F[v] = Idr[v] * s.inv_mu + 2.0 * up[v] + 2.0 * dn[v];
+            if (j == 0) { gnd[v][0] = Idr[v]; gnd[v][1] = dn[v]; gnd[v][2] = up[v]; }
+            if (j == n_z - 1) absorbed[v] = absorbed_from_ends(Idr[v], gnd[v][0], dn[v], gnd[v][1], up[v], gnd[v][2]);
+        }
+        out.st(F_IDR, j, Idr);
+        out.st(F_DN, j, dn);
+        out.st(F_UP, j, up);
+        out.st(F_F, j, F);
+        out.st(F_X0, j, sl);
+        out.st(F_X1, j, sh);
+        out.st(F_X2, j, tot);
+    }
+}
+
+template <int VEC, class Out>
+CRT_HD void column_g77(const ScenBf& s, const double* L, const double* eb, int n_z, const BandIn<VEC>& in, Out& out,
+                       double (&absorbed)[VEC]) {
+    CoefBf k[VEC];
+    double kg[VEC], a_df[VEC], a_sc[VEC], b_sc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        k[v] = coef_bf_common(s, in.leaf_r[v], in.leaf_t[v], in.Idr0[v], in.Idf0[v]);
+        kg[v] = k[v].k_prime * s.k_b;                       // grey-leaf extinction of eq. 5
+        a_df[v] = k[v].Idf0 * (1.0 - k[v].rho_c);           // ref :73
+        a_sc[v] = k[v].Idr0 * (1.0 - k[v].rho_c);           // ref :84
+        b_sc[v] = -k[v].Idr0 * k[v].one_m_sigma;            // ref :84-86
+        const double I_df_g = a_df[v] * k[v].ed0;
+        const double I_sc_g = a_sc[v] * exp(-kg[v] * s.L_T) + b_sc[v] * s.eb0;
+        k[v].soil = in.soil_r[v] * (k[v].Idr0 * s.eb0 + I_df_g + 0.5 * I_sc_g);  // ref :95
+    }
+    double gnd[VEC][3];
+    for (int j = 0; j < n_z; ++j) {
+        const double Lj = L[j], ebj = eb[j];
+        double Idr[VEC], dn[VEC], up[VEC], F[VEC], sl[VEC], sh[VEC], tot[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const double ed = exp_m(-k[v].k_d * Lj);
+            const double eg = exp_m(-kg[v] * Lj);
+            const double e2 = exp_m(-k[v].k_d * (s.L_T - Lj));
+            const double I_df = a_df[v] * ed;
+            Idr[v] = k[v].Idr0 * ebj;
+            const double I_sc = a_sc[v] * eg + b_sc[v] * ebj;            // eq. 5
+            const double I_sc_d = 0.5 * I_sc, I_sc_u = 0.5 * I_sc;       // ref :89-90
+            const double I_sr = k[v].soil * e2;
+            const double diff = k[v].c1 * I_df + k[v].c2 * I_sc_u + k[v].c3 * I_sc_d;
+            sh[v] = (1.0 - ebj) * diff;
+            sl[v] = ebj * (diff + s.k_b * k[v].Idr0);
+            tot[v] = sl[v] + sh[v];
+            dn[v] = I_sc_d + I_df;
+            up[v] = I_sc_u + I_sr;
+            F[v] = Idr[v] * s.inv_mu + 2.0 * up[v] + 2.0 * dn[v];
+            if (j == 0) { gnd[v][0] = Idr[v]; gnd[v][1] = dn[v]; gnd[v][2] = up[v]; }
+            if (j == n_z - 1) absorbed[v] = absorbed_from_ends(Idr[v], gnd[v][0], dn[v], gnd[v][1], up[v], gnd[v][2]);
+        }
+        out.st(F_IDR, j, Idr);
+        out.st(F_DN, j, dn);
+        out.st(F_UP, j, up);
+        out.st(F_F, j, F);
+        out.st(F_X0, j, sl);
+        out.st(F_X1, j, sh);
+        out.st(F_X2, j, tot);
+    }
+}
+
+// =================================================================================================
+// n79  Norman (1979) after Bonan SP 14.3   (ref _solve_n79.py:11-200)
+//
+// The 2 n_z unknowns alternate (up_j, dn_j) per level j.  The reference's Thomas algorithm (`tdma`,
+// ref :167-200) is reproduced row for row; the forward-sweep coefficients e, f of the two rows of
+// level j are parked in the four OUTPUT arrays at level j (I_dr <- e_up, F <- e_dn, I_df_u <- f_up,
+// I_df_d <- f_dn) and overwritten with the final values during back-substitution, so the solve needs
+// no scratch memory beyond the arrays it has to write anyway.
+// Level tables: tbcum[j] = exp(-K_b L[j]) (n_z), tb[j] = exp(-K_b dlai[j]), td[j] = tau_d(dlai[j]),
+// fsun[j] = exp(-K_b laim[j]), dlai[j]  (all n_z - 1)   (ref :41-59).
+// =================================================================================================
+struct ScenN79 {
+    double inv_mu;
+};
+
+CRT_HD void n79_up_row(double td, double tbcum, double tb, double rho, double tau, double Idr0, double& a, double& c,
+                       double& d) {  // ref :101-108 / :122-129
+    const double refld = (1.0 - td) * rho;
+    const double trand = (1.0 - td) * tau + td;
+    const double fiv = refld - trand * trand / refld;
+    const double eiv = trand / refld;
+    a = -eiv;
+    c = -fiv;
+    d = Idr0 * tbcum * (1.0 - tb) * (rho - tau * eiv);
+}
+
+CRT_HD void n79_dn_row(double td, double tbcum, double tb, double rho, double tau, double Idr0, double& a, double& c,
+                       double& d) {  // ref :85-92 / :111-118
+    const double refld = (1.0 - td) * rho;
+    const double trand = (1.0 - td) * tau + td;
+    const double aiv = refld - trand * trand / refld;
+    const double biv = trand / refld;
+    a = -aiv;
+    c = -biv;
+    d = Idr0 * tbcum * (1.0 - tb) * (tau - rho * biv);
+}
+
+template <int VEC, class Out>
+CRT_HD void column_n79(const ScenN79& s, const double* tbcum, const double* tb, const double* td, const double* fsun,
+                       const double* dlai, int n_z, const BandIn<VEC>& in, Out& out, double (&absorbed)[VEC]) {
+    double e_prev[VEC], f_prev[VEC];
+    // ---- forward sweep (ref tdma :183-192); unit diagonal b = 1 everywhere
+    for (int j = 0; j < n_z; ++j) {
+        double eu[VEC], fu[VEC], ed[VEC], fd[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const double rho = in.leaf_r[v], tau = in.leaf_t[v], Idr0 = in.Idr0[v];
+            double a, c, d;
+            // upward row 2j
+            if (j == 0) {  // soil: up = albedo * (dn + direct)   (ref :79-82)
+                c = -in.soil_r[v];
+                d = Idr0 * tbcum[0] * in.soil_r[v];
+                eu[v] = c / 1.0;
+                fu[v] = d / 1.0;
+            } else {
+                n79_up_row(td[j - 1], tbcum[j], tb[j - 1], rho, tau, Idr0, a, c, d);
+                const double den = 1.0 - a * e_prev[v];
+                eu[v] = c / den;
+                fu[v] = (d - a * f_prev[v]) / den;
+            }
+            // downward row 2j+1
+            if (j == n_z - 1) {  // top boundary: dn = sky diffuse   (ref :132-135); a = c = 0
+                ed[v] = 0.0;
+                fd[v] = in.Idf0[v];
+            } else {
+                const int q = (j == 0) ? 1 : j;  // the soil row uses index 1 as shipped (ref :85-92)
+                n79_dn_row(td[q], tbcum[q + 1 - (j == 0 ? 1 : 0)], tb[q], rho, tau, Idr0, a, c, d);
+                const double den = 1.0 - a * eu[v];
+                ed[v] = c / den;
+                fd[v] = (d - a * fu[v]) / den;
+            }
+            e_prev[v] = ed[v];
+            f_prev[v] = fd[v];
+        }
+        out.st_tmp(F_IDR, j, eu);
+        out.st_tmp(F_UP, j, fu);
+        out.st_tmp(F_F, j, ed);
+        out.st_tmp(F_DN, j, fd);
+    }
+    // ---- back substitution (ref tdma :195-198) fused with the output stage (ref :141-161)
+    double up_above[VEC], dn_above[VEC], top[VEC][3];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) up_above[v] = dn_above[v] = 0.0;
+    for (int j = n_z - 1; j >= 0; --j) {
+        double eu[VEC], fu[VEC], ed[VEC], fd[VEC], Idr[VEC], dn[VEC], up[VEC], F[VEC];
+        out.ld_tmp(F_IDR, j, eu);
+        out.ld_tmp(F_UP, j, fu);
+        out.ld_tmp(F_F, j, ed);
+        out.ld_tmp(F_DN, j, fd);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            dn[v] = (j == n_z - 1) ? fd[v] : fd[v] - ed[v] * up_above[v];
+            up[v] = fu[v] - eu[v] * dn[v];
+            Idr[v] = in.Idr0[v] * tbcum[j];                                  // ref :151
+            F[v] = Idr[v] * s.inv_mu + 2.0 * dn[v] + 2.0 * up[v];            // ref :161
+        }
+        if (j < n_z - 1) {  // layer j (between levels j and j+1): absorbed per unit sunlit/shaded leaf area
+            double sl[VEC], sh[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const double one_m_om = 1.0 - (in.leaf_r[v] + in.leaf_t[v]);
+                const double direct = in.Idr0[v] * tbcum[j + 1] * (1.0 - tb[j]) * one_m_om;    // ref :145
+                const double diffuse = (dn_above[v] + up[v]) * (1.0 - td[j]) * one_m_om;       // ref :146
+                const double sun = diffuse * fsun[j] + direct;                                 // ref :147
+                const double shade = diffuse * (1.0 - fsun[j]);                                // ref :148
+                sl[v] = sun / (fsun[j] * dlai[j]);                                             // ref :154
+                sh[v] = shade / ((1.0 - fsun[j]) * dlai[j]);                                   // ref :155
+            }
+            out.st(F_X0, j, sl);
+            out.st(F_X1, j, sh);
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            if (j == n_z - 1) { top[v][0] = Idr[v]; top[v][1] = dn[v]; top[v][2] = up[v]; }
+            if (j == 0) absorbed[v] = absorbed_from_ends(top[v][0], Idr[v], top[v][1], dn[v], top[v][2], up[v]);
+            up_above[v] = up[v];
+            dn_above[v] = dn[v];
+        }
+        out.st(F_IDR, j, Idr);
+        out.st(F_DN, j, dn);
+        out.st(F_UP, j, up);
+        out.st(F_F, j, F);
+    }
+}
+
+// =================================================================================================
+// zq  Zhao & Qualls (2005) with the multiple-scattering correction   (ref _solve_zq.py:13-229)
+//
+// Unknowns x[0 .. 2m+1], m = n_z: SWu0 = x[::2], SWd0 = x[1::2] (m+1 each).  Row 0 (x0 = rho S_0) and
+// row 2m+1 (x = I_df0) are trivial; rows 2li-1, 2li (li = 1..m) are a tridiagonal whose coefficients
+// are identical in every real layer except next to the ghost soil (li = 1) and ghost top (li = m)
+// layers (ref :99-122).  Thomas elimination without pivoting (SuperLU in the reference; agreement
+// ~1e-14); forward coefficients of rows (2li-1, 2li) are parked at level li-1 of
+// the four main output arrays, as in column_n79.
+// =================================================================================================
+struct ScenZq {
+    double inv_mu, cos_psi, tau_i, t_psi;
+};
+
+struct ZqRowSet {  // coefficients of rows 2li-1 ("A") and 2li ("B") for one li class
+    double subA, mainA, supA, subB, mainB, supB, m_lo, m_hi, s_lo, s_me;
+};
+
+CRT_HD ZqRowSet zq_rows(double r_lo, double a_lo, double t_lo, double r_me, double a_me, double t_me, double r_hi,
+                        double a_hi, double t_hi) {
+    ZqRowSet q;
+    const double pen = t_me + (1.0 - t_me) * (1.0 - a_me) * (1.0 - r_me);
+    q.s_lo = r_lo * (1.0 - a_lo) * (1.0 - t_lo);
+    q.s_me = r_me * (1.0 - a_me) * (1.0 - t_me);
+    const double s_hi = r_hi * (1.0 - a_hi) * (1.0 - t_hi);
+    q.m_lo = 1.0 - q.s_lo * q.s_me;
+    q.m_hi = 1.0 - q.s_me * s_hi;
+    q.subA = -pen;             // A[2li-1, 2li-2]  (ref :113)
+    q.mainA = -q.s_lo * pen;   // A[2li-1, 2li-1]  (ref :114)
+    q.supA = q.m_lo;           // A[2li-1, 2li]    (ref :115)
+    q.subB = q.m_hi;           // A[2li,   2li-1]  (ref :116)
+    q.mainB = -s_hi * pen;     // A[2li,   2li]    (ref :117)
+    q.supB = -pen;             // A[2li,   2li+1]  (ref :118)
+    return q;
+}
+
+// eK[j] = exp(-K L[j]) level table.
+template <int VEC, class Out>
+CRT_HD void column_zq(const ScenZq& s, const double* eK, int n_z, const BandIn<VEC>& in, Out& out,
+                      double (&absorbed)[VEC]) {
+    const int m = n_z;
+    ZqRowSet q_bot[VEC], q_mid[VEC], q_top[VEC], q_one[VEC];
+    double cA[VEC], cB[VEC], x0[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        const double bL = in.leaf_r[v], tL = in.leaf_t[v], rho = in.soil_r[v];
+        const double r = 2.0 / 3 * (bL / (bL + tL)) + 1.0 / 3 * (tL / (bL + tL));   // eq. 23 (ref :40-43)
+        const double a = 1.0 - (bL + tL);                                           // ref :88
+        const double t = s.tau_i;
+        const double a0 = 1.0 - rho;                                                // ghost soil layer: r=1, t=0, a=1-rho
+        q_mid[v] = zq_rows(r, a, t, r, a, t, r, a, t);
+        q_bot[v] = zq_rows(1.0, a0, 0.0, r, a, t, r, a, t);                         // li = 1
+        q_top[v] = zq_rows(r, a, t, r, a, t, 0.0, 0.0, 1.0);                        // li = m (ghost top: r=0, t=1, a=0)
+        q_one[v] = zq_rows(1.0, a0, 0.0, r, a, t, 0.0, 0.0, 1.0);                   // m == 1: both ghosts adjacent
+        const double r_psi = 0.5 + 0.3334 * ((bL - tL) / (bL + tL)) * s.cos_psi;    // eq. 22 (ref :35-38)
+        cA[v] = r_psi * (1.0 - s.t_psi) * (1.0 - a);                                // C[2li-1] / (m_lo S)  (ref :136-139)
+        cB[v] = (1.0 - s.t_psi) * (1.0 - a) * (1.0 - r_psi);                        // C[2li]   / (m_hi S)  (ref :140-143)
+        x0[v] = rho * (in.Idr0[v] * eK[0]);                                         // row 0: x0 = rho S[0]  (ref :134)
+    }
+    // ---- forward sweep over li = 1..m; previous row is row 0 (e = 0, f = x0) at the start
+    double e_prev[VEC], f_prev[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { e_prev[v] = 0.0; f_prev[v] = x0[v]; }
+    for (int li = 1; li <= m; ++li) {
+        double eA[VEC], fA[VEC], eB[VEC], fB[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const ZqRowSet& q = (m == 1) ? q_one[v] : (li == 1 ? q_bot[v] : (li == m ? q_top[v] : q_mid[v]));
+            const double S = in.Idr0[v] * eK[li - 1];
+            const double dA = q.m_lo * cA[v] * S;
+            const double dB = q.m_hi * cB[v] * S;
+            const double denA = q.mainA - q.subA * e_prev[v];
+            eA[v] = q.supA / denA;
+            fA[v] = (dA - q.subA * f_prev[v]) / denA;
+            const double denB = q.mainB - q.subB * eA[v];
+            eB[v] = q.supB / denB;
+            fB[v] = (dB - q.subB * fA[v]) / denB;
+            e_prev[v] = eB[v];
+            f_prev[v] = fB[v];
+        }
+        out.st_tmp(F_IDR, li - 1, eA);
+        out.st_tmp(F_UP, li - 1, fA);
+        out.st_tmp(F_F, li - 1, eB);
+        out.st_tmp(F_DN, li - 1, fB);
+    }
+    // ---- back substitution + multiple-scattering correction (eq. 24, 25; ref :173-187) + outputs.
+    // x[2k] = SWu0[k], x[2k+1] = SWd0[k]; x[2m+1] = I_df0 (last row: sub-diagonal is 0).  Step li knows
+    // x[2li+1] and produces x[2li], x[2li-1].  Output level j needs SWu0[j] = x[2j] and
+    // SWd0[j+1] = x[2j+3]: level j = li is completed at step li, using x[2li+3] kept from step li+1.
+    double x_next[VEC];  // x[2li+1]
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) x_next[v] = in.Idf0[v];
+    double top[VEC][3];
+    double pend_SWd0[VEC];  // SWd0[li+1] = x[2li+3] for the output level j = li finished at step li
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) pend_SWd0[v] = 0.0;
+    for (int li = m; li >= 1; --li) {
+        double eA[VEC], fA[VEC], eB[VEC], fB[VEC];
+        out.ld_tmp(F_IDR, li - 1, eA);
+        out.ld_tmp(F_UP, li - 1, fA);
+        out.ld_tmp(F_F, li - 1, eB);
+        out.ld_tmp(F_DN, li - 1, fB);
+        double xB[VEC], xA[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            xB[v] = fB[v] - eB[v] * x_next[v];   // x[2li]   = SWu0[li]
+            xA[v] = fA[v] - eA[v] * xB[v];       // x[2li-1] = SWd0[li-1]
+        }
+        // Now SWu0[li] (xB) is known: finish output level j = li (needs SWu0[li], SWd0[li+1]) -- but
+        // level index j runs 0..m-1 with I_df_u[j] = SWu[j], I_df_d[j] = SWd[j+1]; level j=li exists
+        // only for li <= m-1 and its SWd0[j+1] = x[2li+3] was x_next of the previous step (pend_SWd0).
+        if (li <= m - 1) {
+            const int j = li;
+            double Idr[VEC], dn[VEC], up[VEC], F[VEC], dn_ss[VEC], up_ss[VEC], F_ss[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const ZqRowSet& q = (j + 1 == m) ? q_top[v] : q_mid[v];  // class of li' = j+1 (>= 2 here)
+                const double SWu0 = xB[v], SWd0 = pend_SWd0[v];
+                dn[v] = SWd0 / q.m_lo + q.s_me * SWu0 / q.m_lo;          // eq. 24 with li' = j+1  (ref :178-180)
+                up[v] = SWu0 / q.m_lo + q.s_lo * SWd0 / q.m_lo;          // eq. 25                 (ref :183-185)
+                dn_ss[v] = SWd0;
+                up_ss[v] = SWu0;
+                Idr[v] = in.Idr0[v] * eK[j];
+                F_ss[v] = Idr[v] * s.inv_mu + 2.0 * SWu0 + 2.0 * SWd0;   // ref :206
+                F[v] = Idr[v] * s.inv_mu + 2.0 * up[v] + 2.0 * dn[v];    // ref :207
+                if (j == m - 1) { top[v][0] = Idr[v]; top[v][1] = dn[v]; top[v][2] = up[v]; }
+            }
+            out.st(F_IDR, j, Idr);
+            out.st(F_DN, j, dn);
+            out.st(F_UP, j, up);
+            out.st(F_F, j, F);
+            out.st(F_X0, j, dn_ss);
+            out.st(F_X1, j, up_ss);
+            out.st(F_X2, j, F_ss);
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            pend_SWd0[v] = x_next[v];  // SWd0[li] = x[2li+1], needed by output level j = li-1
+            x_next[v] = xA[v];         // x[2(li-1)+1]
+        }
+    }
+    // output level j = 0: SWu0[0] = x[0] = x0 - e0 x[1] with e0 = 0; SWd0[1] = pend_SWd0
+    {
+        double Idr[VEC], dn[VEC], up[VEC], F[VEC], dn_ss[VEC], up_ss[VEC], F_ss[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const ZqRowSet& q = (m == 1) ? q_one[v] : q_bot[v];  // li' = 1
+            const double SWu0 = x0[v], SWd0 = pend_SWd0[v];
+            dn[v] = SWd0 / q.m_lo + q.s_me * SWu0 / q.m_lo;
+            up[v] = SWu0 / q.m_lo + q.s_lo * SWd0 / q.m_lo;
+            dn_ss[v] = SWd0;
+            up_ss[v] = SWu0;
+            Idr[v] = in.Idr0[v] * eK[0];
+            F_ss[v] = Idr[v] * s.inv_mu + 2.0 * SWu0 + 2.0 * SWd0;
+            F[v] = Idr[v] * s.inv_mu + 2.0 * up[v] + 2.0 * dn[v];
+            if (m == 1) { top[v][0] = Idr[v]; top[v][1] = dn[v]; top[v][2] = up[v]; }
+            absorbed[v] = absorbed_from_ends(top[v][0], Idr[v], top[v][1], dn[v], top[v][2], up[v]);
+        }
+        out.st(F_IDR, 0, Idr);
+        out.st(F_DN, 0, dn);
+        out.st(F_UP, 0, up);
+        out.st(F_F, 0, F);
+        out.st(F_X0, 0, dn_ss);
+        out.st(F_X1, 0, up_ss);
+        out.st(F_X2, 0, F_ss);
+    }
+}
+
+// =================================================================================================
+// 4s  Tian et al. (2007) four-stream   (ref _solve_4s.py:8-293)
+//
+// The reference integrates  y' = M y + v exp(-kappa x),  y = [R2d, R1d, R1u, R2u]  (ref `eqns` :48-97)
+// with scipy's collocation BVP solver, twice per band (direct, diffuse; ref :235-262).  M is constant
+// in x, so the solution is closed-form.  With D = (R2d, R1d), U = (R2u, R1u) the system reads
+//     D' =  P D + Q U + vD e^{-kappa x},     U' = -Q D - P U - vD e^{-kappa x},
+// and for s = D + U, w = D - U:   s' = (P - Q) w,   w' = (P + Q) s + 2 vD e^{-kappa x},
+// where P - Q = -diag(k2/mu2, k1/mu1) is diagonal.  Hence s'' = N s + 2 (P-Q) vD e^{-kappa x} with the
+// 2x2 matrix N = (P-Q)(P+Q), whose eigenvalues lambda_k^2 are real and positive for omega < 1.
+// Solution = 2 decaying + 2 growing exponentials (written as e^{-lambda x} and e^{-lambda (LAI-x)} so
+// nothing overflows) + the particular e^{-kappa x} term; the four coefficients come from the
+// boundary conditions (ref `dfdr_bcs` :99-138): D(0) = incident, U(LAI) = soil reflection of the
+// downward irradiance plus the direct beam.  Direct and diffuse problems share the matrix and their
+// solutions are only ever used summed (ref :274-281), so one 4x4 solve per band suffices.
+// Accuracy: limited by roundoff (~1e-13), i.e. far tighter than the reference's tol = 1e-6 BVP.
+// =================================================================================================
+struct Scen4s {
+    double mu0, inv_mu, kappa, L_T, eKT;  // cos psi, 1/cos psi, K_b = G/mu0, total LAI, exp(-kappa L_T)
+    double mu_s, m1, m2, G1, G2;          // sector cosine, mu_1, mu_2 (ref :188-189), G sector integrals (ref :148-149)
+};
+
+CRT_HD Scen4s scen_4s(double psi, double K_b, double G1, double G2, double mu_s, double L_T) {
+    Scen4s s;
+    s.mu0 = cos(psi);
+    s.inv_mu = 1.0 / s.mu0;
+    s.kappa = K_b;
+    s.L_T = L_T;
+    s.eKT = exp(-K_b * L_T);
+    s.mu_s = mu_s;
+    s.m1 = 0.5 * mu_s * mu_s;
+    s.m2 = 0.5 * (1.0 - mu_s * mu_s);
+    s.G1 = G1;
+    s.G2 = G2;
+    return s;
+}
+
+// 4x4 Gaussian elimination with partial pivoting, written with compare-and-swap so that everything
+// stays in registers on the device.
+CRT_HD void solve4(double (&A)[4][4], double (&b)[4]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int r = c + 1; r < 4; ++r) {
+            const bool sw = fabs(A[r][c]) > fabs(A[c][c]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double t = A[c][k];
+                A[c][k] = sw ? A[r][k] : t;
+                A[r][k] = sw ? t : A[r][k];
+            }
+            const double tb = b[c];
+            b[c] = sw ? b[r] : tb;
+            b[r] = sw ? tb : b[r];
+        }
+        const double inv = 1.0 / A[c][c];
+#pragma unroll
+        for (int r = c + 1; r < 4; ++r) {
+            const double f = A[r][c] * inv;
+#pragma unroll
+            for (int k = c + 1; k < 4; ++k) A[r][k] -= f * A[c][k];
+            b[r] -= f * b[c];
+        }
+    }
+#pragma unroll
+    for (int r = 3; r >= 0; --r) {
+        double acc = b[r];
+#pragma unroll
+        for (int k = r + 1; k < 4; ++k) acc -= A[r][k] * b[k];
+        b[r] = acc / A[r][r];
+    }
+}
+
+// Folded per-band coefficients: I_dn(x) = sum_k dnP[k] e^{-lam_k (LAI-x)} + dnM[k] e^{-lam_k x} + dnK e^{-kappa x}
+struct Coef4s {
+    double lam[2], dnP[2], dnM[2], upP[2], upM[2], dnK, upK, Idr0;
+};
+
+CRT_HD Coef4s coef_4s(const Scen4s& s, double r, double t, double rho, double Idr0, double Idf0) {
+    const double omega = r + t;                                   // ref :180
+    const double R_dr0 = Idr0 / (CRT_PI * s.mu0);                 // ref :169
+    const double R_df0 = Idf0 / CRT_PI;                           // ref :170
+    const double al = 0.5 * omega * (1.0 - s.mu_s) * s.G2;        // alpha_p = alpha_m (ref :190-191), P = 1
+    const double be = 0.5 * omega * (1.0 - s.mu_s) * s.G1;        // beta  (ref :192-193)
+    const double ga = 0.5 * omega * s.mu_s * s.G1;                // gamma (ref :194-195)
+    const double e1 = 0.25 * omega * R_dr0 * s.mu_s;              // eps_1 (ref :196-197)
+    const double e2 = 0.25 * omega * R_dr0 * (1.0 - s.mu_s);      // eps_2 (ref :198-199)
+    const double m1 = s.m1, m2 = s.m2;
+    // index 0 <-> sector 2 (|mu| in [mu_s, 1]), index 1 <-> sector 1
+    const double q0 = s.G2 / m2, q1 = s.G1 / m1;                  // -(P - Q) diagonal
+    const double T00 = (2.0 * al - s.G2) / m2, T01 = 2.0 * be / m2;
+    const double T10 = 2.0 * be / m1, T11 = (2.0 * ga - s.G1) / m1;
+    const double N00 = -q0 * T00, N01 = -q0 * T01, N10 = -q1 * T10, N11 = -q1 * T11;
+    const double G = s.kappa * s.mu0;
+    const double vD0 = G * e2 / m2, vD1 = G * e1 / m1;            // forcing of rows 1, 2 (ref :80-87)
+
+    // eigenpairs of N (real: N01 N10 >= 0)
+    const double tr = N00 + N11, dif = N00 - N11;
+    const double disc = sqrt(dif * dif + 4.0 * N01 * N10);
+    const double det = N00 * N11 - N01 * N10;
+    double l2[2];
+    l2[0] = 0.5 * (tr + disc);
+    l2[1] = det / l2[0];
+    double phi[2][2];
+    if (dif >= 0.0) {
+        phi[0][0] = l2[0] - N11; phi[0][1] = N10;
+        phi[1][0] = N01;         phi[1][1] = 0.5 * (-dif - disc);   // l2[1] - N00 without cancellation
+    } else {
+        phi[0][0] = N01;         phi[0][1] = 0.5 * (-dif + disc);   // l2[0] - N00
+        phi[1][0] = 0.5 * (dif - disc); phi[1][1] = N10;            // l2[1] - N11
+    }
+    Coef4s k;
+    double psi_[2][2], g[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double nrm = 1.0 / fmax(fabs(phi[i][0]), fabs(phi[i][1]));
+        phi[i][0] *= nrm;
+        phi[i][1] *= nrm;
+        k.lam[i] = sqrt(l2[i]);
+        psi_[i][0] = -k.lam[i] * phi[i][0] / q0;   // (P-Q)^{-1} phi lambda
+        psi_[i][1] = -k.lam[i] * phi[i][1] / q1;
+        g[i] = exp(-k.lam[i] * s.L_T);
+    }
+    // particular solution of the direct problem: (kappa^2 I - N) s_p = 2 (P-Q) vD
+    const double kap = s.kappa, k2 = kap * kap;
+    const double B00 = k2 - N00, B01 = -N01, B10 = -N10, B11 = k2 - N11;
+    const double r0 = -2.0 * q0 * vD0, r1 = -2.0 * q1 * vD1;
+    const double dB = B00 * B11 - B01 * B10;
+    const double sp0 = (r0 * B11 - B01 * r1) / dB, sp1 = (B00 * r1 - B10 * r0) / dB;
+    const double wp0 = kap * sp0 / q0, wp1 = kap * sp1 / q1;       // (P-Q)^{-1} (-kappa s_p)
+    const double Dp0 = 0.5 * (sp0 + wp0), Dp1 = 0.5 * (sp1 + wp1);
+    const double Up0 = 0.5 * (sp0 - wp0), Up1 = 0.5 * (sp1 - wp1);
+
+    // boundary conditions -> A c = rhs, c = [a~_1, a~_2, b_1, b_2]
+    double A[4][4], rhs[4];
+    double mP[2], mM[2];  // (m2, m1) . (phi +- psi)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double p0 = phi[i][0] + psi_[i][0], p1 = phi[i][1] + psi_[i][1];
+        const double n0 = phi[i][0] - psi_[i][0], n1 = phi[i][1] - psi_[i][1];
+        mP[i] = m2 * p0 + m1 * p1;
+        mM[i] = m2 * n0 + m1 * n1;
+        // top, x = 0:  D = incident            (ref :113-119, :137)
+        A[0][i] = 0.5 * p0 * g[i];   A[0][2 + i] = 0.5 * n0;
+        A[1][i] = 0.5 * p1 * g[i];   A[1][2 + i] = 0.5 * n1;
+        // bottom, x = LAI:  U_i - 2 rho (m2 D_0 + m1 D_1) = rho mu0 R_dr0 e^{-kappa LAI}   (ref :129-137)
+        A[2][i] = 0.5 * n0 - rho * mP[i];   A[2][2 + i] = (0.5 * p0 - rho * mM[i]) * g[i];
+        A[3][i] = 0.5 * n1 - rho * mP[i];   A[3][2 + i] = (0.5 * p1 - rho * mM[i]) * g[i];
+    }
+    const double mDp = m2 * Dp0 + m1 * Dp1;
+    const double bot = s.eKT * (rho * s.mu0 * R_dr0 + 2.0 * rho * mDp);
+    rhs[0] = R_df0 - Dp0;
+    rhs[1] = R_df0 - Dp1;
+    rhs[2] = bot - s.eKT * Up0;
+    rhs[3] = bot - s.eKT * Up1;
+    solve4(A, rhs);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {  // irradiances: 2 pi (mu_1 R1 + mu_2 R2)   (ref :246-249, :277-281)
+        k.dnP[i] = CRT_PI * rhs[i] * mP[i];
+        k.dnM[i] = CRT_PI * rhs[2 + i] * mM[i];
+        k.upP[i] = CRT_PI * rhs[i] * mM[i];
+        k.upM[i] = CRT_PI * rhs[2 + i] * mP[i];
+    }
+    k.dnK = 2.0 * CRT_PI * mDp;
+    k.upK = 2.0 * CRT_PI * (m2 * Up0 + m1 * Up1);
+    k.Idr0 = Idr0;
+    return k;
+}
+
+// L[j], eK[j] = exp(-kappa L[j]) level tables.
+template <int VEC, class Out>
+CRT_HD void column_4s(const Scen4s& s, const double* L, const double* eK, int n_z, const BandIn<VEC>& in, Out& out,
+                      double (&absorbed)[VEC]) {
+    Coef4s k[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) k[v] = coef_4s(s, in.leaf_r[v], in.leaf_t[v], in.soil_r[v], in.Idr0[v], in.Idf0[v]);
+    double gnd[VEC][3];
+    for (int j = 0; j < n_z; ++j) {
+        const double x = L[j], xr = s.L_T - L[j], eKj = eK[j];
+        double Idr[VEC], dn[VEC], up[VEC], F[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const double m0 = exp_m(-k[v].lam[0] * x), p0 = exp_m(-k[v].lam[0] * xr);
+            const double m1 = exp_m(-k[v].lam[1] * x), p1 = exp_m(-k[v].lam[1] * xr);
+            dn[v] = k[v].dnK * eKj + (k[v].dnP[0] * p0 + k[v].dnM[0] * m0) + (k[v].dnP[1] * p1 + k[v].dnM[1] * m1);
+            up[v] = k[v].upK * eKj + (k[v].upP[0] * p0 + k[v].upM[0] * m0) + (k[v].upP[1] * p1 + k[v].upM[1] * m1);
+            Idr[v] = k[v].Idr0 * eKj;                                  // ref :284
+            F[v] = Idr[v] * s.inv_mu + 2.0 * up[v] + 2.0 * dn[v];      // ref :290
+            if (j == 0) { gnd[v][0] = Idr[v]; gnd[v][1] = dn[v]; gnd[v][2] = up[v]; }
+            if (j == n_z - 1) absorbed[v] = absorbed_from_ends(Idr[v], gnd[v][0], dn[v], gnd[v][1], up[v], gnd[v][2]);
+        }
+        out.st(F_IDR, j, Idr);
+        out.st(F_DN, j, dn);
+        out.st(F_UP, j, up);
+        out.st(F_F, j, F);
+    }
+}
+
+}  // namespace crt

@@ -1,0 +1,22 @@
+// crt_internal.h -- C++ interface between the C ABI (crt_abi.cu) and the kernel launchers (crt_kernels.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "../../include/crt1d_b200.h"
+#include "crt_leafangle.cuh"
+
+namespace crt {
+
+size_t solve_shared_bytes(int scheme, int n_z);
+cudaError_t launch_solve(int scheme, const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream);
+cudaError_t launch_absorption(const crt1d_batch& in, const double* I_dr, const double* I_df_d, const double* I_df_u,
+                              const crt1d_absorption_out& out, bool vec2, cudaStream_t stream);
+cudaError_t launch_leaf_G(int family, double param, int64_t n, const double* psi, double* G, double* K_b,
+                          cudaStream_t stream);
+cudaError_t launch_tau_d(int family, double param, const QuadRule& rule, int64_t n, const double* L, double* tau_d,
+                         cudaStream_t stream);
+cudaError_t launch_leaf_integrals(int family, double param, double mu_s, const QuadRule& rule, double* out,
+                                  cudaStream_t stream);
+
+}  // namespace crt

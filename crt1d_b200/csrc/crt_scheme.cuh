@@ -1,0 +1,122 @@
+// crt_scheme.cuh -- scheme dispatch shared by the CUDA kernels and the host-compiled test harness:
+// which band-independent level tables a scheme needs (the scenario prologue the reference computes
+// before its band loop) and how one group of VEC columns is solved from them.
+#pragma once
+
+#include "../../include/crt1d_b200.h"
+#include "crt_core.cuh"
+
+namespace crt {
+
+// Number of n_z-long level tables each scheme keeps (shared memory on the device).
+CRT_HD int n_level_tables(int scheme) {
+    switch (scheme) {
+        case CRT1D_SCHEME_2S: return 2;   // L, exp(-K L)
+        case CRT1D_SCHEME_4S: return 2;   // L, exp(-K L)
+        case CRT1D_SCHEME_BL: return 3;   // L, tau_b, tau_d
+        case CRT1D_SCHEME_BF: return 2;   // L, exp(-k_b L)
+        case CRT1D_SCHEME_G77: return 2;  // L, exp(-k_b L)
+        case CRT1D_SCHEME_N79: return 5;  // tbcum, tb, td, fsun, dlai
+        case CRT1D_SCHEME_ZQ: return 1;   // exp(-K L)
+        default: return 0;
+    }
+}
+
+// Level-table entry j of scenario s (what each reference solver evaluates once, outside its band loop).
+// `tab` holds n_level_tables(scheme) consecutive arrays of n_z doubles.
+template <int SCHEME>
+CRT_HD void fill_level_tables(const crt1d_batch& in, int64_t s, int j, double* tab) {
+    const int n_z = in.n_z;
+    const double K_b = in.K_b[s];
+    const double* lai = in.lai_lib + (int64_t)in.lai_idx[s] * n_z;
+    const double Lj = lai[j];
+    if constexpr (SCHEME == CRT1D_SCHEME_2S || SCHEME == CRT1D_SCHEME_4S || SCHEME == CRT1D_SCHEME_BF ||
+                  SCHEME == CRT1D_SCHEME_G77) {
+        tab[j] = Lj;
+        tab[n_z + j] = exp(-K_b * Lj);  // _solve_2s.py:125,150; _solve_4s.py:284; _solve_bf.py:90-93; _solve_g77.py:77-80
+    } else if constexpr (SCHEME == CRT1D_SCHEME_BL) {
+        tab[j] = Lj;
+        tab[n_z + j] = exp(-K_b * Lj);  // tau_b, _solve_bl.py:31
+        tab[2 * n_z + j] = in.tau_d_lev[(int64_t)in.lai_idx[s] * n_z + j];  // tau_d, _solve_bl.py:35-37 (prologue quadrature)
+    } else if constexpr (SCHEME == CRT1D_SCHEME_ZQ) {
+        tab[j] = exp(-K_b * Lj);  // S / I_dr0, _solve_zq.py:131
+    } else if constexpr (SCHEME == CRT1D_SCHEME_N79) {
+        tab[j] = exp(-K_b * Lj);  // tbcum, _solve_n79.py:46
+        if (j < n_z - 1) {
+            const double dl = Lj - lai[j + 1];                                    // _solve_n79.py:41
+            tab[n_z + j] = exp(-K_b * dl);                                        // tb, :45
+            tab[2 * n_z + j] = in.tau_d_lev[(int64_t)in.lai_idx[s] * n_z + j];    // td, :53 (prologue quadrature / 9sky)
+            tab[3 * n_z + j] = exp(-K_b * ((Lj + lai[j + 1]) / 2.0));             // fracsun, :57-58
+            tab[4 * n_z + j] = dl;
+        } else {
+            tab[n_z + j] = tab[2 * n_z + j] = tab[3 * n_z + j] = tab[4 * n_z + j] = 0.0;
+        }
+    }
+}
+
+// Solve VEC adjacent columns of scenario s.  `tab` = the level tables above.
+template <int SCHEME, int VEC, class Out>
+CRT_HD void solve_column_group(const crt1d_batch& in, int64_t s, const double* tab, const BandIn<VEC>& b, Out& out,
+                               double (&rho_c)[VEC], double (&absorbed)[VEC]) {
+    const int n_z = in.n_z;
+    const double psi = in.psi[s], K_b = in.K_b[s];
+    const double L_T = in.lai_lib[(int64_t)in.lai_idx[s] * n_z];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) rho_c[v] = 0.0;
+    if constexpr (SCHEME == CRT1D_SCHEME_2S) {
+        const Scen2s sc = scen_2s(psi, K_b, in.mu_bar[s], in.mla_deg, L_T);
+        column_2s<VEC>(sc, tab, tab + n_z, n_z, b, out, absorbed);
+    } else if constexpr (SCHEME == CRT1D_SCHEME_4S) {
+        const double mu_s = in.mu_s > 0.0 ? in.mu_s : 0.501;
+        const Scen4s sc = scen_4s(psi, K_b, in.G_int[2 * s], in.G_int[2 * s + 1], mu_s, L_T);
+        column_4s<VEC>(sc, tab, tab + n_z, n_z, b, out, absorbed);
+    } else if constexpr (SCHEME == CRT1D_SCHEME_BL) {
+        ScenBl sc;
+        sc.K_b = K_b;
+        sc.inv_mu = 1.0 / cos(psi);
+        column_bl<VEC>(sc, tab, tab + n_z, tab + 2 * n_z, n_z, b, out, absorbed);
+    } else if constexpr (SCHEME == CRT1D_SCHEME_BF) {
+        const ScenBf sc = scen_bf(psi, K_b, L_T);
+        column_bf<VEC>(sc, tab, tab + n_z, n_z, b, out, rho_c, absorbed);
+    } else if constexpr (SCHEME == CRT1D_SCHEME_G77) {
+        const ScenBf sc = scen_bf(psi, K_b, L_T);
+        column_g77<VEC>(sc, tab, tab + n_z, n_z, b, out, absorbed);
+    } else if constexpr (SCHEME == CRT1D_SCHEME_N79) {
+        ScenN79 sc;
+        sc.inv_mu = 1.0 / cos(psi);
+        column_n79<VEC>(sc, tab, tab + n_z, tab + 2 * n_z, tab + 3 * n_z, tab + 4 * n_z, n_z, b, out, absorbed);
+    } else if constexpr (SCHEME == CRT1D_SCHEME_ZQ) {
+        ScenZq sc;
+        sc.cos_psi = cos(psi);
+        sc.inv_mu = 1.0 / sc.cos_psi;
+        sc.tau_i = in.tau_i[s];
+        sc.t_psi = in.tau_psi[s];
+        column_zq<VEC>(sc, tab, n_z, b, out, absorbed);
+    }
+}
+
+// Load the band inputs of VEC adjacent bands starting at b0 (b0 + VEC <= n_wl).
+template <int VEC>
+CRT_HD BandIn<VEC> load_bands(const crt1d_batch& in, int64_t s, int b0) {
+    BandIn<VEC> b;
+    const int64_t n_wl = in.n_wl;
+    const double* lr = in.leaf_r_lib + (int64_t)in.leaf_idx[s] * n_wl + b0;
+    const double* lt = in.leaf_t_lib + (int64_t)in.leaf_idx[s] * n_wl + b0;
+    const double* sr = in.soil_r_lib ? in.soil_r_lib + (int64_t)in.soil_idx[s] * n_wl + b0 : nullptr;
+    const double* dr = in.I_dr0_lib + (int64_t)in.sky_idx[s] * n_wl + b0;
+    const double* df = in.I_df0_lib + (int64_t)in.sky_idx[s] * n_wl + b0;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        b.leaf_r[v] = lr[v];
+        b.leaf_t[v] = lt[v];
+        b.soil_r[v] = sr ? sr[v] : 0.0;
+        b.Idr0[v] = dr[v];
+        b.Idf0[v] = df[v];
+    }
+    return b;
+}
+
+// Rows per scenario of extra-output slot x (n79's absorbed profiles live on the n_z - 1 layers).
+CRT_HD int extra_rows(int scheme, int n_z) { return scheme == CRT1D_SCHEME_N79 ? n_z - 1 : n_z; }
+
+}  // namespace crt

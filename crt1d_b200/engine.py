@@ -1,0 +1,249 @@
+"""Device-side execution of a `ScenarioBatch` through the C ABI.
+
+torch is plumbing here: it owns HBM allocations (tensors), streams and (in `distributed.py`) NCCL.  All
+arithmetic of the hot path happens in the kernels of libcrt1d_b200.so, which receive raw device
+pointers (`tensor.data_ptr()`) and the current CUDA stream handle.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _abi
+from . import _lib
+from .scenarios import ScenarioBatch
+from .solvers import common as _common
+
+SCHEMES = tuple(_abi.SCHEME_IDS)
+EXTRA_NAMES = {
+    "zq": ("I_df_d_ss", "I_df_u_ss", "F_ss"),
+    "bf": ("aI_lsl", "aI_lsh", "aI_l"),
+    "g77": ("aI_lsl", "aI_lsh", "aI_l"),
+    "n79": ("aI_lsl", "aI_lsh"),
+}
+MAIN_NAMES = ("I_dr", "I_df_d", "I_df_u", "F")
+DEFAULT_N_QUAD = 64  # Gauss-Legendre nodes per panel for the device-side prologue integrals
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("crt1d_b200 needs a CUDA device (no CPU fallback): torch.cuda.is_available() is False")
+    return torch
+
+
+def _stream_ptr(torch):
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def host_prologue(batch: ScenarioBatch, scheme, *, K_b_fn=None, G_fn=None, mu_s=0.501, tau_d_method="quad"):
+    """Band-independent scalars of every scenario evaluated ON THE HOST from Python callables, with the
+    same scipy calls as the reference solver's prologue (plugin path).  Returns a dict of numpy arrays."""
+    K_b_fn = K_b_fn or batch.leaf_angle.K_b_fn
+    G_fn = G_fn or batch.leaf_angle.G_fn
+    S = batch.n_scen
+    pro = {"K_b": np.array([K_b_fn(p) for p in batch.psi], dtype=np.float64)}
+    if scheme == "2s":
+        pro["mu_bar"] = np.full(S, _common.mu_bar_fn(G_fn))  # depends on G_fn only (ref _solve_2s.py:32)
+    elif scheme == "4s":
+        pro["G"] = np.array([G_fn(p) for p in batch.psi], dtype=np.float64)
+        pro["G_int"] = np.tile(np.array(_common.G_sector_integrals(G_fn, mu_s)), (S, 1))
+    elif scheme == "zq":
+        dm = np.array([_common.mean_dlai(row) for row in batch.lai_lib])
+        ti = np.array([_common.tau_df_fn(K_b_fn, d) for d in dm])
+        pro["tau_i"] = ti[batch.lai_idx]
+        pro["tau_psi"] = np.array(
+            [_common.tau_b_fn(K_b_fn, p, dm[i]) for p, i in zip(batch.psi, batch.lai_idx)], dtype=np.float64
+        )
+    elif scheme == "bl":
+        pro["tau_d_lev"] = np.array([[_common.tau_df_fn(K_b_fn, L) for L in row] for row in batch.lai_lib])
+    elif scheme == "n79":
+        td = np.zeros_like(batch.lai_lib)
+        for i, row in enumerate(batch.lai_lib):
+            td[i, :-1] = _common.tau_df_fn(K_b_fn, row[:-1] - row[1:], method=tau_d_method)
+        pro["tau_d_lev"] = td
+    return pro
+
+
+class DeviceBatch:
+    """A `ScenarioBatch` resident in HBM plus the scheme prologue; owns the ctypes `crt1d_batch`."""
+
+    def __init__(self, batch: ScenarioBatch, scheme, *, device=None, prologue="device", mu_s=0.501,
+                 tau_d_method="quad", n_quad=DEFAULT_N_QUAD):
+        if scheme not in _abi.SCHEME_IDS:
+            raise KeyError(f"{scheme!r} is not a CUDA scheme; valid: {', '.join(SCHEMES)}")
+        if scheme == "n79" and batch.n_z < 3:
+            raise IndexError("n79 needs n_z >= 3 (the reference indexes td[1], _solve_n79.py:85)")
+        torch = _torch()
+        self.lib = _lib.load()
+        self.scheme = scheme
+        self.batch = batch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.mu_s = float(mu_s)
+        self._t = {}
+        with torch.cuda.device(self.device):
+            put = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(self.device, non_blocking=False)  # noqa: E731
+            for k in ("psi", "lai_lib", "leaf_r_lib", "leaf_t_lib", "soil_r_lib", "I_dr0_lib", "I_df0_lib",
+                      "lai_idx", "leaf_idx", "soil_idx", "sky_idx"):
+                self._t[k] = put(getattr(batch, k))
+            if isinstance(prologue, dict):
+                for k, v in prologue.items():
+                    self._t[k] = put(np.asarray(v, dtype=np.float64))
+            elif prologue == "device":
+                self._device_prologue(torch, tau_d_method, n_quad)
+            else:
+                raise ValueError("prologue must be 'device' or a dict from host_prologue()")
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self._t.values())
+        self.cbatch = self._make_cbatch()
+
+    # -- prologue on the device, parametric leaf-angle family -------------------------------------
+    def _device_prologue(self, torch, tau_d_method, n_quad):
+        b, lib, la = self.batch, self.lib, self.batch.leaf_angle
+        S = b.n_scen
+        st = _stream_ptr(torch)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        K_b = torch.empty(S, **f64)
+        G = torch.empty(S, **f64)
+        _lib.check(lib.crt1d_leaf_G(la.family_id, la.param, S, self._t["psi"].data_ptr(), G.data_ptr(), K_b.data_ptr(), st))
+        self._t["K_b"], self._t["G"] = K_b, G
+        nq = 0 if tau_d_method == "9sky" else int(n_quad)
+        if tau_d_method not in ("quad", "9sky"):
+            raise ValueError("invalid `method`. Valid options are 'quad' and '9sky'.")
+        if self.scheme in ("2s", "4s"):
+            tri = torch.empty(3, **f64)
+            _lib.check(lib.crt1d_leaf_integrals(la.family_id, la.param, self.mu_s, int(n_quad), tri.data_ptr(), st))
+            if self.scheme == "2s":
+                self._t["mu_bar"] = tri[0].expand(S).contiguous()
+            else:
+                self._t["G_int"] = tri[1:3].expand(S, 2).contiguous()
+        elif self.scheme == "bl":
+            td = torch.empty_like(self._t["lai_lib"])
+            _lib.check(lib.crt1d_tau_d(la.family_id, la.param, nq, td.numel(), self._t["lai_lib"].data_ptr(), td.data_ptr(), st))
+            self._t["tau_d_lev"] = td
+        elif self.scheme == "n79":
+            dl = np.zeros_like(b.lai_lib)
+            dl[:, :-1] = b.lai_lib[:, :-1] - b.lai_lib[:, 1:]
+            dl_d = torch.as_tensor(dl).to(self.device)
+            td = torch.empty_like(dl_d)
+            _lib.check(lib.crt1d_tau_d(la.family_id, la.param, nq, td.numel(), dl_d.data_ptr(), td.data_ptr(), st))
+            self._t["tau_d_lev"] = td
+        elif self.scheme == "zq":
+            dm = np.array([_common.mean_dlai(row) for row in b.lai_lib])
+            dm_d = torch.as_tensor(dm).to(self.device)
+            ti = torch.empty_like(dm_d)
+            _lib.check(lib.crt1d_tau_d(la.family_id, la.param, int(n_quad), ti.numel(), dm_d.data_ptr(), ti.data_ptr(), st))
+            idx = self._t["lai_idx"].long()
+            self._t["tau_i"] = ti[idx].contiguous()
+            self._t["tau_psi"] = torch.exp(-K_b * dm_d[idx]).contiguous()  # tau_b_fn at the mean dlai (prologue scalar)
+
+    def _make_cbatch(self):
+        b = self.batch
+        cb = _abi.Batch()
+        cb.n_scen, cb.n_z, cb.n_wl = b.n_scen, b.n_z, b.n_wl
+        cb.n_lai, cb.n_leaf = b.lai_lib.shape[0], b.leaf_r_lib.shape[0]
+        cb.n_soil, cb.n_sky = b.soil_r_lib.shape[0], b.I_dr0_lib.shape[0]
+        for name, _ in _abi.Batch._fields_:
+            if name in self._t:
+                setattr(cb, name, self._t[name].data_ptr())
+        cb.mla_deg = float(b.mla)
+        cb.mu_s = self.mu_s
+        return cb
+
+    def tensor(self, name):
+        return self._t[name]
+
+    def narrow(self, lo, hi):
+        """A view of scenarios [lo, hi) sharing every device tensor (no copies): chunked sweeps."""
+        import copy
+
+        v = copy.copy(self)
+        v.batch = self.batch.slice(lo, hi)
+        v._t = dict(self._t)
+        for k in ("psi", "K_b", "G", "mu_bar", "G_int", "tau_i", "tau_psi", "lai_idx", "leaf_idx", "soil_idx", "sky_idx"):
+            if k in v._t:
+                v._t[k] = self._t[k][lo:hi]
+        v.cbatch = v._make_cbatch()
+        return v
+
+
+class OutputBuffers:
+    """Preallocated HBM outputs for up to `capacity` scenarios; reusable across chunks of a sweep."""
+
+    def __init__(self, scheme, capacity, n_z, n_wl, *, device, fields=MAIN_NAMES, extras=True, band_w=None):
+        torch = _torch()
+        self.scheme, self.capacity, self.n_z, self.n_wl = scheme, int(capacity), int(n_z), int(n_wl)
+        f64 = dict(dtype=torch.float64, device=device)
+        self.t = {}
+        for k in fields:
+            self.t[k] = torch.empty((self.capacity, n_z, n_wl), **f64)
+        self.extra_names = EXTRA_NAMES.get(scheme, ()) if extras else ()
+        rows = n_z - 1 if scheme == "n79" else n_z
+        for k in self.extra_names:
+            self.t[k] = torch.empty((self.capacity, rows, n_wl), **f64)
+        if scheme == "bf" and extras:
+            self.t["rho_c"] = torch.empty((self.capacity, n_wl), **f64)
+        self.band_w = None
+        if band_w is not None:
+            bw = np.ascontiguousarray(np.atleast_2d(np.asarray(band_w, dtype=np.float64)))
+            if bw.shape[1] != n_wl or not 1 <= bw.shape[0] <= 4:
+                raise ValueError("band_w must be (1..4, n_wl)")
+            self.band_w = torch.as_tensor(bw).to(device)
+            self.t["absorbed"] = torch.empty((self.capacity, bw.shape[0]), **f64)
+
+    def cout(self, n_scen):
+        if n_scen > self.capacity:
+            raise ValueError(f"{n_scen} scenarios exceed the buffer capacity {self.capacity}")
+        co = _abi.Out()
+        for k in MAIN_NAMES:
+            if k in self.t:
+                setattr(co, k, self.t[k].data_ptr())
+        for slot, k in zip(("x0", "x1", "x2"), self.extra_names):
+            setattr(co, slot, self.t[k].data_ptr())
+        if "rho_c" in self.t:
+            co.rho_c = self.t["rho_c"].data_ptr()
+        if self.band_w is not None:
+            co.band_w = self.band_w.data_ptr()
+            co.n_bw = self.band_w.shape[0]
+            co.absorbed = self.t["absorbed"].data_ptr()
+        return co
+
+    def bytes_written_per_scenario(self):
+        return sum(t[0].numel() * 8 for k, t in self.t.items())
+
+
+def solve_into(dbatch: DeviceBatch, out: OutputBuffers):
+    """Enqueue one solve of every scenario of `dbatch` on the current stream (asynchronous)."""
+    torch = _torch()
+    with torch.cuda.device(dbatch.device):
+        co = out.cout(dbatch.batch.n_scen)
+        rc = dbatch.lib.crt1d_solve(_abi.SCHEME_IDS[dbatch.scheme], ctypes.byref(dbatch.cbatch), ctypes.byref(co),
+                                    _stream_ptr(torch))
+    _lib.check(rc)
+    return out
+
+
+def solve(batch, scheme, *, device=None, prologue="device", band_w=None, extras=True, mu_s=0.501,
+          tau_d_method="quad", n_quad=DEFAULT_N_QUAD):
+    """Solve every scenario of `batch`; returns a dict of torch tensors in HBM, profiles (S, n_z, n_wl)."""
+    db = batch if isinstance(batch, DeviceBatch) else DeviceBatch(
+        batch, scheme, device=device, prologue=prologue, mu_s=mu_s, tau_d_method=tau_d_method, n_quad=n_quad)
+    ob = OutputBuffers(scheme, db.batch.n_scen, db.batch.n_z, db.batch.n_wl, device=db.device, extras=extras, band_w=band_w)
+    solve_into(db, ob)
+    return ob.t
+
+
+def calc_absorption(dbatch: DeviceBatch, I_dr, I_df_d, I_df_u):
+    """Layerwise absorption of every scenario (replaces `_calc_absorption`, ref model.py:573-647).
+    Inputs/outputs are torch tensors in HBM; outputs (S, n_z-1, n_wl)."""
+    torch = _torch()
+    S, nz, nw = dbatch.batch.n_scen, dbatch.batch.n_z, dbatch.batch.n_wl
+    names = ("aI", "aI_df", "aI_dr", "aI_sh", "aI_sl", "aI_df_sl", "aI_df_sh")
+    outs = {k: torch.empty((S, nz - 1, nw), dtype=torch.float64, device=dbatch.device) for k in names}
+    ao = _abi.AbsorptionOut()
+    for k in names:
+        setattr(ao, k, outs[k].data_ptr())
+    with torch.cuda.device(dbatch.device):
+        rc = dbatch.lib.crt1d_calc_absorption(ctypes.byref(dbatch.cbatch), I_dr.data_ptr(), I_df_d.data_ptr(),
+                                              I_df_u.data_ptr(), ctypes.byref(ao), _stream_ptr(torch))
+    _lib.check(rc)
+    return outs
