@@ -24,6 +24,16 @@ MAIN_NAMES = ("I_dr", "I_df_d", "I_df_u", "F")
 DEFAULT_N_QUAD = 64  # Gauss-Legendre nodes per panel for the device-side prologue integrals
 
 
+BATCH_ARRAYS = ("psi", "lai_lib", "leaf_r_lib", "leaf_t_lib", "soil_r_lib", "I_dr0_lib", "I_df0_lib",
+                "lai_idx", "leaf_idx", "soil_idx", "sky_idx")
+
+
+def pin_batch(batch):
+    """Page-locked host copies of a batch's arrays (made once; H2D from them is asynchronous DMA)."""
+    torch = _torch()
+    return {k: torch.as_tensor(np.ascontiguousarray(getattr(batch, k))).pin_memory() for k in BATCH_ARRAYS}
+
+
 def _torch():
     import torch
 
@@ -69,7 +79,7 @@ class DeviceBatch:
     """A `ScenarioBatch` resident in HBM plus the scheme prologue; owns the ctypes `crt1d_batch`."""
 
     def __init__(self, batch: ScenarioBatch, scheme, *, device=None, prologue="device", mu_s=0.501,
-                 tau_d_method="quad", n_quad=DEFAULT_N_QUAD):
+                 tau_d_method="quad", n_quad=DEFAULT_N_QUAD, pinned=None):
         if scheme not in _abi.SCHEME_IDS:
             raise KeyError(f"{scheme!r} is not a CUDA scheme; valid: {', '.join(SCHEMES)}")
         if scheme == "n79" and batch.n_z < 3:
@@ -83,9 +93,11 @@ class DeviceBatch:
         self._t = {}
         with torch.cuda.device(self.device):
             put = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(self.device, non_blocking=False)  # noqa: E731
-            for k in ("psi", "lai_lib", "leaf_r_lib", "leaf_t_lib", "soil_r_lib", "I_dr0_lib", "I_df0_lib",
-                      "lai_idx", "leaf_idx", "soil_idx", "sky_idx"):
-                self._t[k] = put(getattr(batch, k))
+            for k in BATCH_ARRAYS:
+                if pinned is not None:  # page-locked staging copies made once by the caller (pin_batch)
+                    self._t[k] = pinned[k].to(self.device, non_blocking=True)
+                else:
+                    self._t[k] = put(getattr(batch, k))
             if isinstance(prologue, dict):
                 for k, v in prologue.items():
                     self._t[k] = put(np.asarray(v, dtype=np.float64))

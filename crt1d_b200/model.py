@@ -1,0 +1,338 @@
+"""`Model`: the reference's front end for the solver hot path, with a batched scenario axis.
+
+Mirrors the part of `crt1d.Model` that sits directly on the hot path (ref crt1d/model.py:49-336,
+573-664): parameter handling and validation (`update_p`, `_check_inputs`), scheme dispatch through
+`AVAILABLE_SCHEMES` (`run`), the layer-absorption post-step (`calc_absorption`) and -- new -- the
+batched axis (`run_batch`, `run_sensitivity`, which the reference leaves as `NotImplementedError`,
+ref model.py:650-664).  Plotting stays out of scope; `to_xr` is kept but imports xarray lazily.
+"""
+import itertools
+import warnings
+from collections import namedtuple
+from copy import deepcopy
+
+import numpy as np
+
+from .cases import load_default_case
+from .leaf_angle import LeafAngle
+from .scenarios import ScenarioBatch
+from .solvers import AVAILABLE_SCHEMES
+from .solvers import RET_KEYS_ALL_SCHEMES
+from .spectra import BAND_DEFNS_UM
+from .spectra import x_frac_in_bounds
+from .variables import VMD
+
+__all__ = ("Model", "run_sensitivity")
+
+CANOPY_DESCRIPTION_KEYS = [
+    "lai", "z", "dlai", "lai_tot", "lai_eff", "mla", "clump", "leaf_t", "leaf_r", "soil_r", "wl_leafsoil",
+    "orient", "G_fn",
+]
+CanopyDescription = namedtuple("CanopyDescription", " ".join(CANOPY_DESCRIPTION_KEYS))
+
+ABSORPTION_KEYS = ("aI", "aI_df", "aI_dr", "aI_sh", "aI_sl", "aI_df_sl", "aI_df_sh")
+
+
+class Model:
+    """1-D canopy radiative transfer with a selectable scheme, solved on the GPU."""
+
+    required_input_keys = tuple(
+        [k for k in CANOPY_DESCRIPTION_KEYS if k not in ("dlai", "lai_tot", "lai_eff")]
+        + ["I_dr0_all", "I_df0_all", "wl", "dwl", "psi"]
+    )
+    _optional_input_keys = ("leaf_angle", "green")
+    _schemes = AVAILABLE_SCHEMES
+    vmd = VMD
+
+    def __init__(self, scheme="2s", nlayers=60, **p_kwargs):
+        self.nlayers = nlayers
+        self.p_default = load_default_case(nlayers=self.nlayers)
+        self._p = deepcopy(self.p_default)
+        self.assign_scheme(scheme)
+        if p_kwargs:
+            self.update_p(**p_kwargs)
+        else:
+            self._check_inputs()
+        self._run_count = 0
+        self.absorption = None
+        self.out = {}
+        self.out_extra = {}
+
+    # ------------------------------------------------------------------ parameters
+    @property
+    def p(self):
+        print(
+            "Please update parameters using `.update_p()`! Changes to `.p` will not be stored!\n"
+            "Extract (copy) the parameters using `.copy_p()` or summarize using `.print_p()`."
+        )
+
+    def print_p(self):
+        import pprint
+
+        with np.printoptions(precision=3, threshold=7):
+            pprint.PrettyPrinter(indent=1).pprint(self._p)
+
+    def copy_p(self):
+        return deepcopy(self._p)
+
+    @property
+    def cd(self):
+        return CanopyDescription(**{k: v for k, v in self._p.items() if k in CANOPY_DESCRIPTION_KEYS})
+
+    def __repr__(self):
+        return f"Model(scheme={self.scheme['name']!r}, psi={self._p['psi']:.4g})"
+
+    def assign_scheme(self, scheme_name, *, verbose=False):
+        """Select the scheme; an unknown id prints the valid ones and falls back to `2s`, like the
+        reference (ref model.py:151-170)."""
+        try:
+            self.scheme = AVAILABLE_SCHEMES[scheme_name]
+            if verbose:
+                print("\n\n" + "=" * 40 + f"\nscheme: {self.scheme['name']}\n" + "-" * 40)
+        except KeyError:
+            print(f"{scheme_name!r} is not a valid scheme name/ID!")
+            print(f"The valid ones are: {', '.join(AVAILABLE_SCHEMES)}.")
+            print("Defaulting to Dickinson-Sellers two-stream.\n")
+            self.scheme = AVAILABLE_SCHEMES["2s"]
+        return self
+
+    def update_p(self, **kwargs):
+        """Update inputs; on any validation failure warn and revert (ref model.py:172-203)."""
+        import traceback
+
+        saved = deepcopy(self._p)
+        try:
+            for k, v in kwargs.items():
+                if k not in Model.required_input_keys and k not in Model._optional_input_keys:
+                    warnings.warn(f"{k!r} is not intended as an input and will be ignored")
+                    continue
+                self._p[k] = v
+                if k == "G_fn" and "leaf_angle" not in kwargs:
+                    self._p.pop("leaf_angle", None)  # a custom callable invalidates the parametric family
+            self._check_inputs()
+        except Exception:
+            warnings.warn(
+                f"Updating parameters failed. Full traceback:\n\n{traceback.format_exc()}\nReverting."
+            )
+            self._p = saved
+        return self
+
+    def _check_inputs(self):
+        """Validate the LAI profile / wavelength grids and derive dependent inputs (ref model.py:222-294)."""
+        p = self._p
+        for key in Model.required_input_keys:
+            if key not in p:
+                raise Exception(f"required key {key} is not present. Set it using `update_p`.")
+        lai, z = np.asarray(p["lai"], dtype=float), np.asarray(p["z"], dtype=float)
+        assert z.size == lai.size
+        self.nlev = lai.size
+        assert z[-1] > z[0]
+        assert lai[0] > lai[-1]
+        assert lai[-1] == 0
+        dz = np.diff(z)
+        dlai = lai[:-1] - lai[1:]
+        p["lai_tot"] = lai[0]
+        p["lai_eff"] = lai * p["clump"]
+        p["dlai"] = dlai
+        p["dlai_eff"] = dlai * p["clump"]
+        p["zm"] = z[:-1] + 0.5 * dz
+        p["dz"] = dz
+        psi = p["psi"]
+        if "mu" in p:
+            if p["mu"] != np.cos(psi):
+                warnings.warn(
+                    "Provided `mu` not consistent with provided `psi`. "
+                    "`mu` will be updated based on the value of `psi`."
+                )
+        else:
+            p["mu"] = np.cos(psi)
+        wl_toc, wl_op = np.asarray(p["wl"]), np.asarray(p["wl_leafsoil"])
+        assert wl_toc.size == wl_op.size
+        if not np.allclose(wl_toc, wl_op):
+            warnings.warn(
+                "Provided wavelengths for optical props (`wl_leafsoil`) and toc BC (`wl`) "
+                f"appear to be incompatible:\n`wl - wl_leafsoil`:\n{wl_toc - wl_op}"
+            )
+        self.nwl = wl_toc.size
+        assert p["wl"].size == p["dwl"].size
+        p["wle"] = np.r_[p["wl"][0] - 0.5 * p["dwl"][0], p["wl"] + 0.5 * p["dwl"]]
+        G_fn = p["G_fn"]
+        p["K_b_fn"] = lambda psi_: G_fn(psi_) / np.cos(psi_)
+        p["G"] = G_fn(psi)
+        p["K_b"] = p["K_b_fn"](psi)
+
+    # ------------------------------------------------------------------ single-scenario run (plugin path)
+    def run(self, **extra_solver_kwargs):
+        """Run the selected scheme on the current parameters (ref model.py:296-320)."""
+        self._check_inputs()
+        scheme, p = self.scheme, self._p
+        sol = scheme["solver"](**{k: p[k] for k in scheme["args"]}, **extra_solver_kwargs)
+        self.out.update({k: v for k, v in sol.items() if k in RET_KEYS_ALL_SCHEMES})
+        self.out_extra.update({f"{k}_scheme": v for k, v in sol.items() if k not in RET_KEYS_ALL_SCHEMES})
+        self._run_count += 1
+        return self
+
+    @property
+    def out_all(self):
+        return {**self.out, **self.out_extra}
+
+    def calc_absorption(self):
+        """Layerwise absorption from the stored profiles, on the GPU (ref model.py:327-336, 573-647)."""
+        if self._run_count == 0:
+            raise Exception("Must run the model first.")
+        self.absorption = _calc_absorption(self)
+        return self
+
+    # ------------------------------------------------------------------ batched axis
+    def scenario_batch(self, **overrides):
+        """The current parameters as a one-scenario `ScenarioBatch` (starting point for sweeps)."""
+        p = {**self._p, **overrides}
+        la = p.get("leaf_angle")
+        if la is None:
+            raise ValueError(
+                "the batched path needs a parametric leaf-angle family: pass `leaf_angle=LeafAngle(...)` "
+                "(an arbitrary Python `G_fn` cannot be evaluated inside a CUDA kernel)"
+            )
+        return ScenarioBatch.from_params(p, leaf_angle=la)
+
+    def run_batch(self, batch, *, bands=("PAR", "NIR"), profiles=True, **solver_options):
+        """Run the selected scheme on every scenario of `batch` in one launch.
+
+        Returns a dict of numpy arrays with a leading scenario axis: the scheme's profiles
+        `(S, n_z, n_wl)` if `profiles`, and `absorbed` `(S, len(bands))` -- canopy-integrated absorbed
+        irradiance in each named band (fused reduction; needs `batch.wl`/`batch.dwl`)."""
+        from . import engine
+
+        name = self.scheme["name"]
+        band_w = None
+        if bands and batch.wl is not None:
+            wle = np.r_[batch.wl[0] - 0.5 * batch.dwl[0], batch.wl + 0.5 * batch.dwl]
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                band_w = np.stack([x_frac_in_bounds(wle, BAND_DEFNS_UM[b]) for b in bands])
+        res = engine.solve(batch, name, band_w=band_w, **solver_options)
+        keep = res if profiles else {k: v for k, v in res.items() if k == "absorbed"}
+        return {k: v.cpu().numpy() for k, v in keep.items()}
+
+    # ------------------------------------------------------------------ export
+    def to_xr(self, *, info=""):
+        """Pack inputs/outputs into an `xarray.Dataset` with dims z, zm, wl, wle (ref model.py:338-447).
+        xarray is imported here, not at module import: it is not part of this image."""
+        try:
+            import xarray as xr
+        except ImportError as e:
+            raise ImportError("Model.to_xr needs xarray, which is not installed") from e
+        if self._run_count == 0:
+            raise Exception("Must run the model first.")
+        p = self._p
+
+        def tup(name, data, dims):
+            m = VMD[name] if name in VMD else None
+            attrs = {"units": m.units, "long_name": m.long_name} if m else {}
+            return (dims, data, attrs)
+
+        coords = {
+            "z": tup("z", p["z"], "z"), "zm": tup("zm", p["zm"], "zm"),
+            "wl": tup("wl", p["wl"], "wl"), "wle": tup("wle", p["wle"], "wle"),
+        }
+        dv = {k: tup(k, v, ("z", "wl")) for k, v in self.out.items()}
+        dv["lai"] = tup("lai", p["lai"], "z")
+        dv["dlai"] = tup("dlai", p["dlai"], "zm")
+        dv["dwl"] = tup("dwl", p["dwl"], "wl")
+        for k, v in self.out_extra.items():
+            base = k[: -len("_scheme")]
+            if base.startswith("aI"):
+                if base not in VMD:
+                    raise KeyError(f"scheme extra {base!r} has no variable metadata")
+                dims = ("z", "wl") if v.shape[0] == self.nlev else ("zm", "wl")
+                dv[k] = tup(base, v, dims)
+        if self.absorption is not None:
+            for k, v in self.absorption.items():
+                dv[k] = tup(k, v, ("zm", "wl") if v.ndim == 2 else "zm")
+        attrs = {
+            "info": info, "scheme_name": self.scheme["name"], "scheme_long_name": self.scheme["long_name"],
+            "scheme_short_name": self.scheme["short_name"], "sza": np.rad2deg(p["psi"]), "psi": p["psi"],
+            "mu": p["mu"], "G": p["G"], "K_b": p["K_b"],
+        }
+        return xr.Dataset(coords=coords, data_vars=dv, attrs=attrs)
+
+
+def _calc_absorption(m):
+    """Layerwise absorption through the CUDA kernel `crt1d_calc_absorption` (ref model.py:573-647)."""
+    import torch
+
+    from . import engine
+
+    p, out = m._p, m.out
+    batch = ScenarioBatch.from_params({**p, "leaf_angle": p.get("leaf_angle") or LeafAngle()})
+    db = engine.DeviceBatch(batch, "2s", prologue={"K_b": np.array([p["K_b"]], dtype=np.float64)})
+    dev = {k: torch.as_tensor(np.ascontiguousarray(out[k])[None]).to(db.device) for k in ("I_dr", "I_df_d", "I_df_u")}
+    res = engine.calc_absorption(db, dev["I_dr"], dev["I_df_d"], dev["I_df_u"])
+    absorption = {k: res[k][0].cpu().numpy() for k in ABSORPTION_KEYS}
+    lai = p["lai"]
+    laim = (lai[:-1] + lai[1:]) / 2
+    absorption["laim"] = laim
+    absorption["f_slm"] = np.exp(-p["K_b"] * laim)
+    assert np.allclose(absorption["aI_sl"] + absorption["aI_sh"], absorption["aI"])  # ref model.py:635
+    return absorption
+
+
+_SWEEPABLE = ("psi", "lai", "leaf_r", "leaf_t", "soil_r", "I_dr0_all", "I_df0_all")
+
+
+def run_sensitivity(m0, p_sets, *, bands=("PAR", "NIR"), profiles=True):
+    """Run the cross product of the value lists in `p_sets` as ONE batched GPU solve.
+
+    The reference declares this function but never implemented it (ref model.py:650-664).  `m0` is the
+    base case; `p_sets` maps a parameter name (`psi`, `lai`, `leaf_r`, `leaf_t`, `soil_r`, `I_dr0_all`,
+    `I_df0_all`) to a list of values.  Returns a dict: every output array gets one leading axis per key
+    of `p_sets` (in its order), e.g. `I_df_d` has shape `(len(psi_list), len(lai_list), n_z, n_wl)`;
+    `"dims"` lists the swept names.  With xarray installed, `to_dataset(result)` is straightforward --
+    it is not imported here."""
+    for k in p_sets:
+        if k not in _SWEEPABLE:
+            raise KeyError(f"cannot sweep {k!r}; sweepable parameters: {', '.join(_SWEEPABLE)}")
+    m0._check_inputs()
+    p = m0._p
+    la = p.get("leaf_angle")
+    if la is None:
+        raise ValueError("run_sensitivity needs a parametric `leaf_angle` (see Model.scenario_batch)")
+    keys = list(p_sets)
+    sizes = [len(p_sets[k]) for k in keys]
+    vals = {k: list(p_sets[k]) for k in keys}
+
+    def lib(names):
+        """Library rows = cross product of the swept members of `names`; returns (rows per name, index fn)."""
+        swept = [n for n in names if n in vals]
+        combos = list(itertools.product(*[range(len(vals[n])) for n in swept])) or [()]
+        rows = {n: [] for n in names}
+        for c in combos:
+            pick = dict(zip(swept, c))
+            for n in names:
+                rows[n].append(np.asarray(vals[n][pick[n]] if n in pick else p[n], dtype=np.float64))
+        lut = {c: i for i, c in enumerate(combos)}
+        return rows, swept, lut
+
+    lai_rows, lai_sw, lai_lut = lib(["lai"])
+    leaf_rows, leaf_sw, leaf_lut = lib(["leaf_r", "leaf_t"])
+    soil_rows, soil_sw, soil_lut = lib(["soil_r"])
+    sky_rows, sky_sw, sky_lut = lib(["I_dr0_all", "I_df0_all"])
+    psi, i_lai, i_leaf, i_soil, i_sky = [], [], [], [], []
+    for combo in itertools.product(*[range(n) for n in sizes]):
+        pick = dict(zip(keys, combo))
+        psi.append(vals["psi"][pick["psi"]] if "psi" in pick else p["psi"])
+        i_lai.append(lai_lut[tuple(pick[n] for n in lai_sw)])
+        i_leaf.append(leaf_lut[tuple(pick[n] for n in leaf_sw)])
+        i_soil.append(soil_lut[tuple(pick[n] for n in soil_sw)])
+        i_sky.append(sky_lut[tuple(pick[n] for n in sky_sw)])
+    batch = ScenarioBatch(
+        psi=psi, lai_lib=np.stack(lai_rows["lai"]), leaf_r_lib=np.stack(leaf_rows["leaf_r"]),
+        leaf_t_lib=np.stack(leaf_rows["leaf_t"]), soil_r_lib=np.stack(soil_rows["soil_r"]),
+        I_dr0_lib=np.stack(sky_rows["I_dr0_all"]), I_df0_lib=np.stack(sky_rows["I_df0_all"]),
+        lai_idx=i_lai, leaf_idx=i_leaf, soil_idx=i_soil, sky_idx=i_sky, leaf_angle=la, mla=float(p["mla"]),
+        wl=p["wl"], dwl=p["dwl"],
+    )
+    flat = m0.run_batch(batch, bands=bands, profiles=profiles)
+    res = {k: v.reshape(tuple(sizes) + v.shape[1:]) for k, v in flat.items()}
+    res["dims"] = keys
+    return res

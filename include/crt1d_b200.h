@@ -32,6 +32,13 @@ extern "C" {
 
 #define CRT1D_ABI_VERSION 1
 
+/* exported-symbol marker (the library is built with -fvisibility=hidden) */
+#if defined(__GNUC__)
+#define CRT1D_API __attribute__((visibility("default")))
+#else
+#define CRT1D_API
+#endif
+
 /* error codes */
 #define CRT1D_OK 0
 #define CRT1D_ERR_INVALID_ARG (-1)   /* bad scheme id / family id / size */
@@ -124,25 +131,25 @@ typedef struct crt1d_out {
 } crt1d_out;
 
 /* ---- library info ---------------------------------------------------------------------------- */
-int crt1d_abi_version(void);
-const char* crt1d_strerror(int code);
-const char* crt1d_last_error(void);
-int crt1d_device_count(int* n_devices); /* CRT1D_ERR_NO_DEVICE if none */
+CRT1D_API int crt1d_abi_version(void);
+CRT1D_API const char* crt1d_strerror(int code);
+CRT1D_API const char* crt1d_last_error(void);
+CRT1D_API int crt1d_device_count(int* n_devices); /* CRT1D_ERR_NO_DEVICE if none */
 
 /* ---- solvers: device pointers, asynchronous on `stream` ------------------------------------- */
-int crt1d_solve(int scheme, const crt1d_batch* in, const crt1d_out* out, void* stream);
+CRT1D_API int crt1d_solve(int scheme, const crt1d_batch* in, const crt1d_out* out, void* stream);
 /* one named entry per reference solver function (thin aliases of crt1d_solve) */
-int crt1d_solve_2s(const crt1d_batch* in, const crt1d_out* out, void* stream);  /* replaces solve_2s  _solve_2s.py:11  */
-int crt1d_solve_4s(const crt1d_batch* in, const crt1d_out* out, void* stream);  /* replaces solve_4s  _solve_4s.py:8   */
-int crt1d_solve_bf(const crt1d_batch* in, const crt1d_out* out, void* stream);  /* replaces solve_bf  _solve_bf.py:7   */
-int crt1d_solve_bl(const crt1d_batch* in, const crt1d_out* out, void* stream);  /* replaces solve_bl  _solve_bl.py:9   */
-int crt1d_solve_g77(const crt1d_batch* in, const crt1d_out* out, void* stream); /* replaces solve_g77 _solve_g77.py:7  */
-int crt1d_solve_n79(const crt1d_batch* in, const crt1d_out* out, void* stream); /* replaces solve_n79 _solve_n79.py:11 */
-int crt1d_solve_zq(const crt1d_batch* in, const crt1d_out* out, void* stream);  /* replaces solve_zq  _solve_zq.py:13  */
+CRT1D_API int crt1d_solve_2s(const crt1d_batch* in, const crt1d_out* out, void* stream);  /* replaces solve_2s  _solve_2s.py:11  */
+CRT1D_API int crt1d_solve_4s(const crt1d_batch* in, const crt1d_out* out, void* stream);  /* replaces solve_4s  _solve_4s.py:8   */
+CRT1D_API int crt1d_solve_bf(const crt1d_batch* in, const crt1d_out* out, void* stream);  /* replaces solve_bf  _solve_bf.py:7   */
+CRT1D_API int crt1d_solve_bl(const crt1d_batch* in, const crt1d_out* out, void* stream);  /* replaces solve_bl  _solve_bl.py:9   */
+CRT1D_API int crt1d_solve_g77(const crt1d_batch* in, const crt1d_out* out, void* stream); /* replaces solve_g77 _solve_g77.py:7  */
+CRT1D_API int crt1d_solve_n79(const crt1d_batch* in, const crt1d_out* out, void* stream); /* replaces solve_n79 _solve_n79.py:11 */
+CRT1D_API int crt1d_solve_zq(const crt1d_batch* in, const crt1d_out* out, void* stream);  /* replaces solve_zq  _solve_zq.py:13  */
 
 /* ---- solver: host pointers, synchronous (H2D + kernels + D2H inside) ------------------------- */
-int crt1d_solve_host(int scheme, const crt1d_batch* in_host, const crt1d_out* out_host, int device);
-int crt1d_release_workspace(void); /* frees the calling thread's cached device workspace */
+CRT1D_API int crt1d_solve_host(int scheme, const crt1d_batch* in_host, const crt1d_out* out_host, int device);
+CRT1D_API int crt1d_release_workspace(void); /* frees the calling thread's cached device workspace */
 
 /* ---- layer absorption  (replaces _calc_absorption, crt1d/model.py:573-647) -------------------
  * Inputs: profiles [S][n_z][n_wl], K_b [S], lai/leaf libraries + indices as in crt1d_batch.
@@ -157,21 +164,21 @@ typedef struct crt1d_absorption_out {
     double* aI_df_sl;
     double* aI_df_sh;
 } crt1d_absorption_out;
-int crt1d_calc_absorption(const crt1d_batch* in, const double* I_dr, const double* I_df_d,
+CRT1D_API int crt1d_calc_absorption(const crt1d_batch* in, const double* I_dr, const double* I_df_d,
                           const double* I_df_u, const crt1d_absorption_out* out, void* stream);
 
 /* ---- leaf-angle kernels (device pointers, asynchronous) -------------------------------------
  * G(psi) and K_b = G/cos(psi) for n angles         (replaces leaf_angle.G_*, model.py:291)       */
-int crt1d_leaf_G(int family, double param, int64_t n, const double* psi, double* G, double* K_b,
+CRT1D_API int crt1d_leaf_G(int family, double param, int64_t n, const double* psi, double* G, double* K_b,
                  void* stream);
 /* tau_d(L) = 2 int_0^{pi/2} exp(-K_b(psi) L) sin cos dpsi  for n LAI values
  * (replaces common.tau_df_fn, crt1d/solvers/common.py:30-87).  n_quad > 0: Gauss-Legendre with n_quad
  * nodes (<= 128); n_quad == 0: the reference's 9-sector "9sky" rule.                              */
-int crt1d_tau_d(int family, double param, int n_quad, int64_t n, const double* L, double* tau_d,
+CRT1D_API int crt1d_tau_d(int family, double param, int n_quad, int64_t n, const double* L, double* tau_d,
                 void* stream);
 /* scalars that depend on the leaf-angle family only: out[0] = mu_bar (2s), out[1], out[2] = G sector
  * integrals for `mu_s` (4s); Gauss-Legendre with n_quad nodes.  `out` is a DEVICE pointer to 3 doubles. */
-int crt1d_leaf_integrals(int family, double param, double mu_s, int n_quad, double* out, void* stream);
+CRT1D_API int crt1d_leaf_integrals(int family, double param, double mu_s, int n_quad, double* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.dirname(__file__)):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def default_p():
+    """Default case parameters as Model._check_inputs leaves them (with K_b_fn, G, K_b)."""
+    import numpy as np
+
+    from crt1d_b200 import cases
+
+    p = cases.load_default_case(60)
+    G_fn = p["G_fn"]
+    p["K_b_fn"] = lambda psi_: G_fn(psi_) / np.cos(psi_)
+    p["G"] = G_fn(p["psi"])
+    p["K_b"] = p["K_b_fn"](p["psi"])
+    return p

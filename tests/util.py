@@ -1,0 +1,63 @@
+"""Shared helpers of the test suite."""
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# fp64 parity bar of BASELINE.json / SURVEY.md section 8d: max rel err <= 1e-10 on every returned array
+RTOL = 1e-10
+# 4s two-oracle rule: <= 1e-9 vs the tight-tolerance reference,
+# <= 2e-4 relative or 1e-7 W m-2 absolute vs the as-shipped (tol = 1e-6) reference
+RTOL_4S_TIGHT = 1e-9
+RTOL_4S_SHIPPED = 2e-4
+ATOL_4S_SHIPPED = 1e-7
+
+
+def golden(name):
+    with np.load(os.path.join(GOLDEN, name), allow_pickle=False) as f:
+        return {k: f[k] for k in f.files}
+
+
+def relerr(x, ref):
+    """max |x - ref| / max(|ref|, tiny), element-wise (cfg 2)."""
+    x, ref = np.asarray(x, dtype=float), np.asarray(ref, dtype=float)
+    assert x.shape == ref.shape, (x.shape, ref.shape)
+    if x.size == 0:
+        return 0.0
+    return float(np.max(np.abs(x - ref) / np.maximum(np.abs(ref), 1e-300)))
+
+
+def assert_close(x, ref, rtol, what="", atol=0.0):
+    x, ref = np.asarray(x, dtype=float), np.asarray(ref, dtype=float)
+    assert x.shape == ref.shape, (what, x.shape, ref.shape)
+    assert np.all(np.isfinite(x)) or not np.all(np.isfinite(ref)), f"{what}: non-finite values"
+    err = np.abs(x - ref)
+    ok = err <= np.maximum(rtol * np.abs(ref), atol)
+    if not np.all(ok):
+        i = np.unravel_index(np.argmax(err / np.maximum(np.abs(ref), 1e-300)), err.shape)
+        raise AssertionError(f"{what}: max rel err {relerr(x, ref):.3e} > {rtol:g} at {i}: got {x[i]!r}, ref {ref[i]!r}")
+
+
+def with_callables(p):
+    """Add K_b_fn / G / K_b to a case dict, as Model._check_inputs does (ref model.py:291-293)."""
+    q = dict(p)
+    G_fn = q["G_fn"]
+    q["K_b_fn"] = lambda psi_: G_fn(psi_) / np.cos(psi_)
+    q["G"] = G_fn(q["psi"])
+    q["K_b"] = q["K_b_fn"](q["psi"])
+    return q
+
+
+def variant_case(nz, sza_deg):
+    """The inputs of a `ref_variants.npz` entry: default case at nz levels, sza, every 9th band."""
+    from crt1d_b200 import cases
+
+    q = dict(cases.load_default_case(nz))
+    q["psi"] = np.deg2rad(sza_deg)
+    for k in ("leaf_t", "leaf_r", "soil_r", "I_dr0_all", "I_df0_all", "wl", "dwl", "wl_leafsoil"):
+        q[k] = q[k][::9].copy()
+    return with_callables(q)
+
+
+VARIANTS = [(2, 20), (3, 20), (10, 60), (200, 20), (60, 0), (60, 60), (60, 85)]
