@@ -209,7 +209,7 @@ static int make_rule(int n_quad, crt::QuadRule* rule) {
     if (n_quad < 0 || n_quad > 128) return fail(CRT1D_ERR_INVALID_ARG, "n_quad must be in 0..128");
     memset(rule, 0, sizeof(*rule));
     rule->n = n_quad;
-    rule->panels = 6;
+    rule->panels = 12;  // 12 graded panels x n_quad nodes: ~1e-16 abs error down to L = 0.004
     if (n_quad > 0) crt::gauss_legendre(n_quad, rule->x, rule->w);
     return CRT1D_OK;
 }

@@ -21,7 +21,7 @@ EXTRA_NAMES = {
     "n79": ("aI_lsl", "aI_lsh"),
 }
 MAIN_NAMES = ("I_dr", "I_df_d", "I_df_u", "F")
-DEFAULT_N_QUAD = 64  # Gauss-Legendre nodes per panel for the device-side prologue integrals
+DEFAULT_N_QUAD = 32  # Gauss-Legendre nodes per panel (12 graded panels) for the device-side prologue integrals
 
 
 BATCH_ARRAYS = ("psi", "lai_lib", "leaf_r_lib", "leaf_t_lib", "soil_r_lib", "I_dr0_lib", "I_df0_lib",

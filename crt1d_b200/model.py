@@ -144,6 +144,7 @@ class Model:
                     "Provided `mu` not consistent with provided `psi`. "
                     "`mu` will be updated based on the value of `psi`."
                 )
+                p["mu"] = np.cos(psi)  # (the reference warns but leaves the stale value, ref model.py:258-267)
         else:
             p["mu"] = np.cos(psi)
         wl_toc, wl_op = np.asarray(p["wl"]), np.asarray(p["wl_leafsoil"])

@@ -47,7 +47,7 @@ class ScenarioBatch:
             setattr(self, k, _rows(getattr(self, k), k))
         S = self.psi.size
         for k in ("lai_idx", "leaf_idx", "soil_idx", "sky_idx"):
-            v = np.ascontiguousarray(np.broadcast_to(np.asarray(getattr(self, k), dtype=np.int32), (S,)))
+            v = np.array(np.broadcast_to(np.asarray(getattr(self, k), dtype=np.int32), (S,)), dtype=np.int32, order="C")
             setattr(self, k, v)
         n_wl = self.leaf_r_lib.shape[1]
         for k in ("leaf_t_lib", "soil_r_lib", "I_dr0_lib", "I_df0_lib"):

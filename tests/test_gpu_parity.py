@@ -10,6 +10,7 @@ from util import RTOL_4S_SHIPPED
 from util import RTOL_4S_TIGHT
 from util import VARIANTS
 from util import assert_close
+from util import assert_close_4s
 from util import golden
 from util import variant_case
 
@@ -70,7 +71,7 @@ def test_4s_two_oracle_rule(default_p, mu_s, tag):
     tight = golden(f"ref_default_{tag}_tight.npz")
     shipped = golden(f"ref_default_{tag}.npz")
     for k in tight:
-        assert_close(sol[k], tight[k], RTOL_4S_TIGHT, f"4s[tight,{mu_s}].{k}")
+        assert_close_4s(sol[k], tight[k], f"4s[tight,{mu_s}].{k}")
         assert_close(sol[k], shipped[k], RTOL_4S_SHIPPED, f"4s[shipped,{mu_s}].{k}", atol=ATOL_4S_SHIPPED)
 
 
@@ -94,8 +95,10 @@ def test_variants_match_reference_golden(nz, sza):
         sol = crt.solvers.AVAILABLE_SCHEMES[name]["solver"](**_args(name, q))
         for full in keys:
             k = full.split("__")[-1]
-            rtol = RTOL_4S_TIGHT if scheme == "4s_tight" else RTOL
-            assert_close(sol[k], g[full], rtol, f"{tag} {scheme}.{k}")
+            if scheme == "4s_tight":
+                assert_close_4s(sol[k], g[full], f"{tag} {scheme}.{k}")
+            else:
+                assert_close(sol[k], g[full], RTOL, f"{tag} {scheme}.{k}")
 
 
 def test_bonan_sp1403_known_answer():
@@ -173,8 +176,7 @@ def test_batched_sweep_sample_matches_reference_golden():
     torch.cuda.synchronize()
     for n in (1, 4):
         for k in ("I_dr", "I_df_d", "I_df_u", "F"):
-            assert_close(res4[k][n].cpu().numpy()[:, ::step], g[f"s{n}__4s_tight__{k}"], RTOL_4S_TIGHT,
-                         f"sweep[{idx[n]}] 4s.{k}")
+            assert_close_4s(res4[k][n].cpu().numpy()[:, ::step], g[f"s{n}__4s_tight__{k}"], f"sweep[{idx[n]}] 4s.{k}")
 
 
 @pytest.mark.parametrize("scheme", FAST + ("4s",))
@@ -199,10 +201,11 @@ def test_batched_equals_plugin_path(scheme, default_p):
         I_dr0_lib=default_p["I_dr0_all"], I_df0_lib=default_p["I_df0_all"], lai_idx=[0, 1, 1, 0], leaf_idx=[0, 1, 2, 1],
         soil_idx=[0, 1, 0, 1], sky_idx=[0, 0, 0, 0], leaf_angle=la, mla=57.0, wl=default_p["wl"], dwl=default_p["dwl"],
     )
-    res = engine.solve(b, scheme, n_quad=128)
+    res = engine.solve(b, scheme)
     torch.cuda.synchronize()
-    # device Gauss-Legendre vs host QUADPACK prologue: tau_d carries quad's own ~1e-9 abs error
-    rtol = {"2s": RTOL, "4s": 1e-9, "bf": RTOL, "g77": RTOL}.get(scheme, 2e-7)
+    # device Gauss-Legendre vs host QUADPACK prologue: tau_d from quad(epsrel=1e-9) is only good to ~5e-12
+    # absolute, which the tridiagonal solves amplify (cond ~1e2..4e3): 1e-8 for the tau_d-dependent schemes
+    rtol = {"2s": RTOL, "4s": 1e-9, "bf": RTOL, "g77": RTOL}.get(scheme, 1e-8)
     for s in range(b.n_scen):
         q = b.scenario_params(s)
         sol = crt.solvers.AVAILABLE_SCHEMES[scheme]["solver"](**{k: q[k] for k in crt.solvers.AVAILABLE_SCHEMES[scheme]["args"]})
@@ -266,14 +269,14 @@ def test_leaf_angle_kernels_match_host():
     L = np.array([0.004, 0.0678, 0.5, 2.0, 6.0])
     L_d = torch.as_tensor(L).cuda()
     td = torch.empty_like(L_d)
-    _lib.check(lib.crt1d_tau_d(la.family_id, la.param, 64, L.size, L_d.data_ptr(), td.data_ptr(), None))
+    _lib.check(lib.crt1d_tau_d(la.family_id, la.param, 32, L.size, L_d.data_ptr(), td.data_ptr(), None))
     torch.cuda.synchronize()
-    assert_close(td.cpu().numpy(), common.tau_df_fn(la.K_b_fn, L), 1e-8, "tau_d GL vs quad(epsrel=1e-9)")
+    assert_close(td.cpu().numpy(), common.tau_df_fn(la.K_b_fn, L), 1e-10, "tau_d GL vs quad(epsrel=1e-9)")
     _lib.check(lib.crt1d_tau_d(la.family_id, la.param, 0, L.size, L_d.data_ptr(), td.data_ptr(), None))
     torch.cuda.synchronize()
     assert_close(td.cpu().numpy(), common.tau_df_fn(la.K_b_fn, L, method="9sky"), 1e-13, "tau_d 9sky")
     tri = torch.empty(3, dtype=torch.float64, device="cuda")
-    _lib.check(lib.crt1d_leaf_integrals(la.family_id, la.param, 0.501, 64, tri.data_ptr(), None))
+    _lib.check(lib.crt1d_leaf_integrals(la.family_id, la.param, 0.501, 32, tri.data_ptr(), None))
     torch.cuda.synchronize()
     g1, g2 = common.G_sector_integrals(la.G_fn, 0.501)
     assert_close(tri.cpu().numpy(), np.array([common.mu_bar_fn(la.G_fn), g1, g2]), 1e-12, "mu_bar, G sector integrals")

@@ -1,0 +1,142 @@
+"""Host-side logic that needs no GPU: the scheme registry, Model parameter handling, ScenarioBatch
+validation, the synthetic sweep definition, sensitivity cross-product construction."""
+import inspect
+import warnings
+
+import numpy as np
+import pytest
+
+import crt1d_b200 as crt
+from crt1d_b200.scenarios import ScenarioBatch
+
+REF_SIGNATURES = {  # ref crt1d/solvers/_solve_<id>.py
+    "2s": (["psi", "I_dr0_all", "I_df0_all", "lai", "leaf_t", "leaf_r", "soil_r", "K_b_fn", "G_fn", "mla"], []),
+    "4s": (["psi", "I_dr0_all", "I_df0_all", "lai", "leaf_t", "leaf_r", "soil_r", "K_b_fn", "G_fn"], ["mu_s"]),
+    "zq": (["psi", "I_dr0_all", "I_df0_all", "lai", "leaf_t", "leaf_r", "soil_r", "K_b_fn", "G_fn"], []),
+    "bl": (["psi", "I_dr0_all", "I_df0_all", "lai", "leaf_t", "leaf_r", "K_b_fn"], []),
+    "bf": (["psi", "I_dr0_all", "I_df0_all", "lai", "leaf_t", "leaf_r", "soil_r", "K_b_fn"], []),
+    "g77": (["psi", "I_dr0_all", "I_df0_all", "lai", "leaf_t", "leaf_r", "soil_r", "K_b_fn"], []),
+    "n79": (["psi", "I_dr0_all", "I_df0_all", "lai", "leaf_t", "leaf_r", "soil_r", "K_b_fn"], ["tau_d_method"]),
+}
+
+
+def test_registry_has_reference_structure():
+    S = crt.solvers
+    assert set(S.AVAILABLE_SCHEMES) == set(REF_SIGNATURES)
+    assert S.RET_KEYS_ALL_SCHEMES == ["I_dr", "I_df_d", "I_df_u", "F"]
+    assert S.CANOPY_RAD_STATE_INPUT_KEYS == ["psi", "I_dr0_all", "I_df0_all", "lai", "clump", "leaf_t", "leaf_r",
+                                             "soil_r", "K_b", "K_b_fn", "G", "G_fn", "mla"]
+    for name, (args, options) in REF_SIGNATURES.items():
+        d = S.AVAILABLE_SCHEMES[name]
+        assert set(d) == {"module_name", "name", "short_name", "long_name", "solver", "args", "options"}
+        assert d["name"] == name and d["module_name"] == f"_solve_{name}"
+        assert d["args"] == args and d["options"] == options
+        assert d["solver"] is getattr(S, f"solve_{name}")
+        spec = inspect.getfullargspec(d["solver"])
+        assert spec.args == [] and spec.varargs is None  # keyword-only, as the reference requires
+        assert d["long_name"]
+    assert S.AVAILABLE_SCHEMES["4s"]["solver"].__kwdefaults__ == {"mu_s": 0.501}
+    assert S.AVAILABLE_SCHEMES["n79"]["solver"].__kwdefaults__ == {"tau_d_method": "quad"}
+
+
+def test_register_into_foreign_registry():
+    target = {"2s": {"name": "2s"}}
+    added = crt.solvers.register_cuda_schemes(target)
+    assert "2s_cuda" in target and target["2s"] == {"name": "2s"} and len(added) == 7
+    assert target["zq_cuda"]["solver"] is crt.solvers.solve_zq and target["zq_cuda"]["name"] == "zq_cuda"
+    with pytest.raises(KeyError):
+        crt.solvers.register_cuda_schemes(target)
+    crt.solvers.register_cuda_schemes(target, suffix="", overwrite=True)
+    assert target["2s"]["solver"] is crt.solvers.solve_2s
+
+
+def test_model_parameter_handling():
+    m = crt.Model("4s", nlayers=20)
+    assert m.nlev == 20 and m.nwl == 107 and m.scheme["name"] == "4s"
+    p = m.copy_p()
+    assert p["lai"][0] == 4.0 and p["lai"][-1] == 0 and np.isclose(p["K_b"], p["G"] / np.cos(p["psi"]))
+    assert p["wle"].size == 108 and p["dlai"].size == 19
+    m.update_p(psi=0.5)
+    assert m._p["psi"] == 0.5 and np.isclose(m._p["K_b"], m._p["G_fn"](0.5) / np.cos(0.5))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m.update_p(not_a_param=1)
+        assert any("not intended as an input" in str(x.message) for x in w)
+        m.update_p(lai=np.array([1.0, 2.0, 3.0]))  # wrong size / increasing: reverted with a warning
+        assert any("Reverting" in str(x.message) for x in w)
+    assert m._p["lai"].size == 20
+    assert crt.Model("nope").scheme["name"] == "2s"  # falls back like the reference
+    assert "Model(scheme='4s'" in repr(m)
+    with pytest.raises(Exception):
+        m.calc_absorption()
+
+
+def test_scenario_batch_validation(default_p):
+    b = ScenarioBatch.from_params(default_p)
+    assert (b.n_scen, b.n_z, b.n_wl) == (1, 60, 107)
+    q = b.scenario_params(0)
+    assert np.array_equal(q["lai"], default_p["lai"]) and q["psi"] == default_p["psi"]
+    kw = dict(psi=[0.1, 0.2], lai_lib=default_p["lai"], leaf_r_lib=default_p["leaf_r"], leaf_t_lib=default_p["leaf_t"],
+              soil_r_lib=default_p["soil_r"], I_dr0_lib=default_p["I_dr0_all"], I_df0_lib=default_p["I_df0_all"],
+              lai_idx=0, leaf_idx=0, soil_idx=0, sky_idx=0)
+    assert ScenarioBatch(**kw).lai_idx.tolist() == [0, 0]
+    with pytest.raises(IndexError):
+        ScenarioBatch(**{**kw, "leaf_idx": [0, 1]})
+    with pytest.raises(ValueError):
+        ScenarioBatch(**{**kw, "soil_r_lib": default_p["soil_r"][:50]})
+    with pytest.raises(AssertionError):
+        ScenarioBatch(**{**kw, "lai_lib": default_p["lai"][::-1]})
+    with pytest.raises(ValueError):
+        crt.LeafAngle("conical", 1.0)
+
+
+def test_synthetic_sweep_definition():
+    from crt1d_b200 import sweep
+
+    a = sweep.synthetic_sweep_spec(seed=0)
+    b = sweep.synthetic_sweep_spec(seed=0)
+    assert (a.n_scen, a.n_z, a.n_wl) == (1_000_000, 60, 2100)
+    for k in ("psi", "lai_idx", "leaf_idx", "leaf_r_lib", "I_dr0_lib"):
+        assert np.array_equal(getattr(a, k), getattr(b, k))
+    assert not np.array_equal(a.leaf_r_lib, sweep.synthetic_sweep_spec(seed=1).leaf_r_lib)
+    s = (37 * 100 + 58) * 100 + 91  # scenario index = ((i_sza * 100) + i_lai) * 100 + i_spec
+    assert np.isclose(a.psi[s], np.radians(np.linspace(0, 85, 100))[37])
+    assert a.lai_idx[s] == 58 and a.leaf_idx[s] == a.soil_idx[s] == a.sky_idx[s] == 91
+    assert np.isclose(a.lai_lib[58, 0], np.linspace(0.5, 8, 100)[58]) and np.all(a.lai_lib[:, -1] == 0)
+    assert (a.leaf_r_lib + a.leaf_t_lib).max() <= 0.98 + 1e-12 and a.leaf_r_lib.min() >= 1e-4 * 0.9
+    assert np.all(a.I_dr0_lib > 0) and np.all(a.I_df0_lib > 0)
+    assert np.isclose(a.wl[0], 0.4005) and np.isclose(a.wl[-1], 2.4995) and np.allclose(a.dwl, 0.001)
+    sub = a.slice(10, 20)
+    assert sub.n_scen == 10 and sub.lai_lib is a.lai_lib and sub.psi[0] == a.psi[10]
+
+
+def test_sensitivity_requires_parametric_leaf_angle():
+    m = crt.Model("2s", nlayers=10)
+    with pytest.raises(KeyError):
+        crt.run_sensitivity(m, {"z": [1, 2]})
+    m.update_p(G_fn=lambda psi: 0.5)  # an arbitrary callable cannot run inside a kernel
+    assert "leaf_angle" not in m._p
+    with pytest.raises(ValueError):
+        crt.run_sensitivity(m, {"psi": [0.1, 0.2]})
+    with pytest.raises(ValueError):
+        m.scenario_batch()
+
+
+def test_host_prologue_uses_reference_quadratures(default_p):
+    """The plugin path evaluates the Python callables with the same scipy calls as the reference."""
+    import crt_oracle as oracle
+    from crt1d_b200.engine import host_prologue
+
+    b = ScenarioBatch.from_params(default_p)
+    K, Gf = default_p["K_b_fn"], default_p["G_fn"]
+    assert host_prologue(b, "2s", K_b_fn=K, G_fn=Gf)["mu_bar"][0] == oracle.mu_bar_quad(Gf)
+    assert tuple(host_prologue(b, "4s", K_b_fn=K, G_fn=Gf, mu_s=0.4)["G_int"][0]) == oracle.G_sector_integrals(Gf, 0.4)
+    ti, tp = oracle.zq_layer_scalars(default_p["psi"], default_p["lai"], K)
+    pz = host_prologue(b, "zq", K_b_fn=K, G_fn=Gf)
+    assert pz["tau_i"][0] == ti and pz["tau_psi"][0] == tp
+    lai = default_p["lai"]
+    assert np.array_equal(host_prologue(b, "bl", K_b_fn=K)["tau_d_lev"][0], np.array([oracle.tau_df_fn(K, L) for L in lai]))
+    td = host_prologue(b, "n79", K_b_fn=K, tau_d_method="9sky")["tau_d_lev"][0]
+    assert np.array_equal(td[:-1], oracle.tau_df_fn(K, lai[:-1] - lai[1:], method="9sky")) and td[-1] == 0
+    with pytest.raises(ValueError):
+        host_prologue(b, "n79", K_b_fn=K, tau_d_method="nope")

@@ -1,0 +1,132 @@
+"""CPU tier: the arithmetic the CUDA kernels execute (crt1d_b200/csrc/*.cuh, compiled for the host by
+tests/_hostcheck) vs the oracle and the reference-generated goldens.  Catches math regressions in the
+kernels in a container without a GPU; the real parity tests are tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import crt_oracle as oracle
+import hostcheck
+from crt1d_b200.engine import host_prologue
+from crt1d_b200.scenarios import ScenarioBatch
+from util import RTOL
+from util import RTOL_4S_TIGHT
+from util import VARIANTS
+from util import assert_close
+from util import assert_close_4s
+from util import golden
+from util import variant_case
+
+SCHEMES = ("2s", "bf", "bl", "g77", "n79", "zq")
+
+
+def _solve(p, scheme, vec=None, **kw):
+    batch = ScenarioBatch.from_params(p)
+    pro = host_prologue(batch, scheme, K_b_fn=p["K_b_fn"], G_fn=p["G_fn"], **kw)
+    out = hostcheck.solve(batch, scheme, pro, vec=vec, mu_s=kw.get("mu_s", 0.501))
+    sol = {k: v[0] for k, v in out.items()}
+    if "rho_c" in sol:
+        sol["rho_c"] = sol["rho_c"][-1]
+    return sol
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_kernel_math_default_case(scheme, default_p):
+    ref = golden(f"ref_default_{scheme}.npz")
+    sol = _solve(default_p, scheme, vec=1)
+    for k in ref:
+        assert_close(sol[k], ref[k], RTOL, f"{scheme}.{k}")
+
+
+@pytest.mark.parametrize("scheme", SCHEMES + ("4s",))
+def test_vec2_equals_vec1(scheme, default_p):
+    """The 2-bands-per-thread instantiation computes the same columns (even band count needed)."""
+    sub = {k: (v[:106].copy() if isinstance(v, np.ndarray) and v.shape == (107,) else v) for k, v in default_p.items()}
+    a = _solve(sub, scheme, vec=1)
+    b = _solve(sub, scheme, vec=2)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), (scheme, k)
+
+
+def test_kernel_math_4s(default_p):
+    for mu_s, tag in ((0.501, "4s"), (0.33998, "4s_mus034")):
+        ref = golden(f"ref_default_{tag}_tight.npz")
+        sol = _solve(default_p, "4s", vec=1, mu_s=mu_s)
+        for k in ref:
+            assert_close_4s(sol[k], ref[k], f"4s[{mu_s}].{k}")
+
+
+@pytest.mark.parametrize("nz,sza", VARIANTS)
+def test_kernel_math_variants(nz, sza):
+    g = golden("ref_variants.npz")
+    q = variant_case(nz, sza)
+    tag = f"nz{nz}_sza{sza}"
+    for scheme in SCHEMES + ("4s_tight",):
+        name = "4s" if scheme == "4s_tight" else scheme
+        keys = [k for k in g if k.startswith(f"{tag}__{scheme}__") and not k.endswith("__raises")]
+        if not keys:
+            continue
+        sol = _solve(q, name)
+        for full in keys:
+            k = full.split("__")[-1]
+            if name == "4s":
+                assert_close_4s(sol[k], g[full], f"{tag} {scheme}.{k}")
+            else:
+                assert_close(sol[k], g[full], RTOL, f"{tag} {scheme}.{k}")
+
+
+def test_kernel_math_multi_scenario_indexing(default_p):
+    """Library/index plumbing: scenarios pick different rows; each must equal its own single solve."""
+    rng = np.random.default_rng(3)
+    nz = 12
+    lai_lib = np.stack([np.linspace(1, 0, nz) * 2.0, np.linspace(1, 0, nz) ** 2 * 6.0])
+    sc = rng.uniform(0.7, 1.1, (3, 1))
+    b = ScenarioBatch(
+        psi=np.radians([5.0, 40.0, 70.0, 84.0, 20.0]), lai_lib=lai_lib, leaf_r_lib=default_p["leaf_r"] * sc,
+        leaf_t_lib=default_p["leaf_t"] * sc[::-1], soil_r_lib=np.stack([default_p["soil_r"], default_p["soil_r"] * 2]),
+        I_dr0_lib=np.stack([default_p["I_dr0_all"], default_p["I_dr0_all"] * 0.3]),
+        I_df0_lib=np.stack([default_p["I_df0_all"], default_p["I_df0_all"] * 1.9]),
+        lai_idx=[0, 1, 1, 0, 1], leaf_idx=[0, 1, 2, 1, 0], soil_idx=[0, 1, 0, 1, 1], sky_idx=[0, 0, 1, 1, 0],
+        leaf_angle=default_p["leaf_angle"], mla=57.0, wl=default_p["wl"], dwl=default_p["dwl"],
+    )
+    for scheme in SCHEMES + ("4s",):
+        pro = host_prologue(b, scheme)
+        out = hostcheck.solve(b, scheme, pro, band_w=np.ones((2, b.n_wl)))
+        for s in range(b.n_scen):
+            q = b.scenario_params(s)
+            ref = (oracle.solve_4s_tight if scheme == "4s" else oracle.SOLVERS[scheme])(**{k: q[k] for k in oracle.ARGS[scheme]})
+            for k in ("I_dr", "I_df_d", "I_df_u", "F"):
+                if scheme == "4s":
+                    assert_close_4s(out[k][s], ref[k], f"{scheme}[{s}].{k}")
+                else:
+                    assert_close(out[k][s], ref[k], RTOL, f"{scheme}[{s}].{k}")
+            ab = oracle.calc_absorption(lai=q["lai"], K_b=q["K_b"], leaf_r=q["leaf_r"], leaf_t=q["leaf_t"],
+                                        I_dr=ref["I_dr"], I_df_d=ref["I_df_d"], I_df_u=ref["I_df_u"])
+            assert_close(out["absorbed"][s, 0], ab["aI"].sum(), 1e-9, f"{scheme}[{s}] absorbed")
+
+
+def test_leaf_angle_device_functions():
+    from crt1d_b200.leaf_angle import LeafAngle
+    from crt1d_b200.solvers import common
+
+    L = hostcheck.lib()
+    psi = np.radians(np.linspace(0, 89.5, 180))
+    for fam, par in (("spherical", 0), ("horizontal", 0), ("vertical", 0), ("ellipsoidal_approx", 0.9632),
+                     ("ellipsoidal", 2.5), ("ellipsoidal", 0.5), ("ellipsoidal", 1.0), ("ellipsoidal_approx_bonan", 0.25),
+                     ("ellipsoidal_approx_bonan", 0.9)):
+        la = LeafAngle(fam, par)
+        got = np.array([L.hostcheck_leaf_G(la.family_id, la.param, a) for a in psi])
+        assert_close(got, la.G_fn(psi) * np.ones_like(psi), 1e-14, f"G {fam}")
+    la = LeafAngle("ellipsoidal_approx", 0.9632)
+    # Device rule: Gauss-Legendre, 32 nodes x 12 panels graded towards psi = pi/2.  It self-converges to
+    # ~1e-16; QUADPACK(epsrel=1e-9), which the reference uses, is itself within ~5e-12 of that.
+    for Lv in (0.004, 0.0678, 0.5, 2.0, 6.0, 10.0):
+        got = L.hostcheck_tau_d(la.family_id, la.param, 32, 12, Lv)
+        assert abs(got - common.tau_df_fn(la.K_b_fn, Lv)) < 2e-11, Lv
+        assert abs(got - L.hostcheck_tau_d(la.family_id, la.param, 64, 12, Lv)) < 2e-15, Lv
+        assert abs(got - L.hostcheck_tau_d(la.family_id, la.param, 128, 12, Lv)) < 2e-15, Lv
+        assert_close(L.hostcheck_tau_d(la.family_id, la.param, 0, 1, Lv), common.tau_df_fn(la.K_b_fn, Lv, method="9sky"),
+                     1e-14, "9sky")
+    g1, g2 = common.G_sector_integrals(la.G_fn, 0.501)
+    assert abs(L.hostcheck_leaf_integral(la.family_id, la.param, 0.501, 32, 0) - common.mu_bar_fn(la.G_fn)) < 1e-13
+    assert abs(L.hostcheck_leaf_integral(la.family_id, la.param, 0.501, 32, 1) - g1) < 1e-13
+    assert abs(L.hostcheck_leaf_integral(la.family_id, la.param, 0.501, 32, 2) - g2) < 1e-13
