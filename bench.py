@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scheme", default="2s")
     ap.add_argument("--scenarios", type=int, default=1_000_000, help="scenarios per GPU (cross product is truncated)")
-    ap.add_argument("--chunk", type=int, default=4096, help="scenarios per kernel launch")
+    ap.add_argument("--chunk", type=int, default=4144, help="scenarios per kernel launch")
     ap.add_argument("--cpu-sample", type=int, default=0, help="scenarios in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -5,7 +5,8 @@ import os
 
 from . import _abi
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcrt1d_b200.so")
+# CRT1D_B200_LIB selects a tuning variant built by `build.build(defines=..., out=...)` (benchmarks only)
+LIB_PATH = os.environ.get("CRT1D_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcrt1d_b200.so")
 _lib = None
 
 

@@ -40,20 +40,23 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile the shared library; returns its path.  Raises on failure (no fallback)."""
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile the shared library; returns its path.  Raises on failure (no fallback).
+    `defines` / `out` build tuning variants (e.g. ("CRT_BLOCK=256",)) next to the default library."""
+    out = out or LIB_PATH
+    if not force and out == LIB_PATH and not needs_build():
         return LIB_PATH
-    cmd = [nvcc_path()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH + ".tmp"]
+    cmd = [nvcc_path()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-o", out + ".tmp"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed building libcrt1d_b200.so (see output above)")
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
-    with open(os.path.join(PKG_DIR, "csrc", "ptxas_info.txt"), "w") as f:
+    os.replace(out + ".tmp", out)
+    with open(os.path.join(PKG_DIR, "csrc", "ptxas_info.txt" if out == LIB_PATH else os.path.basename(out) + ".ptxas.txt"), "w") as f:
         f.write(proc.stderr)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":

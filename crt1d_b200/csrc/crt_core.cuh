@@ -27,8 +27,72 @@ enum Field : int { F_IDR = 0, F_DN = 1, F_UP = 2, F_F = 3, F_X0 = 4, F_X1 = 5, F
 #define CRT_PI 3.14159265358979323846
 #endif
 
-// exp() hook: one place to swap the exponential used in the level sweeps.
-CRT_HD double exp_m(double x) { return exp(x); }
+
+// ---------------------------------------------------------------------------------------------
+// exp_pm: e^{-x} and e^{+x} for x >= 0 from ONE range reduction.
+// Every level sweep needs a decaying exponential and its reciprocal (2s: e^{-hL}, e^{+hL}; 4s:
+// e^{-lambda x}, e^{-lambda (LAI - x)} = e^{-lambda LAI} e^{+lambda x}; bf: e^{-k_d L}, e^{-k_d (L_T - L)}).
+// libm-style exp() + an IEEE division cost ~50 issue slots per pair on sm_100a (17 FP64 ops + 13
+// constant moves + range checks for exp, MUFU.RCP64H + 5 DFMA + fix-up branch for the reciprocal).
+// Here: x = n ln2 + r, |r| <= ln2/2;  e^{+-r} = cosh r +- sinh r, both even/odd Taylor polynomials in
+// r^2 (truncation < 5e-18), and 2^{+-n} applied by integer adds on the exponent field: 21 FP64 ops and
+// ~6 integer ops for BOTH values, no division, no branches on the fast path.  Max relative error
+// ~2 ulp (tests/test_hostmath.py::test_exp_pm_accuracy).  x > 700 (results beyond the normal range)
+// and NaN take the libm path.
+// ---------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define CRT_CONST __constant__
+#else
+#define CRT_CONST static const
+#endif
+// 1/(2k)! for k = 6..1 then 1/(2k+1)! for k = 6..1
+CRT_CONST double kExpPm[12] = {
+    1.0 / 479001600.0, 1.0 / 3628800.0, 1.0 / 40320.0, 1.0 / 720.0, 1.0 / 24.0, 0.5,
+    1.0 / 6227020800.0, 1.0 / 39916800.0, 1.0 / 362880.0, 1.0 / 5040.0, 1.0 / 120.0, 1.0 / 6.0};
+
+CRT_HD double scale_pow2(double v, int n) {  // v * 2^n for results that stay normal
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(v) + (n << 20), __double2loint(v));
+#else
+    return ldexp(v, n);
+#endif
+}
+
+CRT_HD void exp_pm(double x, double& em, double& ep) {
+    if (!(x <= 700.0)) {  // also catches NaN
+        em = exp(-x);
+        ep = exp(x);
+        return;
+    }
+    const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to nearest integer
+    const double nf = fma(x, 1.4426950408889634074, kMagic);
+    const double nd = nf - kMagic;
+#if defined(__CUDA_ARCH__)
+    const int n = __double2loint(nf);
+#else
+    const int n = (int)nd;
+#endif
+    double r = fma(nd, -6.93147180559945286227e-01, x);   // ln2 hi
+    r = fma(nd, -2.31904681384629955842e-17, r);          // ln2 lo
+    const double r2 = r * r;
+    double c = kExpPm[0], sn = kExpPm[6];
+#pragma unroll
+    for (int i = 1; i < 6; ++i) {
+        c = fma(c, r2, kExpPm[i]);
+        sn = fma(sn, r2, kExpPm[6 + i]);
+    }
+    c = fma(c, r2, 1.0);              // cosh r
+    sn = fma(sn * r2, r, r);          // sinh r = r + r^3 (1/6 + ...)
+    ep = scale_pow2(c + sn, n);
+    em = scale_pow2(c - sn, -n);
+}
+
+// e^{-x} for x >= 0 (the unused e^{+x} half of exp_pm is dead code the compiler drops).
+CRT_HD double exp_neg(double x) {
+    double em, ep;
+    exp_pm(x, em, ep);
+    return em;
+}
 
 // Band inputs of one column group.
 template <int VEC>
@@ -50,6 +114,7 @@ struct Scen2s {
     double K;        // K_b_fn(psi), black-leaf extinction          (ref :26, :40)
     double inv_mu;   // 1/cos(psi)
     double mu_bar;   // (ref :32)
+    double inv_mu_bar;
     double cos2_tl;  // cos^2(radians(mla))                         (ref :28, :68)
     double as_fac;   // 1 - mu log((mu+1)/mu)                       (ref :73)
     double L_T;      // total LAI = lai[0]                          (ref :38)
@@ -62,6 +127,7 @@ CRT_HD Scen2s scen_2s(double psi, double K, double mu_bar, double mla_deg, doubl
     s.K = K;
     s.inv_mu = 1.0 / mu;
     s.mu_bar = mu_bar;
+    s.inv_mu_bar = 1.0 / mu_bar;
     const double ct = cos(mla_deg * (CRT_PI / 180.0));
     s.cos2_tl = ct * ct;
     s.as_fac = 1.0 - mu * log((mu + 1.0) / mu);
@@ -76,41 +142,44 @@ struct Coef2s {
 };
 
 CRT_HD Coef2s coef_2s(const Scen2s& s, double alpha, double tau, double rho_s, double Idr0, double Idf0) {
+    // The reference divides by S1, D1, D2, sigma in a dozen places (ref :96-120); here each reciprocal is
+    // formed once (1/S1 = e^{+h L_T} falls out of exp_pm) -- same algebra, results within a few ulp.
     const double mu_bar = s.mu_bar, K = s.K;
     const double omega = alpha + tau;                                                   // ref :65
     const double beta = (0.5 * (alpha + tau + (alpha - tau) * s.cos2_tl)) / omega;      // ref :68 (eq. 3)
     const double a_s = omega / 2.0 * s.as_fac;                                          // ref :73
-    const double beta_0 = (1.0 + mu_bar * K) / (omega * mu_bar * K) * a_s;              // ref :76 (eq. 4)
+    const double mK = mu_bar * K;
+    const double beta_0 = (1.0 + mK) / (omega * mK) * a_s;                              // ref :76 (eq. 4)
     const double b = 1.0 - (1.0 - beta) * omega;                                        // ref :80-85
     const double c = omega * beta;
-    const double d = omega * mu_bar * K * beta_0;
-    const double f = omega * mu_bar * K * (1.0 - beta_0);
-    const double h = sqrt(b * b - c * c) / mu_bar;
-    const double sigma = (mu_bar * K) * (mu_bar * K) + c * c - b * b;
+    const double d = omega * mK * beta_0;
+    const double f = omega * mK * (1.0 - beta_0);
+    const double h = sqrt(b * b - c * c) * s.inv_mu_bar;
+    const double sigma = mK * mK + c * c - b * b;
     const double u1 = b - c / rho_s;                                                    // ref :87-97
     const double u2 = b - c * rho_s;
     const double u3 = f + c * rho_s;
-    const double S1 = exp(-h * s.L_T);
+    double S1, iS1;                                                                     // e^{-h L_T}, e^{+h L_T}
+    exp_pm(h * s.L_T, S1, iS1);
     const double S2 = s.S2;
-    const double mh = mu_bar * h, mK = mu_bar * K;
+    const double mh = mu_bar * h;
     const double p1 = b + mh, p2 = b - mh, p3 = b + mK, p4 = b - mK;
-    const double D1 = p1 * (u1 - mh) / S1 - p2 * (u1 + mh) * S1;
-    const double D2 = (u2 + mh) / S1 - (u2 - mh) * S1;
-    const double h1 = -d * p4 - c * f;                                                  // ref :99-120
-    const double h1s = h1 / sigma;
+    const double iD1 = 1.0 / (p1 * (u1 - mh) * iS1 - p2 * (u1 + mh) * S1);
+    const double iD2 = 1.0 / ((u2 + mh) * iS1 - (u2 - mh) * S1);
+    const double isig = 1.0 / sigma;
+    const double h1s = (-d * p4 - c * f) * isig;                                        // h1 / sigma, ref :99
     const double t1 = d - h1s * p3;
     const double t2 = d - c - h1s * (u1 + mK);
-    const double h2 = 1.0 / D1 * (t1 * (u1 - mh) / S1 - p2 * t2 * S2);
-    const double h3 = -1.0 / D1 * (t1 * (u1 + mh) * S1 - p1 * t2 * S2);
-    const double h4 = -f * p3 - c * d;  // Sellers (1996) correction
-    const double h4s = h4 / sigma;
+    const double h2 = iD1 * (t1 * (u1 - mh) * iS1 - p2 * t2 * S2);
+    const double h3 = -iD1 * (t1 * (u1 + mh) * S1 - p1 * t2 * S2);
+    const double h4s = (-f * p3 - c * d) * isig;                                        // h4 / sigma (Sellers 1996), ref :109
     const double t3 = u3 - h4s * (u2 - mK);
-    const double h5 = -1.0 / D2 * (h4s * (u2 + mh) / S1 + t3 * S2);
-    const double h6 = 1.0 / D2 * (h4s * (u2 - mh) * S1 + t3 * S2);
-    const double h7 = c / D1 * (u1 - mh) / S1;
-    const double h8 = -c / D1 * (u1 + mh) * S1;
-    const double h9 = 1.0 / D2 * (u2 + mh) / S1;
-    const double h10 = -1.0 / D2 * (u2 - mh) * S1;
+    const double h5 = -iD2 * (h4s * (u2 + mh) * iS1 + t3 * S2);
+    const double h6 = iD2 * (h4s * (u2 - mh) * S1 + t3 * S2);
+    const double h7 = c * iD1 * (u1 - mh) * iS1;
+    const double h8 = -c * iD1 * (u1 + mh) * S1;
+    const double h9 = iD2 * (u2 + mh) * iS1;
+    const double h10 = -iD2 * (u2 - mh) * S1;
     Coef2s k;  // fold  I_dr0 * (h1 eK/sigma + h2 em + h3 ep) + I_df0 * (h7 em + h8 ep)   (ref :125-135)
     k.h = h;
     k.Au = Idr0 * h1s;
@@ -121,6 +190,22 @@ CRT_HD Coef2s coef_2s(const Scen2s& s, double alpha, double tau, double rho_s, d
     k.Cd = Idr0 * h6 + Idf0 * h10;
     k.Idr0 = Idr0;
     return k;
+}
+
+// One level of one 2s column given em = exp(-hL), ep = exp(+hL), eK = exp(-K L)   (ref :125-156).
+CRT_HD void level_2s_e(const Coef2s& k, double inv_mu, double eK, double em, double ep, double& Idr, double& dn,
+                       double& up, double& F) {
+    up = k.Au * eK + (k.Bu * em + k.Cu * ep);
+    dn = k.Ad * eK + (k.Bd * em + k.Cd * ep);
+    Idr = k.Idr0 * eK;                          // ref :150
+    F = Idr * inv_mu + 2.0 * up + 2.0 * dn;     // ref :156
+}
+
+CRT_HD void level_2s(const Coef2s& k, double inv_mu, double L, double eK, double& Idr, double& dn, double& up,
+                     double& F) {
+    double em, ep;
+    exp_pm(k.h * L, em, ep);
+    level_2s_e(k, inv_mu, eK, em, ep, Idr, dn, up, F);
 }
 
 // Level sweep of VEC 2s columns.  `L`, `eK` are the scenario's level tables (eK[j] = exp(-K L[j])).
@@ -136,12 +221,7 @@ CRT_HD void column_2s(const Scen2s& s, const double* L, const double* eK, int n_
         double Idr[VEC], dn[VEC], up[VEC], F[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            const double em = exp_m(-k[v].h * Lj);
-            const double ep = 1.0 / em;  // exp(+hL) (ref :125-131 evaluates it directly; <= 1 ulp apart)
-            up[v] = k[v].Au * eKj + (k[v].Bu * em + k[v].Cu * ep);
-            dn[v] = k[v].Ad * eKj + (k[v].Bd * em + k[v].Cd * ep);
-            Idr[v] = k[v].Idr0 * eKj;                                   // ref :150
-            F[v] = Idr[v] * s.inv_mu + 2.0 * up[v] + 2.0 * dn[v];       // ref :156
+            level_2s(k[v], s.inv_mu, Lj, eKj, Idr[v], dn[v], up[v], F[v]);
             if (j == 0) { gnd[v][0] = Idr[v]; gnd[v][1] = dn[v]; gnd[v][2] = up[v]; }
             if (j == n_z - 1) absorbed[v] = absorbed_from_ends(Idr[v], gnd[v][0], dn[v], gnd[v][1], up[v], gnd[v][2]);
         }
@@ -172,7 +252,7 @@ CRT_HD void column_bl(const ScenBl& s, const double* L, const double* tau_b, con
         double Idr[VEC], dn[VEC], up[VEC], F[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            const double tau_g = exp_m(-Kg[v] * Lj);                                   // ref :65
+            const double tau_g = exp_neg(Kg[v] * Lj);                                  // ref :65
             Idr[v] = in.Idr0[v] * tb;                                                  // ref :69
             dn[v] = in.Idf0[v] * td + 0.5 * (in.Idr0[v] * (tau_g - tb));               // ref :70-79
             up[v] = 0.0;                                                               // ref :87
@@ -250,8 +330,9 @@ CRT_HD void column_bf(const ScenBf& s, const double* L, const double* eb, int n_
         double Idr[VEC], dn[VEC], up[VEC], F[VEC], sl[VEC], sh[VEC], tot[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            const double ed = exp_m(-k[v].k_d * Lj);                     // exp(-k_d L)
-            const double e2 = exp_m(-k[v].k_d * (s.L_T - Lj));           // exp(-k_d (L_T - L))   (ref :114)
+            double ed, ep;                                               // exp(-k_d L), exp(+k_d L)
+            exp_pm(k[v].k_d * Lj, ed, ep);
+            const double e2 = k[v].ed0 * ep;                             // exp(-k_d (L_T - L))   (ref :114)
             const double ex = e2 * s.eb0;                                // exp(k_d L - (k_b + k_d) L_T)  (ref :103)
             const double I_df = k[v].Idf0 * ed;                                                    // ref :86
             Idr[v] = k[v].Idr0 * ebj;                                                              // ref :90
@@ -300,9 +381,10 @@ CRT_HD void column_g77(const ScenBf& s, const double* L, const double* eb, int n
         double Idr[VEC], dn[VEC], up[VEC], F[VEC], sl[VEC], sh[VEC], tot[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            const double ed = exp_m(-k[v].k_d * Lj);
-            const double eg = exp_m(-kg[v] * Lj);
-            const double e2 = exp_m(-k[v].k_d * (s.L_T - Lj));
+            double ed, ep;                                               // exp(-k_d L), exp(+k_d L)
+            exp_pm(k[v].k_d * Lj, ed, ep);
+            const double eg = exp_neg(kg[v] * Lj);                       // exp(-k' k_b L)
+            const double e2 = k[v].ed0 * ep;                             // exp(-k_d (L_T - L))   (ref :95)
             const double I_df = a_df[v] * ed;
             Idr[v] = k[v].Idr0 * ebj;
             const double I_sc = a_sc[v] * eg + b_sc[v] * ebj;            // eq. 5
@@ -696,7 +778,7 @@ CRT_HD void solve4(double (&A)[4][4], double (&b)[4]) {
 
 // Folded per-band coefficients: I_dn(x) = sum_k dnP[k] e^{-lam_k (LAI-x)} + dnM[k] e^{-lam_k x} + dnK e^{-kappa x}
 struct Coef4s {
-    double lam[2], dnP[2], dnM[2], upP[2], upM[2], dnK, upK, Idr0;
+    double lam[2], g[2], dnP[2], dnM[2], upP[2], upM[2], dnK, upK, Idr0;  // g = e^{-lam LAI}
 };
 
 CRT_HD Coef4s coef_4s(const Scen4s& s, double r, double t, double rho, double Idr0, double Idf0) {
@@ -743,6 +825,7 @@ CRT_HD Coef4s coef_4s(const Scen4s& s, double r, double t, double rho, double Id
         psi_[i][0] = -k.lam[i] * phi[i][0] / q0;   // (P-Q)^{-1} phi lambda
         psi_[i][1] = -k.lam[i] * phi[i][1] / q1;
         g[i] = exp(-k.lam[i] * s.L_T);
+        k.g[i] = g[i];
     }
     // particular solution of the direct problem: (kappa^2 I - N) s_p = 2 (P-Q) vD
     const double kap = s.kappa, k2 = kap * kap;
@@ -803,8 +886,17 @@ CRT_HD void column_4s(const Scen4s& s, const double* L, const double* eK, int n_
         double Idr[VEC], dn[VEC], up[VEC], F[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            const double m0 = exp_m(-k[v].lam[0] * x), p0 = exp_m(-k[v].lam[0] * xr);
-            const double m1 = exp_m(-k[v].lam[1] * x), p1 = exp_m(-k[v].lam[1] * xr);
+            // m_i = e^{-lam_i x},  p_i = e^{-lam_i (LAI - x)} = e^{-lam_i LAI} e^{+lam_i x}
+            double m0, p0, m1, p1;
+            if (k[v].lam[0] * s.L_T < 600.0) {  // lam[0] is the larger eigenvalue; product form cannot overflow
+                exp_pm(k[v].lam[0] * x, m0, p0);
+                exp_pm(k[v].lam[1] * x, m1, p1);
+                p0 *= k[v].g[0];
+                p1 *= k[v].g[1];
+            } else {
+                m0 = exp(-k[v].lam[0] * x); p0 = exp(-k[v].lam[0] * xr);
+                m1 = exp(-k[v].lam[1] * x); p1 = exp(-k[v].lam[1] * xr);
+            }
             dn[v] = k[v].dnK * eKj + (k[v].dnP[0] * p0 + k[v].dnM[0] * m0) + (k[v].dnP[1] * p1 + k[v].dnM[1] * m1);
             up[v] = k[v].upK * eKj + (k[v].upP[0] * p0 + k[v].upM[0] * m0) + (k[v].upP[1] * p1 + k[v].upM[1] * m1);
             Idr[v] = k[v].Idr0 * eKj;                                  // ref :284

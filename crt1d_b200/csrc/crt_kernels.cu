@@ -10,13 +10,22 @@
 // loop) are built cooperatively in shared memory once per CTA.  No tensor cores: nothing here is a
 // dense contraction; the kernels are bound by HBM writes and the FP64 pipe.
 #include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "crt_internal.h"
 #include "crt_scheme.cuh"
 
 namespace crt {
 
-constexpr int BLOCK = 128;
+#ifndef CRT_BLOCK
+#define CRT_BLOCK 128
+#endif
+#ifndef CRT_MIN_BLOCKS
+#define CRT_MIN_BLOCKS 1
+#endif
+constexpr int BLOCK = CRT_BLOCK;            // threads per CTA = band tile / VEC
+constexpr int MIN_BLOCKS = CRT_MIN_BLOCKS;  // resident CTAs per SM the register allocator must allow
 
 // ---------------------------------------------------------------------------------------------
 // global-memory column accessor
@@ -62,11 +71,32 @@ struct GlobalOut {
     }
 };
 
+// streaming 8/16-byte load / store helpers
+template <int VEC>
+__device__ __forceinline__ void ld_vec(const double* q, double (&x)[VEC]) {
+    if constexpr (VEC == 2) {
+        const double2 t = __ldcs(reinterpret_cast<const double2*>(q));
+        x[0] = t.x;
+        x[1] = t.y;
+    } else {
+        x[0] = __ldcs(q);
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void st_vec(double* base, int64_t off, const double (&x)[VEC]) {
+    if (base == nullptr) return;
+    if constexpr (VEC == 2) {
+        __stcs(reinterpret_cast<double2*>(base + off), make_double2(x[0], x[1]));
+    } else {
+        __stcs(base + off, x[0]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // the solver kernel
 // ---------------------------------------------------------------------------------------------
 template <int SCHEME, int VEC>
-__global__ void __launch_bounds__(BLOCK) solve_kernel(const crt1d_batch in, const crt1d_out out, int tiles_per_scen,
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) solve_kernel(const crt1d_batch in, const crt1d_out out, int tiles_per_scen,
                                                       int tiles_per_cta) {
     extern __shared__ double tab[];
     __shared__ double red[BLOCK / 32][4];
@@ -155,9 +185,421 @@ static cudaError_t launch_vec(const crt1d_batch& in, const crt1d_out& out, bool 
     return vec2 ? launch_one<SCHEME, 2>(in, out, stream) : launch_one<SCHEME, 1>(in, out, stream);
 }
 
+// ---------------------------------------------------------------------------------------------
+// scenario-CTA kernel: ONE CTA = one whole scenario (all bands, all levels), one resident CTA per SM.
+//
+// Why: the output stream decides the speed of this path, and HBM write efficiency depends on how
+// many distinct rows are "open" at once.  Measured on B200 with a store-only microbenchmark
+// (tools/micro/wbw.cu, profiles/README.md): the tile decomposition above (444 resident CTAs, each
+// walking 2-4 KB row fragments 16.8 KB apart) tops out at 5.1 TB/s no matter how little arithmetic
+// it does, whereas 148 resident CTAs that each sweep complete 16.8 KB band rows, level after level,
+// reach 6.8-7.0 TB/s (a linear memset gets 6.9).  So here every thread owns SLOTS groups of VEC
+// adjacent bands spaced blockDim.x*VEC bands apart; at each level the CTA's warps emit the whole band
+// row of every field back to back.
+// ---------------------------------------------------------------------------------------------
+template <int VEC, int SLOTS>
+struct SplitOut {
+    double* p[N_FIELDS];  // pre-offset to (scenario, level 0, band 0); nullptr = field not requested
+    int64_t stride;       // doubles between levels (= n_wl)
+    int off[SLOTS];       // first band of each slot, or -1 if the slot is past the end of the row
+
+    __device__ __forceinline__ void st(int f, int j, const double (&x)[VEC * SLOTS]) const {
+        double* q = p[f];
+        if (q == nullptr) return;
+        q += (int64_t)j * stride;
+#pragma unroll
+        for (int k = 0; k < SLOTS; ++k) {
+            if (off[k] < 0) continue;
+            if constexpr (VEC == 2) {
+                __stcs(reinterpret_cast<double2*>(q + off[k]), make_double2(x[2 * k], x[2 * k + 1]));
+            } else {
+                __stcs(q + off[k], x[k]);
+            }
+        }
+    }
+    __device__ __forceinline__ void st_tmp(int f, int j, const double (&x)[VEC * SLOTS]) const {
+        double* q = p[f] + (int64_t)j * stride;
+#pragma unroll
+        for (int k = 0; k < SLOTS; ++k) {
+            if (off[k] < 0) continue;
+            if constexpr (VEC == 2) {
+                *reinterpret_cast<double2*>(q + off[k]) = make_double2(x[2 * k], x[2 * k + 1]);
+            } else {
+                q[off[k]] = x[k];
+            }
+        }
+    }
+    __device__ __forceinline__ void ld_tmp(int f, int j, double (&x)[VEC * SLOTS]) const {
+        const double* q = p[f] + (int64_t)j * stride;
+#pragma unroll
+        for (int k = 0; k < SLOTS; ++k) {
+            if (off[k] < 0) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) x[k * VEC + v] = 1.0;
+                continue;
+            }
+            if constexpr (VEC == 2) {
+                const double2 t = __ldcs(reinterpret_cast<const double2*>(q + off[k]));
+                x[2 * k] = t.x;
+                x[2 * k + 1] = t.y;
+            } else {
+                x[k] = __ldcs(q + off[k]);
+            }
+        }
+    }
+};
+
+template <int SCHEME, int VEC, int SLOTS, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) solve_scen_kernel(const crt1d_batch in, const crt1d_out out) {
+    extern __shared__ double tab[];
+    __shared__ double red[MAXT / 32][4];
+    constexpr int W = VEC * SLOTS;  // columns per thread per sweep
+
+    const int64_t s = blockIdx.x;
+    const int n_z = in.n_z, n_wl = in.n_wl, T = blockDim.x;
+    for (int j = threadIdx.x; j < n_z; j += T) fill_level_tables<SCHEME>(in, s, j, tab);
+    __syncthreads();
+
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int64_t prof = (int64_t)n_z * n_wl;
+    const int64_t xprof = (int64_t)extra_rows(SCHEME, n_z) * n_wl;
+    SplitOut<VEC, SLOTS> o;
+    o.stride = n_wl;
+    o.p[F_IDR] = out.I_dr ? out.I_dr + s * prof : nullptr;
+    o.p[F_DN] = out.I_df_d ? out.I_df_d + s * prof : nullptr;
+    o.p[F_UP] = out.I_df_u ? out.I_df_u + s * prof : nullptr;
+    o.p[F_F] = out.F ? out.F + s * prof : nullptr;
+    o.p[F_X0] = out.x0 ? out.x0 + s * xprof : nullptr;
+    o.p[F_X1] = out.x1 ? out.x1 + s * xprof : nullptr;
+    o.p[F_X2] = out.x2 ? out.x2 + s * xprof : nullptr;
+
+    const int n_grp = n_wl / VEC;  // launcher guarantees n_wl % VEC == 0
+    for (int base = 0; base < n_grp; base += SLOTS * T) {
+        if (base + (int)threadIdx.x >= n_grp) break;  // slot 0 invalid => all slots invalid
+        BandIn<W> b;
+#pragma unroll
+        for (int k = 0; k < SLOTS; ++k) {
+            const int g = base + k * T + threadIdx.x;
+            o.off[k] = g < n_grp ? g * VEC : -1;
+            const BandIn<VEC> bk = load_bands<VEC>(in, s, (g < n_grp ? g : base + (int)threadIdx.x) * VEC);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                b.leaf_r[k * VEC + v] = bk.leaf_r[v];
+                b.leaf_t[k * VEC + v] = bk.leaf_t[v];
+                b.soil_r[k * VEC + v] = bk.soil_r[v];
+                b.Idr0[k * VEC + v] = bk.Idr0[v];
+                b.Idf0[k * VEC + v] = bk.Idf0[v];
+            }
+        }
+        double rho_c[W], ab[W];
+        solve_column_group<SCHEME, W>(in, s, tab, b, o, rho_c, ab);
+#pragma unroll
+        for (int k = 0; k < SLOTS; ++k) {
+            if (o.off[k] < 0) continue;
+            if constexpr (SCHEME == CRT1D_SCHEME_BF) {
+                if (out.rho_c) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) out.rho_c[s * n_wl + o.off[k] + v] = rho_c[k * VEC + v];
+                }
+            }
+            if (out.absorbed) {
+                for (int q = 0; q < out.n_bw; ++q) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) acc[q] += out.band_w[(int64_t)q * n_wl + o.off[k] + v] * ab[k * VEC + v];
+                }
+            }
+        }
+    }
+
+    if (out.absorbed) {  // fixed-order block reduction (deterministic)
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double v = acc[k];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            if (lane == 0) red[warp][k] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < out.n_bw) {
+            double v = 0.0;
+            for (int w = 0; w < (T + 31) / 32; ++w) v += red[w][threadIdx.x];
+            out.absorbed[s * out.n_bw + threadIdx.x] = v;
+        }
+    }
+}
+
+template <int SCHEME, int VEC, int SLOTS, int MAXT>
+static cudaError_t launch_scen(const crt1d_batch& in, const crt1d_out& out, int threads, cudaStream_t stream) {
+    if (in.n_scen > 2147483647LL) return cudaErrorInvalidConfiguration;
+    const size_t smem = (size_t)n_level_tables(SCHEME) * in.n_z * sizeof(double);
+    auto kern = solve_scen_kernel<SCHEME, VEC, SLOTS, MAXT>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<(unsigned)in.n_scen, threads, smem, stream>>>(in, out);
+    return cudaGetLastError();
+}
+
+// Pick (SLOTS, threads) for the scenario-CTA kernel: cover the n_wl/VEC column groups of a row with as
+// little idle lane time as possible, within the register budget of each instantiation.
+struct ScenCfg {
+    int slots, threads;
+};
+static ScenCfg pick_scen_cfg(int n_grp) {
+    const char* env = getenv("CRT1D_B200_SCEN_CFG");  // "slots,threads" (tuning experiments only)
+    if (env) {
+        int sl = 0, th = 0;
+        if (sscanf(env, "%d,%d", &sl, &th) == 2 && sl >= 1 && sl <= 3 && th >= 32 && th % 32 == 0) return {sl, th};
+    }
+    const int max_t[4] = {0, 1024, 512, 352};
+    ScenCfg best = {1, 32};
+    double best_cost = 1e30;
+    for (int sl = 1; sl <= 3; ++sl) {
+        for (int th = 64; th <= max_t[sl]; th += 32) {
+            const int sweeps = (n_grp + sl * th - 1) / (sl * th);
+            // cost ~ lane-time: every sweep occupies the CTA for (slots columns) whether lanes are valid or not;
+            // prefer >= 8 warps so a lone CTA per SM can hide FP64 latency
+            double cost = (double)sweeps * sl * th / n_grp;
+            if (th < 256) cost *= 1.0 + (256 - th) / 512.0;
+            if (cost < best_cost - 1e-9) {
+                best_cost = cost;
+                best = {sl, th};
+            }
+        }
+    }
+    return best;
+}
+
+template <int SCHEME, int VEC>
+static cudaError_t launch_scen_cfg(const crt1d_batch& in, const crt1d_out& out, cudaStream_t stream) {
+    const ScenCfg c = pick_scen_cfg(in.n_wl / VEC);
+    switch (c.slots) {
+        case 1: return launch_scen<SCHEME, VEC, 1, 1024>(in, out, c.threads, stream);
+        case 2: return launch_scen<SCHEME, VEC, 2, 512>(in, out, c.threads > 512 ? 512 : c.threads, stream);
+        default: return launch_scen<SCHEME, VEC, 3, 352>(in, out, c.threads > 352 ? 352 : c.threads, stream);
+    }
+}
+
 size_t solve_shared_bytes(int scheme, int n_z) { return (size_t)n_level_tables(scheme) * n_z * sizeof(double); }
 
+// ---------------------------------------------------------------------------------------------
+// 2s row-sweep kernel: ONE CTA = one whole scenario, per-band coefficients in SHARED MEMORY.
+//
+// The level sweep of a closed-form scheme needs only the band's folded coefficients (2s: 8 doubles).
+// Holding them in shared memory (8 x n_wl x 8 B = 134 KB at 2100 bands) instead of registers frees the
+// mapping of lanes to columns: warps pull work items (group of LV consecutive levels x 32*VEC adjacent
+// bands) from a shared counter in row-major order, so the CTA writes complete 16.8 KB band rows of
+// every field, level after level, with perfect load balance and ~64 registers per thread (1024
+// threads, all 64 warp slots of the SM busy).  One resident CTA per SM => 148 row streams in flight,
+// the pattern that reaches ~6.8 TB/s on B200 (tools/micro/wbw.cu) where the band-tile pattern
+// saturates at 5.1 TB/s.  The canopy-absorbed reduction uses the ground/top levels evaluated in the
+// coefficient phase (fixed thread->column assignment), so it stays deterministic.
+// ---------------------------------------------------------------------------------------------
+template <int VEC, int LV, int MAXT, bool REC>
+__global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batch in, const crt1d_out out) {
+    extern __shared__ double sm[];
+    __shared__ double red[MAXT / 32][4];
+    __shared__ int counter;
+    __shared__ unsigned char grp_uniform[1024];  // per level group: 1 if its levels are equally spaced (n_z <= 1024*LV)
+
+    const int64_t s = blockIdx.x;
+    const int n_z = in.n_z, n_wl = in.n_wl, T = blockDim.x;
+    const int ld = (n_wl + 1) & ~1;  // coefficient row stride (even => 16-byte aligned pairs)
+    double* L = sm;
+    double* eK = sm + n_z;
+    double* cf = sm + 2 * n_z + ((2 * n_z) & 1);  // [8][ld], 16-byte aligned
+    const int cf_off = 2 * n_z + ((2 * n_z) & 1);
+    (void)cf_off;
+
+    for (int j = threadIdx.x; j < n_z; j += T) fill_level_tables<CRT1D_SCHEME_2S>(in, s, j, sm);
+    if (threadIdx.x == 0) counter = 0;
+    __syncthreads();
+    if (REC) {
+        const double tol = 8.0 * 2.220446049250313e-16 * L[0];
+        for (int g = threadIdx.x; g < (n_z + LV - 1) / LV && g < 1024; g += T) {
+            const int a = g * LV, b = min(n_z, a + LV);
+            bool u = (b - a) >= 2;
+            for (int j = a + 1; j + 1 < b; ++j) u = u && fabs((L[j] - L[j + 1]) - (L[a] - L[a + 1])) <= tol;
+            grp_uniform[g] = u ? 1 : 0;
+        }
+    }
+
+    // ---- phase B: per-band coefficients -> shared memory; ground/top levels for the absorbed reduction
+    const Scen2s sc = scen_2s(in.psi[s], in.K_b[s], in.mu_bar[s], in.mla_deg, L[0]);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int c = threadIdx.x; c < n_wl; c += T) {
+        const BandIn<1> b = load_bands<1>(in, s, c);
+        const Coef2s k = coef_2s(sc, b.leaf_r[0], b.leaf_t[0], b.soil_r[0], b.Idr0[0], b.Idf0[0]);
+        cf[0 * ld + c] = k.h;
+        cf[1 * ld + c] = k.Au;
+        cf[2 * ld + c] = k.Bu;
+        cf[3 * ld + c] = k.Cu;
+        cf[4 * ld + c] = k.Ad;
+        cf[5 * ld + c] = k.Bd;
+        cf[6 * ld + c] = k.Cd;
+        cf[7 * ld + c] = k.Idr0;
+        if (out.absorbed) {
+            double Ig, dg, ug, Fg, It, dt, ut, Ft;
+            level_2s(k, sc.inv_mu, L[0], eK[0], Ig, dg, ug, Fg);
+            level_2s(k, sc.inv_mu, L[n_z - 1], eK[n_z - 1], It, dt, ut, Ft);
+            const double a = absorbed_from_ends(It, Ig, dt, dg, ut, ug);
+            for (int q = 0; q < out.n_bw; ++q) acc[q] += out.band_w[(int64_t)q * n_wl + c] * a;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: row-major work items
+    const int64_t prof = (int64_t)n_z * n_wl;
+    double* pI = out.I_dr ? out.I_dr + s * prof : nullptr;
+    double* pD = out.I_df_d ? out.I_df_d + s * prof : nullptr;
+    double* pU = out.I_df_u ? out.I_df_u + s * prof : nullptr;
+    double* pF = out.F ? out.F + s * prof : nullptr;
+    const int n_grp = n_wl / VEC;
+    const int n_chunks = (n_grp + 31) / 32;
+    const int n_lg = (n_z + LV - 1) / LV;
+    const int n_items = n_chunks * n_lg;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(&counter, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const int lg = item / n_chunks, g = (item - lg * n_chunks) * 32 + lane;
+        if (g >= n_grp) continue;
+        const int c0 = g * VEC;
+        Coef2s k[VEC];
+        if constexpr (VEC == 2) {
+            const double2 a0 = *reinterpret_cast<const double2*>(cf + 0 * ld + c0);
+            const double2 a1 = *reinterpret_cast<const double2*>(cf + 1 * ld + c0);
+            const double2 a2 = *reinterpret_cast<const double2*>(cf + 2 * ld + c0);
+            const double2 a3 = *reinterpret_cast<const double2*>(cf + 3 * ld + c0);
+            const double2 a4 = *reinterpret_cast<const double2*>(cf + 4 * ld + c0);
+            const double2 a5 = *reinterpret_cast<const double2*>(cf + 5 * ld + c0);
+            const double2 a6 = *reinterpret_cast<const double2*>(cf + 6 * ld + c0);
+            const double2 a7 = *reinterpret_cast<const double2*>(cf + 7 * ld + c0);
+            k[0] = {a0.x, a1.x, a2.x, a3.x, a4.x, a5.x, a6.x, a7.x};
+            k[1] = {a0.y, a1.y, a2.y, a3.y, a4.y, a5.y, a6.y, a7.y};
+        } else {
+            k[0] = {cf[0 * ld + c0], cf[1 * ld + c0], cf[2 * ld + c0], cf[3 * ld + c0],
+                    cf[4 * ld + c0], cf[5 * ld + c0], cf[6 * ld + c0], cf[7 * ld + c0]};
+        }
+        const int j0 = lg * LV, j1 = min(n_z, j0 + LV);
+        // Equally spaced levels inside the group (every profile the reference's LAI generators make:
+        // lai = linspace(1, 0, n) * LAI, ref ../leaf_area.py:82-88): e^{-+h L_j} advance by the constant
+        // factor e^{+-h dL}, so only the first level of the group needs exponentials.  Drift <= LV ulp.
+        const bool uniform = REC && grp_uniform[lg] != 0;
+        double em[VEC], ep[VEC], qm[VEC], qp[VEC];
+        if (uniform) {
+            const double dL = L[j0] - L[j0 + 1];  // > 0: levels run from the ground (largest L) upwards
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                exp_pm(k[v].h * L[j0], em[v], ep[v]);
+                exp_pm(k[v].h * dL, qp[v], qm[v]);  // qp = e^{-h dL} multiplies e^{+hL}; qm = e^{+h dL} multiplies e^{-hL}
+            }
+        }
+        for (int j = j0; j < j1; ++j) {
+            const double Lj = L[j], eKj = eK[j];
+            double Idr[VEC], dn[VEC], up[VEC], F[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                if (uniform) {
+                    level_2s_e(k[v], sc.inv_mu, eKj, em[v], ep[v], Idr[v], dn[v], up[v], F[v]);
+                    em[v] *= qm[v];
+                    ep[v] *= qp[v];
+                } else {
+                    level_2s(k[v], sc.inv_mu, Lj, eKj, Idr[v], dn[v], up[v], F[v]);
+                }
+            }
+            const int64_t o = (int64_t)j * n_wl + c0;
+            st_vec<VEC>(pI, o, Idr);
+            st_vec<VEC>(pD, o, dn);
+            st_vec<VEC>(pU, o, up);
+            st_vec<VEC>(pF, o, F);
+        }
+    }
+
+    if (out.absorbed) {  // fixed-order block reduction (deterministic)
+        const int warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            double v = acc[q];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            if (lane == 0) red[warp][q] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < out.n_bw) {
+            double v = 0.0;
+            for (int w = 0; w < (T + 31) / 32; ++w) v += red[w][threadIdx.x];
+            out.absorbed[s * out.n_bw + threadIdx.x] = v;
+        }
+    }
+}
+
+static size_t rows_2s_shared_bytes(int n_z, int n_wl) {
+    const int ld = (n_wl + 1) & ~1;
+    return (size_t)(2 * n_z + ((2 * n_z) & 1) + 8 * ld) * sizeof(double);
+}
+
+template <int VEC, int LV, int MAXT, bool REC>
+static cudaError_t launch_rows_2s_t(const crt1d_batch& in, const crt1d_out& out, int threads, cudaStream_t stream) {
+    const size_t smem = rows_2s_shared_bytes(in.n_z, in.n_wl);
+    auto kern = solve_2s_rows_kernel<VEC, LV, MAXT, REC>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)in.n_scen, threads, smem, stream>>>(in, out);
+    return cudaGetLastError();
+}
+
+// rows-kernel configuration "LV,threads,rec" via CRT1D_B200_ROWS_CFG (tuning experiments); the default
+// is the best measured on B200 (profiles/README.md).
+template <int VEC>
+static cudaError_t launch_rows_2s(const crt1d_batch& in, const crt1d_out& out, cudaStream_t stream) {
+    int lv = 6, th = 512, rec = 1;  // best of the sweep in profiles/README.md (0.907 of measured HBM peak)
+    const char* env = getenv("CRT1D_B200_ROWS_CFG");
+    if (env) sscanf(env, "%d,%d,%d", &lv, &th, &rec);
+    if (th % 32 != 0 || th < 64 || th > 1024) th = 512;
+    if (in.n_z > 1024 * 2) rec = 0;
+    const int bucket = th > 768 ? 1024 : th > 640 ? 768 : th > 512 ? 640 : 512;
+#define CRT_ROWS_LV(LVV)                                                                                   \
+    if (lv == LVV) {                                                                                       \
+        if (bucket == 1024) return rec ? launch_rows_2s_t<VEC, LVV, 1024, true>(in, out, th, stream)       \
+                                       : launch_rows_2s_t<VEC, LVV, 1024, false>(in, out, th, stream);     \
+        if (bucket == 768) return rec ? launch_rows_2s_t<VEC, LVV, 768, true>(in, out, th, stream)         \
+                                      : launch_rows_2s_t<VEC, LVV, 768, false>(in, out, th, stream);       \
+        if (bucket == 640) return rec ? launch_rows_2s_t<VEC, LVV, 640, true>(in, out, th, stream)         \
+                                      : launch_rows_2s_t<VEC, LVV, 640, false>(in, out, th, stream);       \
+        return rec ? launch_rows_2s_t<VEC, LVV, 512, true>(in, out, th, stream)                            \
+                   : launch_rows_2s_t<VEC, LVV, 512, false>(in, out, th, stream);                          \
+    }
+    CRT_ROWS_LV(2)
+    CRT_ROWS_LV(3)
+    CRT_ROWS_LV(4)
+    CRT_ROWS_LV(6)
+    CRT_ROWS_LV(10)
+#undef CRT_ROWS_LV
+    return rec ? launch_rows_2s_t<VEC, 4, 512, true>(in, out, th > 512 ? 512 : th, stream)
+               : launch_rows_2s_t<VEC, 4, 512, false>(in, out, th > 512 ? 512 : th, stream);
+}
+
+// Batches with at least this many scenarios go to the scenario-CTA kernel (one CTA per SM needs >= n_SM
+// scenarios in flight); smaller ones (the single-scenario plugin path) use the band-tile kernel.
+static int64_t scen_kernel_min_batch() {
+    const char* env = getenv("CRT1D_B200_SCEN_MIN");
+    return env ? atoll(env) : 148;
+}
+
 cudaError_t launch_solve(int scheme, const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream) {
+    if (scheme == CRT1D_SCHEME_2S && in.n_scen >= scen_kernel_min_batch()) {
+        const char* mode = getenv("CRT1D_B200_2S_KERNEL");  // "rows" (default) | "scen" | "tile" (tuning / tests)
+        const bool rows_fit = rows_2s_shared_bytes(in.n_z, in.n_wl) <= 227u * 1024u;
+        if ((mode == nullptr || mode[0] == 'r') && rows_fit)
+            return vec2 ? launch_rows_2s<2>(in, out, stream) : launch_rows_2s<1>(in, out, stream);
+        if (mode != nullptr && mode[0] == 's')
+            return vec2 ? launch_scen_cfg<CRT1D_SCHEME_2S, 2>(in, out, stream) : launch_scen_cfg<CRT1D_SCHEME_2S, 1>(in, out, stream);
+    }
     switch (scheme) {
         case CRT1D_SCHEME_2S: return launch_vec<CRT1D_SCHEME_2S>(in, out, vec2, stream);
         case CRT1D_SCHEME_4S: return launch_vec<CRT1D_SCHEME_4S>(in, out, vec2, stream);
@@ -175,26 +617,6 @@ cudaError_t launch_solve(int scheme, const crt1d_batch& in, const crt1d_out& out
 // thread = VEC adjacent bands, walks up the levels carrying the level below in registers, so every
 // profile value is read exactly once; per-layer scalars (1 - tau_b, f_sl) sit in shared memory.
 // ---------------------------------------------------------------------------------------------
-template <int VEC>
-__device__ __forceinline__ void ld_vec(const double* q, double (&x)[VEC]) {
-    if constexpr (VEC == 2) {
-        const double2 t = __ldcs(reinterpret_cast<const double2*>(q));
-        x[0] = t.x;
-        x[1] = t.y;
-    } else {
-        x[0] = __ldcs(q);
-    }
-}
-template <int VEC>
-__device__ __forceinline__ void st_vec(double* base, int64_t off, const double (&x)[VEC]) {
-    if (base == nullptr) return;
-    if constexpr (VEC == 2) {
-        __stcs(reinterpret_cast<double2*>(base + off), make_double2(x[0], x[1]));
-    } else {
-        __stcs(base + off, x[0]);
-    }
-}
-
 template <int VEC>
 __global__ void __launch_bounds__(BLOCK) absorption_kernel(const crt1d_batch in, const double* __restrict__ I_dr,
                                                            const double* __restrict__ I_df_d,

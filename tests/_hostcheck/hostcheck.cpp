@@ -107,3 +107,7 @@ __attribute__((visibility("default"))) double hostcheck_leaf_integral(int family
     return crt::leaf_integral(family, param, mu_s, r, which);
 }
 }
+
+extern "C" __attribute__((visibility("default"))) void hostcheck_exp_pm(int n, const double* x, double* em, double* ep) {
+    for (int i = 0; i < n; ++i) crt::exp_pm(x[i], em[i], ep[i]);
+}

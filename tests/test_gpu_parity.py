@@ -350,3 +350,62 @@ def test_errors_are_loud():
     with pytest.raises(AssertionError):  # LAI profile must end at 0, as Model._check_inputs demands
         crt.solvers.solve_bl(psi=0.3, I_dr0_all=p["I_dr0_all"], I_df0_all=p["I_df0_all"], lai=p["lai"] + 1.0,
                              leaf_t=p["leaf_t"], leaf_r=p["leaf_r"], K_b_fn=K_b_fn)
+
+
+# ---------------------------------------------------------------------------------- kernel variants
+@pytest.mark.parametrize("mode,cfg", [("rows", "4,512,1"), ("rows", "4,512,0"), ("rows", "3,1024,1"), ("rows", "2,768,0"),
+                                      ("rows", "6,640,1"), ("rows", "10,96,1"), ("scen", "1,1024"), ("scen", "2,512"),
+                                      ("scen", "3,352"), ("scen", "3,64")])
+def test_large_batch_kernels_equal_tile_kernel(mode, cfg, monkeypatch):
+    """Large batches run the row-sweep kernel (coefficients in shared memory, row-major work items, level
+    recurrence on equally spaced levels); the band-tile kernel serves small batches.  Same per-column
+    formulas (crt_core.cuh); instantiations differ in FMA contraction and in how exp(-+hL) is advanced, so
+    they agree to rounding x conditioning: 1e-12 (the recurrence drifts ~1 ulp per level of a group), relaxed only where sigma -> 0 (see util.sigma_rel_2s)."""
+    import copy
+
+    import torch
+
+    from crt1d_b200 import engine
+    from crt1d_b200 import sweep
+    from crt1d_b200.solvers import common
+    from util import assert_close_conditioned
+    from util import sigma_rel_2s
+
+    spec = sweep.synthetic_sweep_spec(seed=0)
+    sub = spec.slice(431900, 431900 + 160)
+    srel = sigma_rel_2s(sub, common.mu_bar_fn(sub.leaf_angle.G_fn))
+    bw = np.stack([np.ones(spec.n_wl), np.linspace(0, 1, spec.n_wl)])
+    monkeypatch.setenv("CRT1D_B200_2S_KERNEL", "tile")
+    a = engine.solve(sub, "2s", band_w=bw)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("CRT1D_B200_2S_KERNEL", mode)
+    monkeypatch.setenv("CRT1D_B200_SCEN_MIN", "1")
+    monkeypatch.setenv("CRT1D_B200_ROWS_CFG" if mode == "rows" else "CRT1D_B200_SCEN_CFG", cfg)
+    b = engine.solve(sub, "2s", band_w=bw)
+    torch.cuda.synchronize()
+    assert torch.equal(a["I_dr"], b["I_dr"])
+    for k in ("I_df_d", "I_df_u", "F"):
+        assert_close_conditioned(b[k].cpu().numpy(), a[k].cpu().numpy(), 1e-12, srel, f"{mode} {cfg} {k}")
+    assert_close(b["absorbed"].cpu().numpy(), a["absorbed"].cpu().numpy(), 1e-11, f"{mode} {cfg} absorbed")
+    # vs the oracle on a few scenarios (the parity bar proper)
+    for i in (0, 72, 159):
+        ref = oracle.run("2s", sub.scenario_params(i))
+        for k in ("I_df_d", "I_df_u", "F"):
+            assert_close_conditioned(b[k][i].cpu().numpy()[None], ref[k][None], RTOL, srel[i:i + 1], f"{mode} {cfg} oracle {k}")
+    # odd band count -> VEC = 1 instantiation; non-uniform level spacing -> no recurrence
+    odd = copy.copy(sub.slice(0, 150))
+    for k in ("leaf_r_lib", "leaf_t_lib", "soil_r_lib", "I_dr0_lib", "I_df0_lib"):
+        setattr(odd, k, np.ascontiguousarray(getattr(sub, k)[:, :333]))
+    odd.wl, odd.dwl = sub.wl[:333], sub.dwl[:333]
+    odd.lai_lib = np.ascontiguousarray(sub.lai_lib * np.linspace(1.0, 0.6, sub.n_z) ** 0.5)
+    srel_o = srel[:150, :333]
+    monkeypatch.setenv("CRT1D_B200_2S_KERNEL", "tile")
+    a = engine.solve(odd, "2s")
+    monkeypatch.setenv("CRT1D_B200_2S_KERNEL", mode)
+    b = engine.solve(odd, "2s")
+    torch.cuda.synchronize()
+    for k in ("I_df_d", "I_df_u", "F"):
+        assert_close_conditioned(b[k].cpu().numpy(), a[k].cpu().numpy(), 1e-12, srel_o, f"{mode} {cfg} odd n_wl {k}")
+    ref = oracle.run("2s", odd.scenario_params(7))
+    for k in ("I_df_d", "I_df_u", "F"):
+        assert_close_conditioned(b[k][7].cpu().numpy()[None], ref[k][None], RTOL, srel_o[7:8], f"{mode} {cfg} odd oracle {k}")
