@@ -109,44 +109,60 @@ class DeviceBatch:
         self.cbatch = self._make_cbatch()
 
     # -- prologue on the device, parametric leaf-angle family -------------------------------------
+    def _buf(self, torch, name, shape, like=None):
+        """Reuse the device tensor `name` if it exists with the right shape (stable pointers across
+        `reload()`), else allocate it."""
+        t = self._t.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=torch.float64, device=self.device)
+            self._t[name] = t
+        return t
+
     def _device_prologue(self, torch, tau_d_method, n_quad):
         b, lib, la = self.batch, self.lib, self.batch.leaf_angle
         S = b.n_scen
         st = _stream_ptr(torch)
-        f64 = dict(dtype=torch.float64, device=self.device)
-        K_b = torch.empty(S, **f64)
-        G = torch.empty(S, **f64)
-        _lib.check(lib.crt1d_leaf_G(la.family_id, la.param, S, self._t["psi"].data_ptr(), G.data_ptr(), K_b.data_ptr(), st))
-        self._t["K_b"], self._t["G"] = K_b, G
-        nq = 0 if tau_d_method == "9sky" else int(n_quad)
         if tau_d_method not in ("quad", "9sky"):
             raise ValueError("invalid `method`. Valid options are 'quad' and '9sky'.")
+        K_b = self._buf(torch, "K_b", (S,))
+        G = self._buf(torch, "G", (S,))
+        _lib.check(lib.crt1d_leaf_G(la.family_id, la.param, S, self._t["psi"].data_ptr(), G.data_ptr(), K_b.data_ptr(), st))
+        nq = 0 if tau_d_method == "9sky" else int(n_quad)
         if self.scheme in ("2s", "4s"):
-            tri = torch.empty(3, **f64)
+            tri = self._buf(torch, "_tri", (3,))
             _lib.check(lib.crt1d_leaf_integrals(la.family_id, la.param, self.mu_s, int(n_quad), tri.data_ptr(), st))
             if self.scheme == "2s":
-                self._t["mu_bar"] = tri[0].expand(S).contiguous()
+                self._buf(torch, "mu_bar", (S,)).copy_(tri[0].expand(S))
             else:
-                self._t["G_int"] = tri[1:3].expand(S, 2).contiguous()
+                self._buf(torch, "G_int", (S, 2)).copy_(tri[1:3].expand(S, 2))
         elif self.scheme == "bl":
-            td = torch.empty_like(self._t["lai_lib"])
+            td = self._buf(torch, "tau_d_lev", tuple(self._t["lai_lib"].shape))
             _lib.check(lib.crt1d_tau_d(la.family_id, la.param, nq, td.numel(), self._t["lai_lib"].data_ptr(), td.data_ptr(), st))
-            self._t["tau_d_lev"] = td
         elif self.scheme == "n79":
             dl = np.zeros_like(b.lai_lib)
             dl[:, :-1] = b.lai_lib[:, :-1] - b.lai_lib[:, 1:]
             dl_d = torch.as_tensor(dl).to(self.device)
-            td = torch.empty_like(dl_d)
+            td = self._buf(torch, "tau_d_lev", tuple(dl_d.shape))
             _lib.check(lib.crt1d_tau_d(la.family_id, la.param, nq, td.numel(), dl_d.data_ptr(), td.data_ptr(), st))
-            self._t["tau_d_lev"] = td
         elif self.scheme == "zq":
             dm = np.array([_common.mean_dlai(row) for row in b.lai_lib])
             dm_d = torch.as_tensor(dm).to(self.device)
             ti = torch.empty_like(dm_d)
             _lib.check(lib.crt1d_tau_d(la.family_id, la.param, int(n_quad), ti.numel(), dm_d.data_ptr(), ti.data_ptr(), st))
             idx = self._t["lai_idx"].long()
-            self._t["tau_i"] = ti[idx].contiguous()
-            self._t["tau_psi"] = torch.exp(-K_b * dm_d[idx]).contiguous()  # tau_b_fn at the mean dlai (prologue scalar)
+            self._buf(torch, "tau_i", (S,)).copy_(ti[idx])
+            self._buf(torch, "tau_psi", (S,)).copy_(torch.exp(-K_b * dm_d[idx]))  # tau_b_fn at the mean dlai (prologue scalar)
+
+    def reload(self, pinned, tau_d_method="quad", n_quad=DEFAULT_N_QUAD):
+        """Copy a new batch of the SAME shape from page-locked host tensors into the existing device
+        tensors (asynchronous DMA on the current stream) and redo the device prologue.  Device pointers --
+        and therefore every ctypes call struct built from them -- stay valid."""
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            for k in BATCH_ARRAYS:
+                self._t[k].copy_(pinned[k], non_blocking=True)
+            self._device_prologue(torch, tau_d_method, n_quad)
+        return self
 
     def _make_cbatch(self):
         b = self.batch

@@ -148,10 +148,15 @@ def test_bonan_absorption_through_model():
 
 
 # ---------------------------------------------------------------------------------- batched path
-def test_batched_sweep_sample_matches_reference_golden():
+@pytest.mark.parametrize("kernel", ["tile", "rows"])
+def test_batched_sweep_sample_matches_reference_golden(kernel, monkeypatch):
     """cfg 3 at full band count: strided sample of the synthetic sweep, device-side prologue
-    (G/K_b kernel + Gauss-Legendre mu_bar) vs the reference's 2s with host quad."""
+    (G/K_b kernel + Gauss-Legendre mu_bar) vs the reference's 2s with host quad -- through both 2s
+    kernels (the row-sweep kernel that large batches use is forced on for this small one)."""
     import torch
+
+    monkeypatch.setenv("CRT1D_B200_2S_KERNEL", kernel)
+    monkeypatch.setenv("CRT1D_B200_SCEN_MIN", "1")
 
     from crt1d_b200 import engine
     from crt1d_b200 import sweep
@@ -360,7 +365,8 @@ def test_large_batch_kernels_equal_tile_kernel(mode, cfg, monkeypatch):
     """Large batches run the row-sweep kernel (coefficients in shared memory, row-major work items, level
     recurrence on equally spaced levels); the band-tile kernel serves small batches.  Same per-column
     formulas (crt_core.cuh); instantiations differ in FMA contraction and in how exp(-+hL) is advanced, so
-    they agree to rounding x conditioning: 1e-12 (the recurrence drifts ~1 ulp per level of a group), relaxed only where sigma -> 0 (see util.sigma_rel_2s)."""
+    they agree to rounding x conditioning: 1e-11 (the recurrence drifts ~1 ulp per level of a group, amplified ~1e3 where
+    the three exponential terms cancel, e.g. at the canopy top), relaxed further only where sigma -> 0 (see util.sigma_rel_2s)."""
     import copy
 
     import torch
@@ -385,7 +391,7 @@ def test_large_batch_kernels_equal_tile_kernel(mode, cfg, monkeypatch):
     torch.cuda.synchronize()
     assert torch.equal(a["I_dr"], b["I_dr"])
     for k in ("I_df_d", "I_df_u", "F"):
-        assert_close_conditioned(b[k].cpu().numpy(), a[k].cpu().numpy(), 1e-12, srel, f"{mode} {cfg} {k}")
+        assert_close_conditioned(b[k].cpu().numpy(), a[k].cpu().numpy(), 1e-11, srel, f"{mode} {cfg} {k}")
     assert_close(b["absorbed"].cpu().numpy(), a["absorbed"].cpu().numpy(), 1e-11, f"{mode} {cfg} absorbed")
     # vs the oracle on a few scenarios (the parity bar proper)
     for i in (0, 72, 159):
@@ -405,7 +411,7 @@ def test_large_batch_kernels_equal_tile_kernel(mode, cfg, monkeypatch):
     b = engine.solve(odd, "2s")
     torch.cuda.synchronize()
     for k in ("I_df_d", "I_df_u", "F"):
-        assert_close_conditioned(b[k].cpu().numpy(), a[k].cpu().numpy(), 1e-12, srel_o, f"{mode} {cfg} odd n_wl {k}")
+        assert_close_conditioned(b[k].cpu().numpy(), a[k].cpu().numpy(), 1e-11, srel_o, f"{mode} {cfg} odd n_wl {k}")
     ref = oracle.run("2s", odd.scenario_params(7))
     for k in ("I_df_d", "I_df_u", "F"):
         assert_close_conditioned(b[k][7].cpu().numpy()[None], ref[k][None], RTOL, srel_o[7:8], f"{mode} {cfg} odd oracle {k}")
