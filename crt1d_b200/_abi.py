@@ -11,7 +11,7 @@ ERR_CUDA = -4
 ERR_NO_DEVICE = -5
 ERR_NO_MEMORY = -6
 
-SCHEME_IDS = {"2s": 0, "4s": 1, "bf": 2, "bl": 3, "g77": 4, "n79": 5, "zq": 6}
+SCHEME_IDS = {"2s": 0, "4s": 1, "bf": 2, "bl": 3, "g77": 4, "n79": 5, "zq": 6, "zq_pa": 7}
 
 _pd = C.c_void_p  # double* / int32_t* carried as raw addresses (device or host)
 
@@ -88,6 +88,7 @@ PROTOTYPES = {
     "crt1d_solve_g77": (C.c_int, [C.POINTER(Batch), C.POINTER(Out), C.c_void_p]),
     "crt1d_solve_n79": (C.c_int, [C.POINTER(Batch), C.POINTER(Out), C.c_void_p]),
     "crt1d_solve_zq": (C.c_int, [C.POINTER(Batch), C.POINTER(Out), C.c_void_p]),
+    "crt1d_solve_zq_pa": (C.c_int, [C.POINTER(Batch), C.POINTER(Out), C.c_void_p]),
     "crt1d_solve_host": (C.c_int, [C.c_int, C.POINTER(Batch), C.POINTER(Out), C.c_int]),
     "crt1d_release_workspace": (C.c_int, []),
     "crt1d_calc_absorption": (

@@ -24,7 +24,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 const char* scheme_name(int scheme) {
-    static const char* names[CRT1D_N_SCHEMES] = {"2s", "4s", "bf", "bl", "g77", "n79", "zq"};
+    static const char* names[CRT1D_N_SCHEMES] = {"2s", "4s", "bf", "bl", "g77", "n79", "zq", "zq_pa"};
     return (scheme >= 0 && scheme < CRT1D_N_SCHEMES) ? names[scheme] : "?";
 }
 
@@ -65,6 +65,7 @@ int validate(int scheme, const crt1d_batch* in, const crt1d_out* out) {
         NEED(tau_i);
         NEED(tau_psi);
     }
+    if (scheme == CRT1D_SCHEME_ZQ_PA) NEED(tau_i);
     if (scheme == CRT1D_SCHEME_BL || scheme == CRT1D_SCHEME_N79) NEED(tau_d_lev);
 #undef NEED
     if (scheme == CRT1D_SCHEME_N79 || scheme == CRT1D_SCHEME_ZQ) {
@@ -177,6 +178,7 @@ int crt1d_solve_bl(const crt1d_batch* in, const crt1d_out* out, void* stream) { 
 int crt1d_solve_g77(const crt1d_batch* in, const crt1d_out* out, void* stream) { return crt1d_solve(CRT1D_SCHEME_G77, in, out, stream); }
 int crt1d_solve_n79(const crt1d_batch* in, const crt1d_out* out, void* stream) { return crt1d_solve(CRT1D_SCHEME_N79, in, out, stream); }
 int crt1d_solve_zq(const crt1d_batch* in, const crt1d_out* out, void* stream) { return crt1d_solve(CRT1D_SCHEME_ZQ, in, out, stream); }
+int crt1d_solve_zq_pa(const crt1d_batch* in, const crt1d_out* out, void* stream) { return crt1d_solve(CRT1D_SCHEME_ZQ_PA, in, out, stream); }
 
 int crt1d_calc_absorption(const crt1d_batch* in, const double* I_dr, const double* I_df_d, const double* I_df_u,
                           const crt1d_absorption_out* out, void* stream) {

@@ -704,6 +704,122 @@ CRT_HD void column_zq(const ScenZq& s, const double* eK, int n_z, const BandIn<V
 }
 
 // =================================================================================================
+// zq_pa  Zhao & Qualls, pyAPES variant   (ref _solve_zq_pa.py:24-418)
+//
+// Same tridiagonal as zq (identical row formulas, ref :195-236 vs _solve_zq.py:113-118), but on a
+// computational grid of M = min(100, n_z) equal-LAI LAYERS (ref :94-100) with per-layer beam
+// transmittance exp(-Kb LAI/M), solved densely by the reference (np.linalg.solve, ref :278) and mapped
+// back to the caller's levels by np.interp (ref :354-361).  One thread per column; the M-grid work
+// arrays (<= 100 layers) live in local memory.  The absorption block of the reference (ref :363-401)
+// does not reach its return value and is not computed.
+// =================================================================================================
+constexpr int ZQPA_MAX_M = 100;
+
+struct ScenZqPa {
+    double inv_mu, cos_psi, Kb, tau_d, LAI;  // tau_d = tau_df_fn(K_b_fn, LAI / M)  (ref :175)
+    int M;
+};
+
+// np.interp(x, xp, fp) for ascending xp[0..n-1] (numpy's rules at and beyond the ends, ref :359-361)
+CRT_HD double interp_np(double x, const double* xp, const double* fp_rev, int n, double dl) {
+    // fp_rev is indexed so that the value at xp[i] is fp_rev[n - 1 - i]
+    if (x < xp[0]) return fp_rev[n - 1];
+    if (x > xp[n - 1]) return fp_rev[0];
+    int j = (int)(x / dl);
+    if (j > n - 1) j = n - 1;
+    if (j < 0) j = 0;
+    while (j > 0 && xp[j] > x) --j;
+    while (j < n - 1 && xp[j + 1] <= x) ++j;
+    if (j == n - 1 || xp[j] == x) return fp_rev[n - 1 - j];
+    const double y0 = fp_rev[n - 1 - j], y1 = fp_rev[n - 2 - j];
+    const double slope = (y1 - y0) / (xp[j + 1] - xp[j]);
+    return slope * (x - xp[j]) + y0;
+}
+
+// lai[j]: the caller's cumulative-LAI levels; eK[j] = exp(-Kb lai[j]); cum[i] (i = 0..M): running sum of
+// LAI/M as np.cumsum produces it (ref :161); eC[i] = exp(-Kb cum[i]).
+template <int VEC, class Out>
+CRT_HD void column_zq_pa(const ScenZqPa& s, const double* lai, const double* eK, const double* cum, const double* eC,
+                         int n_z, const BandIn<VEC>& in, Out& out, double (&absorbed)[VEC]) {
+    const int M = s.M;
+    const double dl = s.LAI / M;
+    const double taub = exp(-s.Kb * dl);                                            // ref :173
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        const double bL = in.leaf_r[v], tLf = in.leaf_t[v], rho = in.soil_r[v];
+        const double alb = bL + tLf;                                                // ref :136
+        const double aL = 1.0 - alb;
+        const double tL = tLf / alb, rL = bL / alb;                                 // ref :142-145
+        const double rb = 0.5 + 0.3334 * (rL - tL) / (rL + tL) * s.cos_psi;         // ref :185
+        const double rd = 2.0 / 3.0 * rL / (rL + tL) + 1.0 / 3.0 * tL / (rL + tL);  // ref :186
+        const double t = s.tau_d, a0 = 1.0 - rho;
+        const ZqRowSet q_mid = zq_rows(rd, aL, t, rd, aL, t, rd, aL, t);
+        const ZqRowSet q_bot = zq_rows(1.0, a0, 0.0, rd, aL, t, rd, aL, t);         // k = 1 (soil below)
+        const ZqRowSet q_top = zq_rows(rd, aL, t, rd, aL, t, 0.0, 0.0, t);          // k = M (rd[M+1] = 0)
+        const ZqRowSet q_one = zq_rows(1.0, a0, 0.0, rd, aL, t, 0.0, 0.0, t);
+        const double cA = rb * (1.0 - taub) * (1.0 - aL);                           // ref :243-256
+        const double cB = (1.0 - taub) * (1.0 - aL) * (1.0 - rb);                   // ref :257-271
+        const double IbSky = in.Idr0[v], IdSky = in.Idf0[v];
+        const double x0 = rho * (eC[M] * IbSky);                                    // C[0] = SoilAlbedo Ib[0]  (ref :241)
+
+        double eA[ZQPA_MAX_M + 1], fA[ZQPA_MAX_M + 1], eB[ZQPA_MAX_M + 1], fB[ZQPA_MAX_M + 1];
+        double SWd[ZQPA_MAX_M + 1], SWu[ZQPA_MAX_M + 1];
+        double e_prev = 0.0, f_prev = x0;
+        for (int k = 1; k <= M; ++k) {  // forward elimination, rows 2k-1 and 2k
+            const ZqRowSet& q = (M == 1) ? q_one : (k == 1 ? q_bot : (k == M ? q_top : q_mid));
+            const double Ib = eC[M + 1 - k] * IbSky;                                // f_sl[k] IbSky  (ref :165-169)
+            const double dA = q.m_lo * cA * Ib, dB = q.m_hi * cB * Ib;
+            const double denA = q.mainA - q.subA * e_prev;
+            eA[k] = q.supA / denA;
+            fA[k] = (dA - q.subA * f_prev) / denA;
+            const double denB = q.mainB - q.subB * eA[k];
+            eB[k] = q.supB / denB;
+            fB[k] = (dB - q.subB * fA[k]) / denB;
+            e_prev = eB[k];
+            f_prev = fB[k];
+        }
+        // back substitution: SWu0[k] = x[2k], SWd0[k] = x[2k+1]; multiple scattering eq. 24/25 (ref :286-345)
+        double SWd0_hi = IdSky;  // x[2M+1]
+        for (int k = M; k >= 1; --k) {
+            const ZqRowSet& q = (M == 1) ? q_one : (k == 1 ? q_bot : (k == M ? q_top : q_mid));
+            const double SWu0_k = fB[k] - eB[k] * SWd0_hi;   // x[2k]
+            const double SWd0_lo = fA[k] - eA[k] * SWu0_k;   // x[2k-1] = SWd0[k-1]
+            // pair (k-1, k): needs SWu0[k-1] -> deferred one step; store what is known now
+            SWd[k] = SWd0_hi;    // temporarily SWd0[k]
+            SWu[k] = SWu0_k;     // temporarily SWu0[k]
+            SWd0_hi = SWd0_lo;
+            (void)q;
+        }
+        SWu[0] = x0;             // SWu0[0] = x[0]
+        SWd[0] = SWd0_hi;        // SWd0[0] (unused by the correction)
+        for (int k = 0; k < M; ++k) {  // D_k couples layers k and k+1: row class of li = k+1
+            const ZqRowSet& q = (M == 1) ? q_one : (k + 1 == 1 ? q_bot : (k + 1 == M ? q_top : q_mid));
+            const double SWd0_k1 = SWd[k + 1], SWu0_k = SWu[k];
+            const double newd = SWd0_k1 / q.m_lo + SWu0_k * q.s_me / q.m_lo;        // eq. 24 (ref :288-312)
+            const double newu = SWu0_k / q.m_lo + SWd0_k1 * q.s_lo / q.m_lo;        // eq. 25 (ref :318-342)
+            SWd[k + 1] = newd;   // SWd0[k+1] is not needed again (pair k+1 uses SWd0[k+2], SWu0[k+1])
+            SWu[k] = newu;       // SWu0[k] is not needed again
+        }
+        SWd[0] = SWd[1];         // ref :313
+        SWu[M] = SWu[M - 1];     // ref :343
+        // back to the caller's levels (ref :350-361) and outputs (ref :403-407)
+        double gnd[3] = {0, 0, 0};
+        for (int j = 0; j < n_z; ++j) {
+            const double dn = interp_np(lai[j], cum, SWd, M + 1, dl);
+            const double up = interp_np(lai[j], cum, SWu, M + 1, dl);
+            const double Idr = IbSky * eK[j];
+            const double F = Idr * s.inv_mu + 2.0 * up + 2.0 * dn;
+            if (j == 0) { gnd[0] = Idr; gnd[1] = dn; gnd[2] = up; }
+            if (j == n_z - 1) absorbed[v] = absorbed_from_ends(Idr, gnd[0], dn, gnd[1], up, gnd[2]);
+            out.st1(F_IDR, j, v, Idr);
+            out.st1(F_DN, j, v, dn);
+            out.st1(F_UP, j, v, up);
+            out.st1(F_F, j, v, F);
+        }
+    }
+}
+
+// =================================================================================================
 // 4s  Tian et al. (2007) four-stream   (ref _solve_4s.py:8-293)
 //
 // The reference integrates  y' = M y + v exp(-kappa x),  y = [R2d, R1d, R1u, R2u]  (ref `eqns` :48-97)

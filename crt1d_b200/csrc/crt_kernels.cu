@@ -47,6 +47,10 @@ struct GlobalOut {
             for (int v = 0; v < VEC; ++v) __stcs(q + v, x[v]);
         }
     }
+    // one column at a time (zq_pa finishes each column before starting the next)
+    __device__ __forceinline__ void st1(int f, int j, int v, double x) const {
+        if (p[f] != nullptr) __stcs(p[f] + (int64_t)j * stride + v, x);
+    }
     // elimination scratch parked in the output arrays: re-read by the same thread during
     // back-substitution -> default (write-back, L2-resident) stores
     __device__ __forceinline__ void st_tmp(int f, int j, const double (&x)[VEC]) const {
@@ -608,6 +612,7 @@ cudaError_t launch_solve(int scheme, const crt1d_batch& in, const crt1d_out& out
         case CRT1D_SCHEME_G77: return launch_vec<CRT1D_SCHEME_G77>(in, out, vec2, stream);
         case CRT1D_SCHEME_N79: return launch_vec<CRT1D_SCHEME_N79>(in, out, vec2, stream);
         case CRT1D_SCHEME_ZQ: return launch_vec<CRT1D_SCHEME_ZQ>(in, out, vec2, stream);
+        case CRT1D_SCHEME_ZQ_PA: return launch_vec<CRT1D_SCHEME_ZQ_PA>(in, out, vec2, stream);
         default: return cudaErrorInvalidValue;
     }
 }

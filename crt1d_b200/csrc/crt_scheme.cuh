@@ -18,6 +18,7 @@ CRT_HD int n_level_tables(int scheme) {
         case CRT1D_SCHEME_G77: return 2;  // L, exp(-k_b L)
         case CRT1D_SCHEME_N79: return 5;  // tbcum, tb, td, fsun, dlai
         case CRT1D_SCHEME_ZQ: return 1;   // exp(-K L)
+        case CRT1D_SCHEME_ZQ_PA: return 5;  // lai, exp(-Kb lai), cum[0..M], exp(-Kb cum[0..M]) (M <= n_z)
         default: return 0;
     }
 }
@@ -40,6 +41,23 @@ CRT_HD void fill_level_tables(const crt1d_batch& in, int64_t s, int j, double* t
         tab[2 * n_z + j] = in.tau_d_lev[(int64_t)in.lai_idx[s] * n_z + j];  // tau_d, _solve_bl.py:35-37 (prologue quadrature)
     } else if constexpr (SCHEME == CRT1D_SCHEME_ZQ) {
         tab[j] = exp(-K_b * Lj);  // S / I_dr0, _solve_zq.py:131
+    } else if constexpr (SCHEME == CRT1D_SCHEME_ZQ_PA) {
+        tab[j] = Lj;
+        tab[n_z + j] = exp(-K_b * Lj);  // f_slo, _solve_zq_pa.py:352
+        if (j == 0) {  // running sum of LAI/M exactly as np.cumsum accumulates it (_solve_zq_pa.py:161)
+            const int M = n_z < ZQPA_MAX_M ? n_z : ZQPA_MAX_M;
+            const double dl = lai[0] / M;
+            double* cum = tab + 2 * n_z;
+            double* eC = cum + (M + 1);
+            double c = 0.0;
+            cum[0] = 0.0;
+            eC[0] = 1.0;
+            for (int i = 1; i <= M; ++i) {
+                c += dl;
+                cum[i] = c;
+                eC[i] = exp(-K_b * c);
+            }
+        }
     } else if constexpr (SCHEME == CRT1D_SCHEME_N79) {
         tab[j] = exp(-K_b * Lj);  // tbcum, _solve_n79.py:46
         if (j < n_z - 1) {
@@ -85,6 +103,15 @@ CRT_HD void solve_column_group(const crt1d_batch& in, int64_t s, const double* t
         ScenN79 sc;
         sc.inv_mu = 1.0 / cos(psi);
         column_n79<VEC>(sc, tab, tab + n_z, tab + 2 * n_z, tab + 3 * n_z, tab + 4 * n_z, n_z, b, out, absorbed);
+    } else if constexpr (SCHEME == CRT1D_SCHEME_ZQ_PA) {
+        ScenZqPa sc;
+        sc.cos_psi = cos(psi);
+        sc.inv_mu = 1.0 / sc.cos_psi;
+        sc.Kb = K_b;
+        sc.tau_d = in.tau_i[s];
+        sc.LAI = L_T;
+        sc.M = n_z < ZQPA_MAX_M ? n_z : ZQPA_MAX_M;
+        column_zq_pa<VEC>(sc, tab, tab + n_z, tab + 2 * n_z, tab + 2 * n_z + sc.M + 1, n_z, b, out, absorbed);
     } else if constexpr (SCHEME == CRT1D_SCHEME_ZQ) {
         ScenZq sc;
         sc.cos_psi = cos(psi);

@@ -65,6 +65,10 @@ def host_prologue(batch: ScenarioBatch, scheme, *, K_b_fn=None, G_fn=None, mu_s=
         pro["tau_psi"] = np.array(
             [_common.tau_b_fn(K_b_fn, p, dm[i]) for p, i in zip(batch.psi, batch.lai_idx)], dtype=np.float64
         )
+    elif scheme == "zq_pa":
+        M = min(100, batch.n_z)  # ref _solve_zq_pa.py:95, :175: one tau_d for every equal-LAI layer
+        td = np.array([_common.tau_df_fn(K_b_fn, row[0] / M) for row in batch.lai_lib])
+        pro["tau_i"] = td[batch.lai_idx]
     elif scheme == "bl":
         pro["tau_d_lev"] = np.array([[_common.tau_df_fn(K_b_fn, L) for L in row] for row in batch.lai_lib])
     elif scheme == "n79":
@@ -144,6 +148,12 @@ class DeviceBatch:
             dl_d = torch.as_tensor(dl).to(self.device)
             td = self._buf(torch, "tau_d_lev", tuple(dl_d.shape))
             _lib.check(lib.crt1d_tau_d(la.family_id, la.param, nq, td.numel(), dl_d.data_ptr(), td.data_ptr(), st))
+        elif self.scheme == "zq_pa":
+            M = min(100, b.n_z)
+            dl_d = torch.as_tensor(np.ascontiguousarray(b.lai_lib[:, 0] / M)).to(self.device)
+            td = torch.empty_like(dl_d)
+            _lib.check(lib.crt1d_tau_d(la.family_id, la.param, int(n_quad), td.numel(), dl_d.data_ptr(), td.data_ptr(), st))
+            self._buf(torch, "tau_i", (S,)).copy_(td[self._t["lai_idx"].long()])
         elif self.scheme == "zq":
             dm = np.array([_common.mean_dlai(row) for row in b.lai_lib])
             dm_d = torch.as_tensor(dm).to(self.device)

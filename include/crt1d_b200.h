@@ -56,7 +56,8 @@ extern "C" {
 #define CRT1D_SCHEME_G77 4  /* Goudriaan (1977)                     crt1d/solvers/_solve_g77.py:7-135  */
 #define CRT1D_SCHEME_N79 5  /* Norman (1979)                        crt1d/solvers/_solve_n79.py:11-200 */
 #define CRT1D_SCHEME_ZQ 6   /* Zhao & Qualls                        crt1d/solvers/_solve_zq.py:13-229  */
-#define CRT1D_N_SCHEMES 7
+#define CRT1D_SCHEME_ZQ_PA 7 /* Zhao & Qualls, pyAPES variant       crt1d/solvers/_solve_zq_pa.py:24-418 */
+#define CRT1D_N_SCHEMES 8
 
 /* leaf-angle families (crt1d/leaf_angle.py:118-202) */
 #define CRT1D_G_SPHERICAL 0
@@ -83,7 +84,8 @@ typedef struct crt1d_batch {
     const double* G;      /* G_fn(psi)                                    (4s: _solve_4s.py:145)            */
     const double* mu_bar; /* int cos/G sin  over the hemisphere           (2s: _solve_2s.py:32)             */
     const double* G_int;  /* [S][2] sector integrals of G over [0,mu_s],[mu_s,1]  (4s: _solve_4s.py:148-149) */
-    const double* tau_i;  /* tau_df_fn(K_b_fn, mean dlai)                 (zq: _solve_zq.py:50-51)          */
+    const double* tau_i;  /* tau_df_fn(K_b_fn, mean dlai)                 (zq: _solve_zq.py:50-51);
+                             zq_pa: tau_df_fn(K_b_fn, LAI / min(100, n_z))  (_solve_zq_pa.py:175)            */
     const double* tau_psi;/* tau_b_fn(K_b_fn, psi, mean dlai)             (zq: _solve_zq.py:52)             */
     const int32_t* lai_idx;  /* row of lai_lib      */
     const int32_t* leaf_idx; /* row of leaf_*_lib   */
@@ -146,6 +148,7 @@ CRT1D_API int crt1d_solve_bl(const crt1d_batch* in, const crt1d_out* out, void* 
 CRT1D_API int crt1d_solve_g77(const crt1d_batch* in, const crt1d_out* out, void* stream); /* replaces solve_g77 _solve_g77.py:7  */
 CRT1D_API int crt1d_solve_n79(const crt1d_batch* in, const crt1d_out* out, void* stream); /* replaces solve_n79 _solve_n79.py:11 */
 CRT1D_API int crt1d_solve_zq(const crt1d_batch* in, const crt1d_out* out, void* stream);  /* replaces solve_zq  _solve_zq.py:13  */
+CRT1D_API int crt1d_solve_zq_pa(const crt1d_batch* in, const crt1d_out* out, void* stream); /* replaces solve_zq_pa _solve_zq_pa.py:24 */
 
 /* ---- solver: host pointers, synchronous (H2D + kernels + D2H inside) ------------------------- */
 CRT1D_API int crt1d_solve_host(int scheme, const crt1d_batch* in_host, const crt1d_out* out_host, int device);

@@ -404,6 +404,83 @@ def solve_zq(*, psi, I_dr0_all, I_df0_all, lai, leaf_t, leaf_r, soil_r, K_b_fn, 
 
 
 # ----------------------------------------------------------------------------------------------
+# zq_pa  Zhao & Qualls, pyAPES variant  (ref solvers/_solve_zq_pa.py:24-418)
+# ----------------------------------------------------------------------------------------------
+def solve_zq_pa(*, psi, I_dr0_all, I_df0_all, lai, clump, leaf_t, leaf_r, soil_r, K_b_fn):
+    """The zq tridiagonal on M = min(100, n_z) equal-LAI layers, interpolated back to `lai`.  Only what
+    reaches the reference's return value is restated (its absorption block, ref :363-401, does not)."""
+    lai = np.asarray(lai, dtype=float)
+    LAI = lai[0]
+    N = lai.size
+    M = int(np.minimum(100, N))  # ref :94-95
+    L = np.ones(M + 2) * LAI / M  # ref :96-100
+    L[0] = L[M + 1] = 0.0
+    Kb = K_b_fn(psi)
+    taud_layer = tau_df_fn(K_b_fn, LAI / M)  # ref :175 (recomputed per band by the reference; band-independent)
+    Lcum_full = np.cumsum(np.flipud(L), 0)  # ref :161
+    f_sl = np.flipud(np.exp(-Kb * Lcum_full))  # ref :165
+    taub = np.exp(-Kb * L)  # ref :173
+    taub[0] = 0.0
+    nb = I_dr0_all.size
+    out = {k: np.zeros((N, nb)) for k in ("I_dr", "I_df_d", "I_df_u", "F")}
+    k = np.arange(1, M + 1)
+    n = 2 * M + 2
+    for ib in range(nb):
+        alb = leaf_r[ib] + leaf_t[ib]
+        aL = np.ones(M + 2) * (1 - alb)
+        tL = np.ones(M + 2) * leaf_t[ib] / alb
+        rL = np.ones(M + 2) * leaf_r[ib] / alb
+        aL[0], tL[0], rL[0] = 1.0 - soil_r[ib], 0.0, 1.0  # soil (ref :148-150)
+        aL[M + 1], tL[M + 1], rL[M + 1] = 0.0, 1.0, 0.0  # transparent atmosphere (ref :153-155)
+        taud = np.full(M + 2, taud_layer)
+        taud[0] = 0.0  # ref :178-179
+        rb = 0.5 + 0.3334 * (rL - tL) / (rL + tL) * np.cos(psi)  # ref :185-186
+        rd = 2.0 / 3.0 * rL / (rL + tL) + 1.0 / 3.0 * tL / (rL + tL)
+        rb[0] = rd[0] = 1.0
+        rb[M + 1] = rd[M + 1] = 0.0
+        Ib = f_sl * I_dr0_all[ib]
+        pen = taud[k] + (1 - taud[k]) * (1 - aL[k]) * (1 - rd[k])
+        s_lo = rd[k - 1] * (1 - aL[k - 1]) * (1 - taud[k - 1])
+        s_me = rd[k] * (1 - aL[k]) * (1 - taud[k])
+        s_hi = rd[k + 1] * (1 - aL[k + 1]) * (1 - taud[k + 1])
+        D_lo = 1 - s_lo * s_me
+        D_hi = 1 - s_me * s_hi
+        ab = np.zeros((3, n))  # LAPACK banded storage of the matrix of ref :195-236
+        ab[1, 0] = ab[1, -1] = 1.0
+        ab[2, 2 * k - 2] = -pen
+        ab[1, 2 * k - 1] = -s_lo * pen
+        ab[0, 2 * k] = D_lo
+        ab[2, 2 * k - 1] = D_hi
+        ab[1, 2 * k] = -s_hi * pen
+        ab[0, 2 * k + 1] = -pen
+        C = np.zeros(n)
+        C[0] = soil_r[ib] * Ib[0]  # ref :241
+        C[2 * k - 1] = D_lo * rb[k] * (1 - taub[k]) * (1 - aL[k]) * Ib[k]  # ref :243-256
+        C[2 * k] = D_hi * (1 - taub[k]) * (1 - aL[k]) * (1 - rb[k]) * Ib[k]  # ref :257-271
+        C[-1] = I_df0_all[ib]
+        SW = solve_banded((1, 1), ab, C)  # ref :278 (dense LAPACK solve there)
+        SWu0, SWd0 = SW[0::2], SW[1::2]
+        kk = np.arange(M)  # pairs (kk, kk+1): eq. 24 / 25 (ref :286-345)
+        D = 1 - rd[kk] * rd[kk + 1] * (1 - aL[kk]) * (1 - taud[kk]) * (1 - aL[kk + 1]) * (1 - taud[kk + 1])
+        SWd = np.zeros(M + 1)
+        SWu = np.zeros(M + 1)
+        SWd[kk + 1] = SWd0[kk + 1] / D + SWu0[kk] * rd[kk + 1] * (1 - aL[kk + 1]) * (1 - taud[kk + 1]) / D
+        SWd[0] = SWd[1]
+        SWu[kk] = SWu0[kk] / D + SWd0[kk + 1] * rd[kk] * (1 - aL[kk]) * (1 - taud[kk]) / D
+        SWu[M] = SWu[M - 1]
+        Lcum = np.flipud(Lcum_full[0:M + 1])  # ref :350
+        X, xi = np.flipud(lai), np.flipud(Lcum)
+        SWdo = np.flipud(np.interp(X, xi, np.flipud(SWd)))  # ref :359-361
+        SWuo = np.flipud(np.interp(X, xi, np.flipud(SWu)))
+        SWbo = np.exp(-Kb * lai) * I_dr0_all[ib]  # ref :352-353
+        out["I_dr"][:, ib] = SWbo
+        out["I_df_u"][:, ib] = SWuo
+        out["I_df_d"][:, ib] = SWdo
+        out["F"][:, ib] = SWbo / np.cos(psi) + 2 * SWuo + 2 * SWdo
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # 4s  Tian et al. (2007) four-stream  (ref solvers/_solve_4s.py:8-293)
 # ----------------------------------------------------------------------------------------------
 def fourstream_system(omega, G_int_1, G_int_2, mu_s, P=1.0):
@@ -557,7 +634,7 @@ def canopy_absorbed_bands(aI, wle, bands=((0.4, 0.7), (0.7, 2.5))):
 
 SOLVERS = {
     "2s": solve_2s, "4s": solve_4s, "bf": solve_bf, "bl": solve_bl, "g77": solve_g77,
-    "n79": solve_n79, "zq": solve_zq,
+    "n79": solve_n79, "zq": solve_zq, "zq_pa": solve_zq_pa,
 }
 ARGS = {
     "2s": ["psi", "I_dr0_all", "I_df0_all", "lai", "leaf_t", "leaf_r", "soil_r", "K_b_fn", "G_fn", "mla"],
@@ -567,6 +644,7 @@ ARGS = {
     "bf": ["psi", "I_dr0_all", "I_df0_all", "lai", "leaf_t", "leaf_r", "soil_r", "K_b_fn"],
     "g77": ["psi", "I_dr0_all", "I_df0_all", "lai", "leaf_t", "leaf_r", "soil_r", "K_b_fn"],
     "n79": ["psi", "I_dr0_all", "I_df0_all", "lai", "leaf_t", "leaf_r", "soil_r", "K_b_fn"],
+    "zq_pa": ["psi", "I_dr0_all", "I_df0_all", "lai", "clump", "leaf_t", "leaf_r", "soil_r", "K_b_fn"],
 }
 
 

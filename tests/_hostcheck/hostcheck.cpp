@@ -21,6 +21,9 @@ struct HostOut {
         if (!p[f]) return;
         for (int v = 0; v < VEC; ++v) p[f][(int64_t)j * stride + v] = x[v];
     }
+    void st1(int f, int j, int v, double x) const {
+        if (p[f]) p[f][(int64_t)j * stride + v] = x;
+    }
     void st_tmp(int f, int j, const double (&x)[VEC]) const { st(f, j, x); }
     void ld_tmp(int f, int j, double (&x)[VEC]) const {
         for (int v = 0; v < VEC; ++v) x[v] = p[f][(int64_t)j * stride + v];
@@ -79,6 +82,7 @@ __attribute__((visibility("default"))) int hostcheck_solve(int scheme, const crt
         case CRT1D_SCHEME_G77: run_vec<CRT1D_SCHEME_G77>(*in, *out, vec); break;
         case CRT1D_SCHEME_N79: run_vec<CRT1D_SCHEME_N79>(*in, *out, vec); break;
         case CRT1D_SCHEME_ZQ: run_vec<CRT1D_SCHEME_ZQ>(*in, *out, vec); break;
+        case CRT1D_SCHEME_ZQ_PA: run_vec<CRT1D_SCHEME_ZQ_PA>(*in, *out, vec); break;
         default: return -1;
     }
     return 0;

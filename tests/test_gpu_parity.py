@@ -16,7 +16,7 @@ from util import variant_case
 
 pytestmark = pytest.mark.gpu
 
-FAST = ("2s", "bf", "bl", "g77", "n79", "zq")
+FAST = ("2s", "bf", "bl", "g77", "n79", "zq", "zq_pa")
 
 
 def _args(scheme, p):
@@ -415,3 +415,23 @@ def test_large_batch_kernels_equal_tile_kernel(mode, cfg, monkeypatch):
     ref = oracle.run("2s", odd.scenario_params(7))
     for k in ("I_df_d", "I_df_u", "F"):
         assert_close_conditioned(b[k][7].cpu().numpy()[None], ref[k][None], RTOL, srel_o[7:8], f"{mode} {cfg} odd oracle {k}")
+
+
+def test_deep_canopy_nz1000():
+    """BASELINE.json configs[4]: n_z = 1000, LAI = 6 -- the 2002-unknown zq tridiagonal, n79, the closed
+    forms, and 4s (vs the tight-tolerance oracle) through the plugin API."""
+    import crt1d_b200 as crt
+    from test_hostmath import _deep_case
+
+    q = _deep_case()
+    for scheme in ("2s", "bf", "g77", "zq", "zq_pa", "n79"):
+        kw = {"tau_d_method": "9sky"} if scheme == "n79" else {}
+        ref = oracle.run(scheme, q, **kw)
+        sol = crt.solvers.AVAILABLE_SCHEMES[scheme]["solver"](**_args(scheme, q), **kw)
+        for k in ref:
+            assert_close(sol[k], ref[k], 1e-9 if scheme in ("zq", "n79", "zq_pa") else RTOL, f"deep {scheme}.{k}")
+    q2 = {k: (v[:2].copy() if isinstance(v, np.ndarray) and v.shape == (6,) else v) for k, v in q.items()}
+    ref = oracle.solve_4s_tight(**{k: q2[k] for k in oracle.ARGS["4s"]})
+    sol = crt.solvers.solve_4s(**_args("4s", q2))
+    for k in ref:
+        assert_close_4s(sol[k], ref[k], f"deep 4s.{k}")

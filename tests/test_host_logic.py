@@ -17,6 +17,7 @@ REF_SIGNATURES = {  # ref crt1d/solvers/_solve_<id>.py
     "bf": (["psi", "I_dr0_all", "I_df0_all", "lai", "leaf_t", "leaf_r", "soil_r", "K_b_fn"], []),
     "g77": (["psi", "I_dr0_all", "I_df0_all", "lai", "leaf_t", "leaf_r", "soil_r", "K_b_fn"], []),
     "n79": (["psi", "I_dr0_all", "I_df0_all", "lai", "leaf_t", "leaf_r", "soil_r", "K_b_fn"], ["tau_d_method"]),
+    "zq_pa": (["psi", "I_dr0_all", "I_df0_all", "lai", "clump", "leaf_t", "leaf_r", "soil_r", "K_b_fn"], []),
 }
 
 
@@ -42,7 +43,7 @@ def test_registry_has_reference_structure():
 def test_register_into_foreign_registry():
     target = {"2s": {"name": "2s"}}
     added = crt.solvers.register_cuda_schemes(target)
-    assert "2s_cuda" in target and target["2s"] == {"name": "2s"} and len(added) == 7
+    assert "2s_cuda" in target and target["2s"] == {"name": "2s"} and len(added) == 8
     assert target["zq_cuda"]["solver"] is crt.solvers.solve_zq and target["zq_cuda"]["name"] == "zq_cuda"
     with pytest.raises(KeyError):
         crt.solvers.register_cuda_schemes(target)

@@ -16,7 +16,7 @@ from util import assert_close_4s
 from util import golden
 from util import variant_case
 
-SCHEMES = ("2s", "bf", "bl", "g77", "n79", "zq")
+SCHEMES = ("2s", "bf", "bl", "g77", "n79", "zq", "zq_pa")
 
 
 def _solve(p, scheme, vec=None, **kw):
@@ -130,3 +130,52 @@ def test_leaf_angle_device_functions():
     assert abs(L.hostcheck_leaf_integral(la.family_id, la.param, 0.501, 32, 0) - common.mu_bar_fn(la.G_fn)) < 1e-13
     assert abs(L.hostcheck_leaf_integral(la.family_id, la.param, 0.501, 32, 1) - g1) < 1e-13
     assert abs(L.hostcheck_leaf_integral(la.family_id, la.param, 0.501, 32, 2) - g2) < 1e-13
+
+
+def _deep_case(n_bands=6):
+    """BASELINE.json configs[4]: deep canopy, n_z = 1000, LAI = 6 (SURVEY.md section 8d cfg 5)."""
+    from crt1d_b200 import cases
+    from util import with_callables
+
+    q = dict(cases.load_default_case(1000))
+    q["lai"] = np.linspace(1, 0, 1000) * 6.0
+    step = 107 // n_bands
+    for k in ("leaf_t", "leaf_r", "soil_r", "I_dr0_all", "I_df0_all", "wl", "dwl", "wl_leafsoil"):
+        q[k] = q[k][::step][:n_bands].copy()
+    return with_callables(q)
+
+
+def test_kernel_math_deep_canopy_nz1000():
+    q = _deep_case()
+    for scheme in ("2s", "bf", "g77", "zq", "zq_pa", "n79"):
+        kw = {"tau_d_method": "9sky"} if scheme == "n79" else {}  # 999 quad calls are slow; 9sky is exact to compare
+        ref = oracle.run(scheme, q, **kw)
+        sol = _solve(q, scheme, **kw)
+        for k in ref:
+            # 2 x 1000 unknowns per tridiagonal column: rounding accumulates over the sweep
+            assert_close(sol[k], ref[k], 1e-9 if scheme in ("zq", "n79", "zq_pa") else RTOL, f"deep {scheme}.{k}")
+    q2 = {k: (v[:2].copy() if isinstance(v, np.ndarray) and v.shape == (6,) else v) for k, v in q.items()}
+    ref = oracle.solve_4s_tight(**{k: q2[k] for k in oracle.ARGS["4s"]})
+    sol = _solve(q2, "4s")
+    for k in ref:
+        assert_close_4s(sol[k], ref[k], f"deep 4s.{k}")
+
+
+def test_exp_pm_accuracy():
+    """exp_pm (shared-range-reduction e^-x, e^+x used by every level sweep) vs numpy: <= 2 ulp on [0, 700]."""
+    import ctypes as C
+
+    L = hostcheck.lib()
+    L.hostcheck_exp_pm.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(0, 30, 400000), rng.uniform(0, 700, 100000),
+                        [0.0, 1e-300, 1e-17, 0.34657359027997264, 0.3465735902799727, 699.999, 700.0]])
+    em, ep = np.empty_like(x), np.empty_like(x)
+    L.hostcheck_exp_pm(x.size, x.ctypes.data, em.ctypes.data, ep.ctypes.data)
+    assert np.max(np.abs(em - np.exp(-x)) / np.exp(-x)) < 4.5e-16
+    assert np.max(np.abs(ep - np.exp(x)) / np.exp(x)) < 4.5e-16
+    big = np.array([700.5, 745.0, 800.0, np.inf])  # beyond the fast path: libm semantics (underflow / overflow)
+    em, ep = np.empty_like(big), np.empty_like(big)
+    L.hostcheck_exp_pm(big.size, big.ctypes.data, em.ctypes.data, ep.ctypes.data)
+    with np.errstate(over="ignore"):
+        assert np.array_equal(em, np.exp(-big)) and np.array_equal(ep, np.exp(big))
