@@ -18,14 +18,7 @@
 
 namespace crt {
 
-#ifndef CRT_BLOCK
-#define CRT_BLOCK 128
-#endif
-#ifndef CRT_MIN_BLOCKS
-#define CRT_MIN_BLOCKS 1
-#endif
-constexpr int BLOCK = CRT_BLOCK;            // threads per CTA = band tile / VEC
-constexpr int MIN_BLOCKS = CRT_MIN_BLOCKS;  // resident CTAs per SM the register allocator must allow
+constexpr int BLOCK = 128;  // threads per CTA of the elementwise kernels (absorption)
 
 // ---------------------------------------------------------------------------------------------
 // global-memory column accessor
@@ -99,11 +92,11 @@ __device__ __forceinline__ void st_vec(double* base, int64_t off, const double (
 // ---------------------------------------------------------------------------------------------
 // the solver kernel
 // ---------------------------------------------------------------------------------------------
-template <int SCHEME, int VEC>
-__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) solve_kernel(const crt1d_batch in, const crt1d_out out, int tiles_per_scen,
-                                                      int tiles_per_cta) {
+template <int SCHEME, int VEC, int BLK, int MINB>
+__global__ void __launch_bounds__(BLK, MINB) solve_kernel(const crt1d_batch in, const crt1d_out out, int tiles_per_scen,
+                                                          int tiles_per_cta) {
     extern __shared__ double tab[];
-    __shared__ double red[BLOCK / 32][4];
+    __shared__ double red[BLK / 32][4];
 
     const int ctas_per_scen = (tiles_per_scen + tiles_per_cta - 1) / tiles_per_cta;
     const int64_t s = blockIdx.x / ctas_per_scen;
@@ -111,7 +104,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) solve_kernel(const crt1d_ba
     const int t1 = min(t0 + tiles_per_cta, tiles_per_scen);
     const int n_z = in.n_z, n_wl = in.n_wl;
 
-    for (int j = threadIdx.x; j < n_z; j += BLOCK) fill_level_tables<SCHEME>(in, s, j, tab);
+    for (int j = threadIdx.x; j < n_z; j += BLK) fill_level_tables<SCHEME>(in, s, j, tab);
     __syncthreads();
 
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -119,7 +112,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) solve_kernel(const crt1d_ba
     const int64_t xprof = (int64_t)extra_rows(SCHEME, n_z) * n_wl;  // ... in an extra-output slot
 
     for (int t = t0; t < t1; ++t) {
-        const int b0 = (t * BLOCK + threadIdx.x) * VEC;
+        const int b0 = (t * BLK + threadIdx.x) * VEC;
         if (b0 >= n_wl) continue;
         const BandIn<VEC> b = load_bands<VEC>(in, s, b0);
         GlobalOut<VEC> o;
@@ -160,33 +153,60 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) solve_kernel(const crt1d_ba
         if (threadIdx.x < out.n_bw) {
             double v = 0.0;
 #pragma unroll
-            for (int w = 0; w < BLOCK / 32; ++w) v += red[w][threadIdx.x];
+            for (int w = 0; w < BLK / 32; ++w) v += red[w][threadIdx.x];
             out.absorbed[s * out.n_bw + threadIdx.x] = v;
         }
     }
 }
 
-template <int SCHEME, int VEC>
+template <int SCHEME, int VEC, int BLK, int MINB>
 static cudaError_t launch_one(const crt1d_batch& in, const crt1d_out& out, cudaStream_t stream) {
-    const int cols = BLOCK * VEC;
+    const int cols = BLK * VEC;
     const int tiles_per_scen = (in.n_wl + cols - 1) / cols;
     const int tiles_per_cta = out.absorbed ? tiles_per_scen : 1;
     const int ctas_per_scen = (tiles_per_scen + tiles_per_cta - 1) / tiles_per_cta;
     const int64_t grid = in.n_scen * ctas_per_scen;
     if (grid <= 0 || grid > 2147483647LL) return cudaErrorInvalidConfiguration;
     const size_t smem = (size_t)n_level_tables(SCHEME) * in.n_z * sizeof(double);
-    auto kern = solve_kernel<SCHEME, VEC>;
+    auto kern = solve_kernel<SCHEME, VEC, BLK, MINB>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    kern<<<(unsigned)grid, BLOCK, smem, stream>>>(in, out, tiles_per_scen, tiles_per_cta);
+    kern<<<(unsigned)grid, BLK, smem, stream>>>(in, out, tiles_per_scen, tiles_per_cta);
     return cudaGetLastError();
+}
+
+// Tile-kernel launch configuration per scheme: (threads per CTA, resident CTAs per SM the register
+// allocator must allow).  Defaults = best of the variant sweep in profiles/; "block,minblocks" in
+// CRT1D_B200_TILE_CFG overrides (tuning experiments): 128,1 | 128,4 | 256,2.
+static int tile_cfg_id(int scheme) {
+    const char* env = getenv("CRT1D_B200_TILE_CFG");
+    if (env) {
+        int b = 0, m = 0;
+        if (sscanf(env, "%d,%d", &b, &m) == 2) return b == 256 ? 2 : (m >= 4 ? 1 : 0);
+    }
+    switch (scheme) {  // measured: profiles/r01_tile_kernel_config_all_schemes.txt
+        case CRT1D_SCHEME_2S:   // 256-thread tiles write 4 KB row fragments: +7 % (0.79 -> 0.85 of HBM peak)
+        case CRT1D_SCHEME_BL:   // +9 %  (0.80 -> 0.87)
+        case CRT1D_SCHEME_BF:   // +3.5 %
+        case CRT1D_SCHEME_G77:  // +3.4 %
+        case CRT1D_SCHEME_4S:   // 176 -> 128 registers and bigger tiles: +26 % (0.51 -> 0.64)
+            return 2;
+        case CRT1D_SCHEME_ZQ:   // 128 registers, 4 CTAs/SM hide the Thomas recurrence latency: +14 %
+        case CRT1D_SCHEME_N79:  // +22 %
+            return 1;
+        default: return 0;      // zq_pa: local-memory bound, insensitive
+    }
 }
 
 template <int SCHEME>
 static cudaError_t launch_vec(const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream) {
-    return vec2 ? launch_one<SCHEME, 2>(in, out, stream) : launch_one<SCHEME, 1>(in, out, stream);
+    switch (tile_cfg_id(SCHEME)) {
+        case 1: return vec2 ? launch_one<SCHEME, 2, 128, 4>(in, out, stream) : launch_one<SCHEME, 1, 128, 4>(in, out, stream);
+        case 2: return vec2 ? launch_one<SCHEME, 2, 256, 2>(in, out, stream) : launch_one<SCHEME, 1, 256, 2>(in, out, stream);
+        default: return vec2 ? launch_one<SCHEME, 2, 128, 1>(in, out, stream) : launch_one<SCHEME, 1, 128, 1>(in, out, stream);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
