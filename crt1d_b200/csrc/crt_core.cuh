@@ -417,7 +417,8 @@ CRT_HD void column_g77(const ScenBf& s, const double* L, const double* eb, int n
 // ref :167-200) is reproduced row for row; the forward-sweep coefficients e, f of the two rows of
 // level j are parked in the four OUTPUT arrays at level j (I_dr <- e_up, F <- e_dn, I_df_u <- f_up,
 // I_df_d <- f_dn) and overwritten with the final values during back-substitution, so the solve needs
-// no scratch memory beyond the arrays it has to write anyway.
+// no scratch memory beyond the arrays it has to write anyway.  (Only the downward row's pair is parked;
+// the upward row's is recomputed from it in the back sweep: half the scratch traffic.)
 // Level tables: tbcum[j] = exp(-K_b L[j]) (n_z), tb[j] = exp(-K_b dlai[j]), td[j] = tau_d(dlai[j]),
 // fsun[j] = exp(-K_b laim[j]), dlai[j]  (all n_z - 1)   (ref :41-59).
 // =================================================================================================
@@ -425,12 +426,21 @@ struct ScenN79 {
     double inv_mu;
 };
 
-CRT_HD void n79_up_row(double td, double tbcum, double tb, double rho, double tau, double Idr0, double& a, double& c,
-                       double& d) {  // ref :101-108 / :122-129
+// Layer coefficients shared by the upward row above a layer and the downward row below it:
+// aiv = fiv = refld - trand^2/refld,  biv = eiv = trand/refld   (ref :85-88, :98-101, :111-114).
+// One reciprocal instead of the reference's two divisions (same algebra; <= 1 ulp apart).
+CRT_HD void n79_layer(double td, double rho, double tau, double& fiv, double& eiv) {
     const double refld = (1.0 - td) * rho;
     const double trand = (1.0 - td) * tau + td;
-    const double fiv = refld - trand * trand / refld;
-    const double eiv = trand / refld;
+    const double ir = 1.0 / refld;
+    eiv = trand * ir;
+    fiv = refld - trand * eiv;
+}
+
+CRT_HD void n79_up_row(double td, double tbcum, double tb, double rho, double tau, double Idr0, double& a, double& c,
+                       double& d) {  // ref :101-108 / :122-129
+    double fiv, eiv;
+    n79_layer(td, rho, tau, fiv, eiv);
     a = -eiv;
     c = -fiv;
     d = Idr0 * tbcum * (1.0 - tb) * (rho - tau * eiv);
@@ -438,71 +448,83 @@ CRT_HD void n79_up_row(double td, double tbcum, double tb, double rho, double ta
 
 CRT_HD void n79_dn_row(double td, double tbcum, double tb, double rho, double tau, double Idr0, double& a, double& c,
                        double& d) {  // ref :85-92 / :111-118
-    const double refld = (1.0 - td) * rho;
-    const double trand = (1.0 - td) * tau + td;
-    const double aiv = refld - trand * trand / refld;
-    const double biv = trand / refld;
+    double aiv, biv;
+    n79_layer(td, rho, tau, aiv, biv);
     a = -aiv;
     c = -biv;
     d = Idr0 * tbcum * (1.0 - tb) * (tau - rho * biv);
 }
 
+// Forward-sweep coefficients of the UPWARD row of level j from those of the downward row of level j-1
+// (e_prev, f_prev); level 0 is the soil row (ref :79-82).  Used identically in both sweeps, so the
+// back-substitution recomputes bit-identical values instead of loading them.
+CRT_HD void n79_up_ef(int j, const double* tbcum, const double* tb, const double* td, double rho, double tau,
+                      double soil_r, double Idr0, double e_prev, double f_prev, double& eu, double& fu) {
+    if (j == 0) {
+        eu = -soil_r;
+        fu = Idr0 * tbcum[0] * soil_r;
+    } else {
+        double a, c, d;
+        n79_up_row(td[j - 1], tbcum[j], tb[j - 1], rho, tau, Idr0, a, c, d);
+        const double r = 1.0 / (1.0 - a * e_prev);  // one reciprocal for both quotients of tdma (ref :186, :191)
+        eu = c * r;
+        fu = (d - a * f_prev) * r;
+    }
+}
+
 template <int VEC, class Out>
 CRT_HD void column_n79(const ScenN79& s, const double* tbcum, const double* tb, const double* td, const double* fsun,
                        const double* dlai, int n_z, const BandIn<VEC>& in, Out& out, double (&absorbed)[VEC]) {
+    // ---- forward sweep (ref tdma :183-192); unit diagonal.  Only the DOWNWARD row's (e, f) of each level
+    // is parked (F <- e_dn, I_df_d <- f_dn): 16 B per layer.band instead of 32.
     double e_prev[VEC], f_prev[VEC];
-    // ---- forward sweep (ref tdma :183-192); unit diagonal b = 1 everywhere
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) e_prev[v] = f_prev[v] = 0.0;
     for (int j = 0; j < n_z; ++j) {
-        double eu[VEC], fu[VEC], ed[VEC], fd[VEC];
+        double ed[VEC], fd[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             const double rho = in.leaf_r[v], tau = in.leaf_t[v], Idr0 = in.Idr0[v];
-            double a, c, d;
-            // upward row 2j
-            if (j == 0) {  // soil: up = albedo * (dn + direct)   (ref :79-82)
-                c = -in.soil_r[v];
-                d = Idr0 * tbcum[0] * in.soil_r[v];
-                eu[v] = c / 1.0;
-                fu[v] = d / 1.0;
-            } else {
-                n79_up_row(td[j - 1], tbcum[j], tb[j - 1], rho, tau, Idr0, a, c, d);
-                const double den = 1.0 - a * e_prev[v];
-                eu[v] = c / den;
-                fu[v] = (d - a * f_prev[v]) / den;
-            }
-            // downward row 2j+1
+            double eu, fu;
+            n79_up_ef(j, tbcum, tb, td, rho, tau, in.soil_r[v], Idr0, e_prev[v], f_prev[v], eu, fu);
             if (j == n_z - 1) {  // top boundary: dn = sky diffuse   (ref :132-135); a = c = 0
                 ed[v] = 0.0;
                 fd[v] = in.Idf0[v];
             } else {
                 const int q = (j == 0) ? 1 : j;  // the soil row uses index 1 as shipped (ref :85-92)
+                double a, c, d;
                 n79_dn_row(td[q], tbcum[q + 1 - (j == 0 ? 1 : 0)], tb[q], rho, tau, Idr0, a, c, d);
-                const double den = 1.0 - a * eu[v];
-                ed[v] = c / den;
-                fd[v] = (d - a * fu[v]) / den;
+                const double r = 1.0 / (1.0 - a * eu);
+                ed[v] = c * r;
+                fd[v] = (d - a * fu) * r;
             }
             e_prev[v] = ed[v];
             f_prev[v] = fd[v];
         }
-        out.st_tmp(F_IDR, j, eu);
-        out.st_tmp(F_UP, j, fu);
         out.st_tmp(F_F, j, ed);
         out.st_tmp(F_DN, j, fd);
     }
     // ---- back substitution (ref tdma :195-198) fused with the output stage (ref :141-161)
-    double up_above[VEC], dn_above[VEC], top[VEC][3];
+    double up_above[VEC], dn_above[VEC], top[VEC][3], ed[VEC], fd[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) up_above[v] = dn_above[v] = 0.0;
+    out.ld_tmp(F_F, n_z - 1, ed);
+    out.ld_tmp(F_DN, n_z - 1, fd);
     for (int j = n_z - 1; j >= 0; --j) {
-        double eu[VEC], fu[VEC], ed[VEC], fd[VEC], Idr[VEC], dn[VEC], up[VEC], F[VEC];
-        out.ld_tmp(F_IDR, j, eu);
-        out.ld_tmp(F_UP, j, fu);
-        out.ld_tmp(F_F, j, ed);
-        out.ld_tmp(F_DN, j, fd);
+        double edl[VEC], fdl[VEC], Idr[VEC], dn[VEC], up[VEC], F[VEC];  // (e, f) of the level below
+        if (j > 0) {
+            out.ld_tmp(F_F, j - 1, edl);
+            out.ld_tmp(F_DN, j - 1, fdl);
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) edl[v] = fdl[v] = 0.0;
+        }
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
+            double eu, fu;
+            n79_up_ef(j, tbcum, tb, td, in.leaf_r[v], in.leaf_t[v], in.soil_r[v], in.Idr0[v], edl[v], fdl[v], eu, fu);
             dn[v] = (j == n_z - 1) ? fd[v] : fd[v] - ed[v] * up_above[v];
-            up[v] = fu[v] - eu[v] * dn[v];
+            up[v] = fu - eu * dn[v];
             Idr[v] = in.Idr0[v] * tbcum[j];                                  // ref :151
             F[v] = Idr[v] * s.inv_mu + 2.0 * dn[v] + 2.0 * up[v];            // ref :161
         }
@@ -527,6 +549,8 @@ CRT_HD void column_n79(const ScenN79& s, const double* tbcum, const double* tb, 
             if (j == 0) absorbed[v] = absorbed_from_ends(top[v][0], Idr[v], top[v][1], dn[v], top[v][2], up[v]);
             up_above[v] = up[v];
             dn_above[v] = dn[v];
+            ed[v] = edl[v];
+            fd[v] = fdl[v];
         }
         out.st(F_IDR, j, Idr);
         out.st(F_DN, j, dn);
@@ -550,7 +574,7 @@ struct ScenZq {
 };
 
 struct ZqRowSet {  // coefficients of rows 2li-1 ("A") and 2li ("B") for one li class
-    double subA, mainA, supA, subB, mainB, supB, m_lo, m_hi, s_lo, s_me;
+    double subA, mainA, supA, subB, mainB, supB, m_lo, m_hi, s_lo, s_me, inv_m_lo;
 };
 
 CRT_HD ZqRowSet zq_rows(double r_lo, double a_lo, double t_lo, double r_me, double a_me, double t_me, double r_hi,
@@ -562,6 +586,7 @@ CRT_HD ZqRowSet zq_rows(double r_lo, double a_lo, double t_lo, double r_me, doub
     const double s_hi = r_hi * (1.0 - a_hi) * (1.0 - t_hi);
     q.m_lo = 1.0 - q.s_lo * q.s_me;
     q.m_hi = 1.0 - q.s_me * s_hi;
+    q.inv_m_lo = 1.0 / q.m_lo;
     q.subA = -pen;             // A[2li-1, 2li-2]  (ref :113)
     q.mainA = -q.s_lo * pen;   // A[2li-1, 2li-1]  (ref :114)
     q.supA = q.m_lo;           // A[2li-1, 2li]    (ref :115)
@@ -606,19 +631,17 @@ CRT_HD void column_zq(const ScenZq& s, const double* eK, int n_z, const BandIn<V
             const double S = in.Idr0[v] * eK[li - 1];
             const double dA = q.m_lo * cA[v] * S;
             const double dB = q.m_hi * cB[v] * S;
-            const double denA = q.mainA - q.subA * e_prev[v];
-            eA[v] = q.supA / denA;
-            fA[v] = (dA - q.subA * f_prev[v]) / denA;
-            const double denB = q.mainB - q.subB * eA[v];
-            eB[v] = q.supB / denB;
-            fB[v] = (dB - q.subB * fA[v]) / denB;
+            const double rA = 1.0 / (q.mainA - q.subA * e_prev[v]);  // one reciprocal per row
+            eA[v] = q.supA * rA;
+            fA[v] = (dA - q.subA * f_prev[v]) * rA;
+            const double rB = 1.0 / (q.mainB - q.subB * eA[v]);
+            eB[v] = q.supB * rB;
+            fB[v] = (dB - q.subB * fA[v]) * rB;
             e_prev[v] = eB[v];
             f_prev[v] = fB[v];
         }
-        out.st_tmp(F_IDR, li - 1, eA);
-        out.st_tmp(F_UP, li - 1, fA);
-        out.st_tmp(F_F, li - 1, eB);
-        out.st_tmp(F_DN, li - 1, fB);
+        out.st_tmp(F_F, li - 1, eB);   // only row B's pair is parked (16 B per layer.band); row A's is
+        out.st_tmp(F_DN, li - 1, fB);  // recomputed from the level below during back-substitution
     }
     // ---- back substitution + multiple-scattering correction (eq. 24, 25; ref :173-187) + outputs.
     // x[2k] = SWu0[k], x[2k+1] = SWd0[k]; x[2m+1] = I_df0 (last row: sub-diagonal is 0).  Step li knows
@@ -631,17 +654,30 @@ CRT_HD void column_zq(const ScenZq& s, const double* eK, int n_z, const BandIn<V
     double pend_SWd0[VEC];  // SWd0[li+1] = x[2li+3] for the output level j = li finished at step li
 #pragma unroll
     for (int v = 0; v < VEC; ++v) pend_SWd0[v] = 0.0;
+    double eB[VEC], fB[VEC];
+    out.ld_tmp(F_F, m - 1, eB);
+    out.ld_tmp(F_DN, m - 1, fB);
     for (int li = m; li >= 1; --li) {
-        double eA[VEC], fA[VEC], eB[VEC], fB[VEC];
-        out.ld_tmp(F_IDR, li - 1, eA);
-        out.ld_tmp(F_UP, li - 1, fA);
-        out.ld_tmp(F_F, li - 1, eB);
-        out.ld_tmp(F_DN, li - 1, fB);
+        double eBl[VEC], fBl[VEC];  // row B of the level below = the row preceding this level's row A
+        if (li >= 2) {
+            out.ld_tmp(F_F, li - 2, eBl);
+            out.ld_tmp(F_DN, li - 2, fBl);
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { eBl[v] = 0.0; fBl[v] = x0[v]; }
+        }
         double xB[VEC], xA[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
+            const ZqRowSet& q = (m == 1) ? q_one[v] : (li == 1 ? q_bot[v] : (li == m ? q_top[v] : q_mid[v]));
+            const double dA = q.m_lo * cA[v] * (in.Idr0[v] * eK[li - 1]);  // same expressions as the forward sweep
+            const double rA = 1.0 / (q.mainA - q.subA * eBl[v]);
+            const double eA = q.supA * rA;
+            const double fA = (dA - q.subA * fBl[v]) * rA;
             xB[v] = fB[v] - eB[v] * x_next[v];   // x[2li]   = SWu0[li]
-            xA[v] = fA[v] - eA[v] * xB[v];       // x[2li-1] = SWd0[li-1]
+            xA[v] = fA - eA * xB[v];             // x[2li-1] = SWd0[li-1]
+            eB[v] = eBl[v];
+            fB[v] = fBl[v];
         }
         // Now SWu0[li] (xB) is known: finish output level j = li (needs SWu0[li], SWd0[li+1]) -- but
         // level index j runs 0..m-1 with I_df_u[j] = SWu[j], I_df_d[j] = SWd[j+1]; level j=li exists
@@ -653,8 +689,8 @@ CRT_HD void column_zq(const ScenZq& s, const double* eK, int n_z, const BandIn<V
             for (int v = 0; v < VEC; ++v) {
                 const ZqRowSet& q = (j + 1 == m) ? q_top[v] : q_mid[v];  // class of li' = j+1 (>= 2 here)
                 const double SWu0 = xB[v], SWd0 = pend_SWd0[v];
-                dn[v] = SWd0 / q.m_lo + q.s_me * SWu0 / q.m_lo;          // eq. 24 with li' = j+1  (ref :178-180)
-                up[v] = SWu0 / q.m_lo + q.s_lo * SWd0 / q.m_lo;          // eq. 25                 (ref :183-185)
+                dn[v] = (SWd0 + q.s_me * SWu0) * q.inv_m_lo;             // eq. 24 with li' = j+1  (ref :178-180)
+                up[v] = (SWu0 + q.s_lo * SWd0) * q.inv_m_lo;             // eq. 25                 (ref :183-185)
                 dn_ss[v] = SWd0;
                 up_ss[v] = SWu0;
                 Idr[v] = in.Idr0[v] * eK[j];
@@ -683,8 +719,8 @@ CRT_HD void column_zq(const ScenZq& s, const double* eK, int n_z, const BandIn<V
         for (int v = 0; v < VEC; ++v) {
             const ZqRowSet& q = (m == 1) ? q_one[v] : q_bot[v];  // li' = 1
             const double SWu0 = x0[v], SWd0 = pend_SWd0[v];
-            dn[v] = SWd0 / q.m_lo + q.s_me * SWu0 / q.m_lo;
-            up[v] = SWu0 / q.m_lo + q.s_lo * SWd0 / q.m_lo;
+            dn[v] = (SWd0 + q.s_me * SWu0) * q.inv_m_lo;
+            up[v] = (SWu0 + q.s_lo * SWd0) * q.inv_m_lo;
             dn_ss[v] = SWd0;
             up_ss[v] = SWu0;
             Idr[v] = in.Idr0[v] * eK[0];
@@ -762,41 +798,43 @@ CRT_HD void column_zq_pa(const ScenZqPa& s, const double* lai, const double* eK,
         const double IbSky = in.Idr0[v], IdSky = in.Idf0[v];
         const double x0 = rho * (eC[M] * IbSky);                                    // C[0] = SoilAlbedo Ib[0]  (ref :241)
 
-        double eA[ZQPA_MAX_M + 1], fA[ZQPA_MAX_M + 1], eB[ZQPA_MAX_M + 1], fB[ZQPA_MAX_M + 1];
+        double eB[ZQPA_MAX_M + 1], fB[ZQPA_MAX_M + 1];  // forward coefficients of rows 2k (row 2k-1's are recomputed)
         double SWd[ZQPA_MAX_M + 1], SWu[ZQPA_MAX_M + 1];
-        double e_prev = 0.0, f_prev = x0;
+        eB[0] = 0.0;   // row 0: x[0] = x0
+        fB[0] = x0;
         for (int k = 1; k <= M; ++k) {  // forward elimination, rows 2k-1 and 2k
             const ZqRowSet& q = (M == 1) ? q_one : (k == 1 ? q_bot : (k == M ? q_top : q_mid));
             const double Ib = eC[M + 1 - k] * IbSky;                                // f_sl[k] IbSky  (ref :165-169)
             const double dA = q.m_lo * cA * Ib, dB = q.m_hi * cB * Ib;
-            const double denA = q.mainA - q.subA * e_prev;
-            eA[k] = q.supA / denA;
-            fA[k] = (dA - q.subA * f_prev) / denA;
-            const double denB = q.mainB - q.subB * eA[k];
-            eB[k] = q.supB / denB;
-            fB[k] = (dB - q.subB * fA[k]) / denB;
-            e_prev = eB[k];
-            f_prev = fB[k];
+            const double rA = 1.0 / (q.mainA - q.subA * eB[k - 1]);
+            const double eA = q.supA * rA;
+            const double fA = (dA - q.subA * fB[k - 1]) * rA;
+            const double rB = 1.0 / (q.mainB - q.subB * eA);
+            eB[k] = q.supB * rB;
+            fB[k] = (dB - q.subB * fA) * rB;
         }
         // back substitution: SWu0[k] = x[2k], SWd0[k] = x[2k+1]; multiple scattering eq. 24/25 (ref :286-345)
         double SWd0_hi = IdSky;  // x[2M+1]
         for (int k = M; k >= 1; --k) {
             const ZqRowSet& q = (M == 1) ? q_one : (k == 1 ? q_bot : (k == M ? q_top : q_mid));
+            const double Ib = eC[M + 1 - k] * IbSky;
+            const double dA = q.m_lo * cA * Ib;
+            const double rA = 1.0 / (q.mainA - q.subA * eB[k - 1]);   // row 2k-1 again, same expressions
+            const double eA = q.supA * rA;
+            const double fA = (dA - q.subA * fB[k - 1]) * rA;
             const double SWu0_k = fB[k] - eB[k] * SWd0_hi;   // x[2k]
-            const double SWd0_lo = fA[k] - eA[k] * SWu0_k;   // x[2k-1] = SWd0[k-1]
-            // pair (k-1, k): needs SWu0[k-1] -> deferred one step; store what is known now
+            const double SWd0_lo = fA - eA * SWu0_k;         // x[2k-1] = SWd0[k-1]
             SWd[k] = SWd0_hi;    // temporarily SWd0[k]
             SWu[k] = SWu0_k;     // temporarily SWu0[k]
             SWd0_hi = SWd0_lo;
-            (void)q;
         }
         SWu[0] = x0;             // SWu0[0] = x[0]
         SWd[0] = SWd0_hi;        // SWd0[0] (unused by the correction)
         for (int k = 0; k < M; ++k) {  // D_k couples layers k and k+1: row class of li = k+1
             const ZqRowSet& q = (M == 1) ? q_one : (k + 1 == 1 ? q_bot : (k + 1 == M ? q_top : q_mid));
             const double SWd0_k1 = SWd[k + 1], SWu0_k = SWu[k];
-            const double newd = SWd0_k1 / q.m_lo + SWu0_k * q.s_me / q.m_lo;        // eq. 24 (ref :288-312)
-            const double newu = SWu0_k / q.m_lo + SWd0_k1 * q.s_lo / q.m_lo;        // eq. 25 (ref :318-342)
+            const double newd = (SWd0_k1 + SWu0_k * q.s_me) * q.inv_m_lo;           // eq. 24 (ref :288-312)
+            const double newu = (SWu0_k + SWd0_k1 * q.s_lo) * q.inv_m_lo;           // eq. 25 (ref :318-342)
             SWd[k + 1] = newd;   // SWd0[k+1] is not needed again (pair k+1 uses SWd0[k+2], SWu0[k+1])
             SWu[k] = newu;       // SWu0[k] is not needed again
         }

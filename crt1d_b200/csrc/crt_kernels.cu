@@ -422,7 +422,7 @@ size_t solve_shared_bytes(int scheme, int n_z) { return (size_t)n_level_tables(s
 // coefficient phase (fixed thread->column assignment), so it stays deterministic.
 // ---------------------------------------------------------------------------------------------
 template <int VEC, int LV, int MAXT, bool REC>
-__global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batch in, const crt1d_out out) {
+__global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batch in, const crt1d_out out, int dbg) {
     extern __shared__ double sm[];
     __shared__ double red[MAXT / 32][4];
     __shared__ int counter;
@@ -455,7 +455,12 @@ __global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batc
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int c = threadIdx.x; c < n_wl; c += T) {
         const BandIn<1> b = load_bands<1>(in, s, c);
-        const Coef2s k = coef_2s(sc, b.leaf_r[0], b.leaf_t[0], b.soil_r[0], b.Idr0[0], b.Idf0[0]);
+        Coef2s k;
+        if (dbg == 2) {  // timing experiment: skip the coefficient arithmetic
+            k = {b.leaf_r[0], b.leaf_t[0], b.soil_r[0], b.Idr0[0], b.Idf0[0], b.leaf_r[0], b.leaf_t[0], b.Idr0[0]};
+        } else {
+            k = coef_2s(sc, b.leaf_r[0], b.leaf_t[0], b.soil_r[0], b.Idr0[0], b.Idf0[0]);
+        }
         cf[0 * ld + c] = k.h;
         cf[1 * ld + c] = k.Au;
         cf[2 * ld + c] = k.Bu;
@@ -485,7 +490,7 @@ __global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batc
     const int n_lg = (n_z + LV - 1) / LV;
     const int n_items = n_chunks * n_lg;
     const int lane = threadIdx.x & 31;
-    for (;;) {
+    for (; dbg != 1;) {  // dbg == 1: timing experiment, coefficient phase only
         int item = 0;
         if (lane == 0) item = atomicAdd(&counter, 1);
         item = __shfl_sync(0xffffffffu, item, 0);
@@ -573,7 +578,8 @@ static cudaError_t launch_rows_2s_t(const crt1d_batch& in, const crt1d_out& out,
     auto kern = solve_2s_rows_kernel<VEC, LV, MAXT, REC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)in.n_scen, threads, smem, stream>>>(in, out);
+    const char* dbg = getenv("CRT1D_B200_ROWS_DEBUG");  // 1 = coefficient phase only, 2 = sweep phase only (timing experiments)
+    kern<<<(unsigned)in.n_scen, threads, smem, stream>>>(in, out, dbg ? atoi(dbg) : 0);
     return cudaGetLastError();
 }
 
@@ -632,7 +638,7 @@ cudaError_t launch_solve(int scheme, const crt1d_batch& in, const crt1d_out& out
         case CRT1D_SCHEME_G77: return launch_vec<CRT1D_SCHEME_G77>(in, out, vec2, stream);
         case CRT1D_SCHEME_N79: return launch_vec<CRT1D_SCHEME_N79>(in, out, vec2, stream);
         case CRT1D_SCHEME_ZQ: return launch_vec<CRT1D_SCHEME_ZQ>(in, out, vec2, stream);
-        case CRT1D_SCHEME_ZQ_PA: return launch_vec<CRT1D_SCHEME_ZQ_PA>(in, out, vec2, stream);
+        case CRT1D_SCHEME_ZQ_PA: return launch_vec<CRT1D_SCHEME_ZQ_PA>(in, out, false, stream);  // columns are solved one at a time: 8-byte stores coalesce only with VEC = 1
         default: return cudaErrorInvalidValue;
     }
 }
