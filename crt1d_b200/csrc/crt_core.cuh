@@ -239,24 +239,40 @@ struct ScenBl {
     double K_b, inv_mu;
 };
 
-// tables: tau_b[j] = exp(-K_b L[j]) (ref :31), tau_d[j] = tau_df_fn(K_b_fn, L[j]) (ref :35-37)
+struct CoefBl {
+    double Kg, Idr0, Idf0;  // grey-leaf extinction K_b sqrt(1 - omega) (ref :58-62)
+};
+
+CRT_HD CoefBl coef_bl(const ScenBl& s, double r, double t, double Idr0, double Idf0) {
+    CoefBl k;
+    k.Kg = s.K_b * sqrt(1.0 - (t + r));
+    k.Idr0 = Idr0;
+    k.Idf0 = Idf0;
+    return k;
+}
+
+// tb = exp(-K_b L) (ref :31), td = tau_df_fn(K_b_fn, L) (ref :35-37): scenario level tables
+CRT_HD void level_bl(const ScenBl& s, const CoefBl& k, double L, double tb, double td, double& Idr, double& dn,
+                     double& up, double& F) {
+    const double tau_g = exp_neg(k.Kg * L);               // ref :65
+    Idr = k.Idr0 * tb;                                    // ref :69
+    dn = k.Idf0 * td + 0.5 * (k.Idr0 * (tau_g - tb));     // ref :70-79
+    up = 0.0;                                             // ref :87
+    F = Idr * s.inv_mu + 2.0 * dn;                        // ref :90
+}
+
 template <int VEC, class Out>
 CRT_HD void column_bl(const ScenBl& s, const double* L, const double* tau_b, const double* tau_d, int n_z,
                       const BandIn<VEC>& in, Out& out, double (&absorbed)[VEC]) {
-    double Kg[VEC];
+    CoefBl k[VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) Kg[v] = s.K_b * sqrt(1.0 - (in.leaf_t[v] + in.leaf_r[v]));  // ref :58-62
+    for (int v = 0; v < VEC; ++v) k[v] = coef_bl(s, in.leaf_r[v], in.leaf_t[v], in.Idr0[v], in.Idf0[v]);
     double gnd[VEC][2];
     for (int j = 0; j < n_z; ++j) {
-        const double Lj = L[j], tb = tau_b[j], td = tau_d[j];
         double Idr[VEC], dn[VEC], up[VEC], F[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            const double tau_g = exp_neg(Kg[v] * Lj);                                  // ref :65
-            Idr[v] = in.Idr0[v] * tb;                                                  // ref :69
-            dn[v] = in.Idf0[v] * td + 0.5 * (in.Idr0[v] * (tau_g - tb));               // ref :70-79
-            up[v] = 0.0;                                                               // ref :87
-            F[v] = Idr[v] * s.inv_mu + 2.0 * dn[v];                                    // ref :90
+            level_bl(s, k[v], L[j], tau_b[j], tau_d[j], Idr[v], dn[v], up[v], F[v]);
             if (j == 0) { gnd[v][0] = Idr[v]; gnd[v][1] = dn[v]; }
             if (j == n_z - 1) absorbed[v] = absorbed_from_ends(Idr[v], gnd[v][0], dn[v], gnd[v][1], 0.0, 0.0);
         }
@@ -286,128 +302,125 @@ CRT_HD ScenBf scen_bf(double psi, double K_b, double L_T) {
     return s;
 }
 
+// Folded per-band coefficients shared by bf and g77.  Per level both schemes need e^{-k_d L} and
+// e^{-k_d (L_T - L)} = ed0 e^{+k_d L}: one exp_pm.  bf: a1, a2 scale (eb - ed), (eb - ex) (eq. 8, 9);
+// g77: a1 = I_dr0 (1 - rho_c), a2 = -I_dr0 (1 - sigma), kg = k' k_b (eq. 5), adf = I_df0 (1 - rho_c).
 struct CoefBf {
-    double r_l, t_l, k_prime, rho_c, k_d, c1, c2, c3, soil, Idr0, Idf0, one_m_sigma, ed0;
+    double k_d, ed0, adf, Idr0, a1, a2, soil, c1, c2, c3, kg, rho_c;
 };
 
-// band coefficients common to bf and g77 (ref _solve_bf.py:66-81 / _solve_g77.py:54-69)
-CRT_HD CoefBf coef_bf_common(const ScenBf& s, double r_l, double t_l, double Idr0, double Idf0) {
+CRT_HD CoefBf coef_bfg_common(const ScenBf& s, double r_l, double t_l, double Idr0) {
     CoefBf k;
-    k.r_l = r_l;
-    k.t_l = t_l;
     const double sigma = r_l + t_l;
-    k.one_m_sigma = 1.0 - sigma;
-    k.k_prime = sqrt(1.0 - sigma);
-    k.rho_c = ((1.0 - k.k_prime) / (1.0 + k.k_prime)) * (2.0 / (1.0 + 1.6 * s.mu));  // Spitters (1986) eq. 1
-    k.k_d = 0.8 * sqrt(1.0 - sigma);                                                  // B&F eq. 2
-    k.c1 = k.k_d / k.k_prime;                                                         // eq. 14/15 factors
+    const double k_prime = sqrt(1.0 - sigma);                                    // ref _solve_bf.py:69
+    k.rho_c = ((1.0 - k_prime) / (1.0 + k_prime)) * (2.0 / (1.0 + 1.6 * s.mu));  // Spitters (1986) eq. 1 (ref :78)
+    k.k_d = 0.8 * sqrt(1.0 - sigma);                                             // B&F eq. 2 (ref :81)
+    k.c1 = k.k_d / k_prime;                                                      // eq. 14/15 factors (ref :118-130)
     k.c2 = k.k_d / sqrt(1.0 - r_l);
     k.c3 = k.k_d / sqrt(1.0 - t_l);
     k.Idr0 = Idr0;
-    k.Idf0 = Idf0;
     k.ed0 = exp(-k.k_d * s.L_T);
-    k.soil = 0.0;
+    k.kg = k_prime * s.k_b;
+    k.adf = k.a1 = k.a2 = k.soil = 0.0;
     return k;
 }
 
-// eb[j] = exp(-k_b L[j]) is the scenario level table.
-template <int VEC, class Out>
-CRT_HD void column_bf(const ScenBf& s, const double* L, const double* eb, int n_z, const BandIn<VEC>& in, Out& out,
-                      double (&rho_c)[VEC], double (&absorbed)[VEC]) {
+CRT_HD CoefBf coef_bf(const ScenBf& s, double r_l, double t_l, double soil_r, double Idr0, double Idf0) {
+    CoefBf k = coef_bfg_common(s, r_l, t_l, Idr0);
+    k.adf = Idf0;                                                // ref :86 (no (1 - rho_c) factor in bf)
+    k.a1 = Idr0 * t_l / (k.k_d - s.k_b);                         // eq. 8 (ref :97); k_d = k_b is a pole the reference shares
+    k.a2 = Idr0 * r_l / (k.k_d + s.k_b);                         // eq. 9 (ref :101-105)
+    const double I_df_g = k.adf * k.ed0;                         // ground-level values for eq. 11 (ref :114)
+    const double I_sc_d_g = k.a1 * (s.eb0 - k.ed0);
+    k.soil = soil_r * (Idr0 * s.eb0 + I_df_g + I_sc_d_g);
+    return k;
+}
+
+CRT_HD CoefBf coef_g77(const ScenBf& s, double r_l, double t_l, double soil_r, double Idr0, double Idf0) {
+    CoefBf k = coef_bfg_common(s, r_l, t_l, Idr0);
+    k.adf = Idf0 * (1.0 - k.rho_c);                              // ref _solve_g77.py:73
+    k.a1 = Idr0 * (1.0 - k.rho_c);                               // ref :84
+    k.a2 = -Idr0 * (1.0 - (r_l + t_l));                          // ref :84-86
+    const double I_df_g = k.adf * k.ed0;
+    const double I_sc_g = k.a1 * exp(-k.kg * s.L_T) + k.a2 * s.eb0;
+    k.soil = soil_r * (Idr0 * s.eb0 + I_df_g + 0.5 * I_sc_g);    // ref :95
+    return k;
+}
+
+// f = {I_dr, I_df_d, I_df_u, F, aI_lsl, aI_lsh, aI_l}; eb = exp(-k_b L) from the scenario level table
+template <bool G77>
+CRT_HD void level_bfg(const ScenBf& s, const CoefBf& k, double L, double eb, double (&f)[7]) {
+    double ed, ep;                                  // exp(-k_d L), exp(+k_d L)
+    exp_pm(k.k_d * L, ed, ep);
+    const double e2 = k.ed0 * ep;                   // exp(-k_d (L_T - L))   (ref _solve_bf.py:114)
+    const double I_df = k.adf * ed;                 // ref _solve_bf.py:86 / _solve_g77.py:73
+    const double Idr = k.Idr0 * eb;                 // ref :90
+    double I_sc_d, I_sc_u;
+    if (G77) {
+        const double I_sc = k.a1 * exp_neg(k.kg * L) + k.a2 * eb;   // eq. 5 (ref _solve_g77.py:84-86)
+        I_sc_d = 0.5 * I_sc;                                        // ref :89-90
+        I_sc_u = 0.5 * I_sc;
+    } else {
+        I_sc_d = k.a1 * (eb - ed);                                  // eq. 8
+        I_sc_u = k.a2 * (eb - e2 * s.eb0);                          // eq. 9: exp(k_d L - (k_b + k_d) L_T) = e2 eb0
+    }
+    const double I_sr = k.soil * e2;                                // eq. 11
+    const double diff = k.c1 * I_df + k.c2 * I_sc_u + k.c3 * I_sc_d;
+    const double sh = (1.0 - eb) * diff;                            // eq. 14
+    const double sl = eb * (diff + s.k_b * k.Idr0);                 // eq. 15
+    const double dn = I_sc_d + I_df, up = I_sc_u + I_sr;
+    f[0] = Idr;
+    f[1] = dn;
+    f[2] = up;
+    f[3] = Idr * s.inv_mu + 2.0 * up + 2.0 * dn;
+    f[4] = sl;
+    f[5] = sh;
+    f[6] = sl + sh;
+}
+
+template <bool G77, int VEC, class Out>
+CRT_HD void column_bfg(const ScenBf& s, const double* L, const double* eb, int n_z, const BandIn<VEC>& in, Out& out,
+                       double (&rho_c)[VEC], double (&absorbed)[VEC]) {
     CoefBf k[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-        k[v] = coef_bf_common(s, in.leaf_r[v], in.leaf_t[v], in.Idr0[v], in.Idf0[v]);
-        // ground-level values feeding the soil-reflection term (eq. 11, ref :114)
-        const double I_df_g = k[v].Idf0 * k[v].ed0;
-        const double I_sc_d_g = k[v].Idr0 * k[v].t_l * ((s.eb0 - k[v].ed0) / (k[v].k_d - s.k_b));
-        k[v].soil = in.soil_r[v] * (k[v].Idr0 * s.eb0 + I_df_g + I_sc_d_g);
+        k[v] = G77 ? coef_g77(s, in.leaf_r[v], in.leaf_t[v], in.soil_r[v], in.Idr0[v], in.Idf0[v])
+                   : coef_bf(s, in.leaf_r[v], in.leaf_t[v], in.soil_r[v], in.Idr0[v], in.Idf0[v]);
         rho_c[v] = k[v].rho_c;
     }
     double gnd[VEC][3];
     for (int j = 0; j < n_z; ++j) {
-        const double Lj = L[j], ebj = eb[j];
-        double Idr[VEC], dn[VEC], up[VEC], F[VEC], sl[VEC], sh[VEC], tot[VEC];
+        double o[7][VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            double ed, ep;                                               // exp(-k_d L), exp(+k_d L)
-            exp_pm(k[v].k_d * Lj, ed, ep);
-            const double e2 = k[v].ed0 * ep;                             // exp(-k_d (L_T - L))   (ref :114)
-            const double ex = e2 * s.eb0;                                // exp(k_d L - (k_b + k_d) L_T)  (ref :103)
-            const double I_df = k[v].Idf0 * ed;                                                    // ref :86
-            Idr[v] = k[v].Idr0 * ebj;                                                              // ref :90
-            const double I_sc_d = k[v].Idr0 * k[v].t_l * ((ebj - ed) / (k[v].k_d - s.k_b));        // eq. 8, ref :97
-            const double I_sc_u = k[v].Idr0 * k[v].r_l * ((ebj - ex) / (k[v].k_d + s.k_b));        // eq. 9, ref :101-105
-            const double I_sr = k[v].soil * e2;                                                    // eq. 11
-            const double diff = k[v].c1 * I_df + k[v].c2 * I_sc_u + k[v].c3 * I_sc_d;
-            sh[v] = (1.0 - ebj) * diff;                                                            // eq. 14, ref :118-120
-            sl[v] = ebj * (diff + s.k_b * k[v].Idr0);                                              // eq. 15, ref :125-130
-            tot[v] = sl[v] + sh[v];
-            dn[v] = I_sc_d + I_df;
-            up[v] = I_sc_u + I_sr;
-            F[v] = Idr[v] * s.inv_mu + 2.0 * up[v] + 2.0 * dn[v];
-            if (j == 0) { gnd[v][0] = Idr[v]; gnd[v][1] = dn[v]; gnd[v][2] = up[v]; }
-            if (j == n_z - 1) absorbed[v] = absorbed_from_ends(Idr[v], gnd[v][0], dn[v], gnd[v][1], up[v], gnd[v][2]);
+            double f[7];
+            level_bfg<G77>(s, k[v], L[j], eb[j], f);
+#pragma unroll
+            for (int q = 0; q < 7; ++q) o[q][v] = f[q];
+            if (j == 0) { gnd[v][0] = f[0]; gnd[v][1] = f[1]; gnd[v][2] = f[2]; }
+            if (j == n_z - 1) absorbed[v] = absorbed_from_ends(f[0], gnd[v][0], f[1], gnd[v][1], f[2], gnd[v][2]);
         }
-        out.st(F_IDR, j, Idr);
-        out.st(F_DN, j, dn);
-        out.st(F_UP, j, up);
-        out.st(F_F, j, F);
-        out.st(F_X0, j, sl);
-        out.st(F_X1, j, sh);
-        out.st(F_X2, j, tot);
+        out.st(F_IDR, j, o[0]);
+        out.st(F_DN, j, o[1]);
+        out.st(F_UP, j, o[2]);
+        out.st(F_F, j, o[3]);
+        out.st(F_X0, j, o[4]);
+        out.st(F_X1, j, o[5]);
+        out.st(F_X2, j, o[6]);
     }
+}
+
+template <int VEC, class Out>
+CRT_HD void column_bf(const ScenBf& s, const double* L, const double* eb, int n_z, const BandIn<VEC>& in, Out& out,
+                      double (&rho_c)[VEC], double (&absorbed)[VEC]) {
+    column_bfg<false, VEC>(s, L, eb, n_z, in, out, rho_c, absorbed);
 }
 
 template <int VEC, class Out>
 CRT_HD void column_g77(const ScenBf& s, const double* L, const double* eb, int n_z, const BandIn<VEC>& in, Out& out,
                        double (&absorbed)[VEC]) {
-    CoefBf k[VEC];
-    double kg[VEC], a_df[VEC], a_sc[VEC], b_sc[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-        k[v] = coef_bf_common(s, in.leaf_r[v], in.leaf_t[v], in.Idr0[v], in.Idf0[v]);
-        kg[v] = k[v].k_prime * s.k_b;                       // grey-leaf extinction of eq. 5
-        a_df[v] = k[v].Idf0 * (1.0 - k[v].rho_c);           // ref :73
-        a_sc[v] = k[v].Idr0 * (1.0 - k[v].rho_c);           // ref :84
-        b_sc[v] = -k[v].Idr0 * k[v].one_m_sigma;            // ref :84-86
-        const double I_df_g = a_df[v] * k[v].ed0;
-        const double I_sc_g = a_sc[v] * exp(-kg[v] * s.L_T) + b_sc[v] * s.eb0;
-        k[v].soil = in.soil_r[v] * (k[v].Idr0 * s.eb0 + I_df_g + 0.5 * I_sc_g);  // ref :95
-    }
-    double gnd[VEC][3];
-    for (int j = 0; j < n_z; ++j) {
-        const double Lj = L[j], ebj = eb[j];
-        double Idr[VEC], dn[VEC], up[VEC], F[VEC], sl[VEC], sh[VEC], tot[VEC];
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            double ed, ep;                                               // exp(-k_d L), exp(+k_d L)
-            exp_pm(k[v].k_d * Lj, ed, ep);
-            const double eg = exp_neg(kg[v] * Lj);                       // exp(-k' k_b L)
-            const double e2 = k[v].ed0 * ep;                             // exp(-k_d (L_T - L))   (ref :95)
-            const double I_df = a_df[v] * ed;
-            Idr[v] = k[v].Idr0 * ebj;
-            const double I_sc = a_sc[v] * eg + b_sc[v] * ebj;            // eq. 5
-            const double I_sc_d = 0.5 * I_sc, I_sc_u = 0.5 * I_sc;       // ref :89-90
-            const double I_sr = k[v].soil * e2;
-            const double diff = k[v].c1 * I_df + k[v].c2 * I_sc_u + k[v].c3 * I_sc_d;
-            sh[v] = (1.0 - ebj) * diff;
-            sl[v] = ebj * (diff + s.k_b * k[v].Idr0);
-            tot[v] = sl[v] + sh[v];
-            dn[v] = I_sc_d + I_df;
-            up[v] = I_sc_u + I_sr;
-            F[v] = Idr[v] * s.inv_mu + 2.0 * up[v] + 2.0 * dn[v];
-            if (j == 0) { gnd[v][0] = Idr[v]; gnd[v][1] = dn[v]; gnd[v][2] = up[v]; }
-            if (j == n_z - 1) absorbed[v] = absorbed_from_ends(Idr[v], gnd[v][0], dn[v], gnd[v][1], up[v], gnd[v][2]);
-        }
-        out.st(F_IDR, j, Idr);
-        out.st(F_DN, j, dn);
-        out.st(F_UP, j, up);
-        out.st(F_F, j, F);
-        out.st(F_X0, j, sl);
-        out.st(F_X1, j, sh);
-        out.st(F_X2, j, tot);
-    }
+    double rho_c[VEC];
+    column_bfg<true, VEC>(s, L, eb, n_z, in, out, rho_c, absorbed);
 }
 
 // =================================================================================================
@@ -932,7 +945,11 @@ CRT_HD void solve4(double (&A)[4][4], double (&b)[4]) {
 
 // Folded per-band coefficients: I_dn(x) = sum_k dnP[k] e^{-lam_k (LAI-x)} + dnM[k] e^{-lam_k x} + dnK e^{-kappa x}
 struct Coef4s {
-    double lam[2], g[2], dnP[2], dnM[2], upP[2], upM[2], dnK, upK, Idr0;  // g = e^{-lam LAI}
+    // I_dn(x) = sum_k dnP[k] p_k + dnM[k] m_k + dnK e^{-kappa x},  m_k = e^{-lam_k x},  p_k = e^{-lam_k (LAI - x)}.
+    // Fast form (lam[0] > 0): dnP/upP are pre-multiplied by g_k = e^{-lam_k LAI}, so p_k's factor is just e^{+lam_k x},
+    // the other half of the exp_pm that yields m_k.  If lam_0 LAI >= 600 that product could overflow: the
+    // coefficients stay unscaled and lam[0] is stored NEGATED as the flag for direct exponentials.
+    double lam[2], dnP[2], dnM[2], upP[2], upM[2], dnK, upK, Idr0;
 };
 
 CRT_HD Coef4s coef_4s(const Scen4s& s, double r, double t, double rho, double Idr0, double Idf0) {
@@ -979,7 +996,6 @@ CRT_HD Coef4s coef_4s(const Scen4s& s, double r, double t, double rho, double Id
         psi_[i][0] = -k.lam[i] * phi[i][0] / q0;   // (P-Q)^{-1} phi lambda
         psi_[i][1] = -k.lam[i] * phi[i][1] / q1;
         g[i] = exp(-k.lam[i] * s.L_T);
-        k.g[i] = g[i];
     }
     // particular solution of the direct problem: (kappa^2 I - N) s_p = 2 (P-Q) vD
     const double kap = s.kappa, k2 = kap * kap;
@@ -1024,10 +1040,50 @@ CRT_HD Coef4s coef_4s(const Scen4s& s, double r, double t, double rho, double Id
     k.dnK = 2.0 * CRT_PI * mDp;
     k.upK = 2.0 * CRT_PI * (m2 * Up0 + m1 * Up1);
     k.Idr0 = Idr0;
+    if (k.lam[0] * s.L_T < 600.0) {  // lam[0] is the larger eigenvalue
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            k.dnP[i] *= g[i];
+            k.upP[i] *= g[i];
+        }
+    } else {
+        k.lam[0] = -k.lam[0];
+    }
     return k;
 }
 
+// One level of one 4s column from its exponentials m_k = e^{-lam_k x}, p_k = (scaled) e^{-lam_k (LAI - x)}.
+CRT_HD void level_4s_e(const Scen4s& s, const Coef4s& k, double eK, double m0, double p0, double m1, double p1,
+                       double& Idr, double& dn, double& up, double& F) {
+    dn = k.dnK * eK + (k.dnP[0] * p0 + k.dnM[0] * m0) + (k.dnP[1] * p1 + k.dnM[1] * m1);
+    up = k.upK * eK + (k.upP[0] * p0 + k.upM[0] * m0) + (k.upP[1] * p1 + k.upM[1] * m1);
+    Idr = k.Idr0 * eK;                        // ref :284
+    F = Idr * s.inv_mu + 2.0 * up + 2.0 * dn; // ref :290
+}
+
+// One level of one 4s column: x = cumulative LAI of the level, eK = exp(-kappa x)   (ref :246-290)
+CRT_HD void level_4s(const Scen4s& s, const Coef4s& k, double x, double eK, double& Idr, double& dn, double& up,
+                     double& F) {
+    double m0, p0, m1, p1;
+    if (k.lam[0] > 0.0) {
+        exp_pm(k.lam[0] * x, m0, p0);
+        exp_pm(k.lam[1] * x, m1, p1);
+    } else {
+        const double l0 = -k.lam[0], xr = s.L_T - x;
+        m0 = exp(-l0 * x);
+        p0 = exp(-l0 * xr);
+        m1 = exp(-k.lam[1] * x);
+        p1 = exp(-k.lam[1] * xr);
+    }
+    level_4s_e(s, k, eK, m0, p0, m1, p1, Idr, dn, up, F);
+}
+
 // L[j], eK[j] = exp(-kappa L[j]) level tables.
+// 4s is FP64-bound (two exp_pm per level), so on equally spaced levels -- every profile the reference's
+// generators make (ref ../leaf_area.py:82-88) -- the four exponentials are advanced by constant factors
+// e^{+-lam_k dL} and re-anchored with exact exp_pm every LV4 levels (drift <= LV4 ulp).  Spacing is checked
+// per group against the level table; irregular groups and flagged (huge lam LAI) columns take exp_pm.
+constexpr int LV4 = 8;
 template <int VEC, class Out>
 CRT_HD void column_4s(const Scen4s& s, const double* L, const double* eK, int n_z, const BandIn<VEC>& in, Out& out,
                       double (&absorbed)[VEC]) {
@@ -1035,33 +1091,45 @@ CRT_HD void column_4s(const Scen4s& s, const double* L, const double* eK, int n_
 #pragma unroll
     for (int v = 0; v < VEC; ++v) k[v] = coef_4s(s, in.leaf_r[v], in.leaf_t[v], in.soil_r[v], in.Idr0[v], in.Idf0[v]);
     double gnd[VEC][3];
-    for (int j = 0; j < n_z; ++j) {
-        const double x = L[j], xr = s.L_T - L[j], eKj = eK[j];
-        double Idr[VEC], dn[VEC], up[VEC], F[VEC];
+    const double tol = 8.0 * 2.220446049250313e-16 * s.L_T;
+    for (int j0 = 0; j0 < n_z; j0 += LV4) {
+        const int j1 = (j0 + LV4 < n_z) ? j0 + LV4 : n_z;
+        bool uniform = (j1 - j0) >= 3;
+        const double dL = (j1 - j0) >= 2 ? L[j0] - L[j0 + 1] : 0.0;
+        for (int j = j0 + 1; j + 1 < j1; ++j) uniform = uniform && fabs((L[j] - L[j + 1]) - dL) <= tol;
+        double m0[VEC], p0[VEC], m1[VEC], p1[VEC], qi0[VEC], qd0[VEC], qi1[VEC], qd1[VEC];
+        bool rec[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            // m_i = e^{-lam_i x},  p_i = e^{-lam_i (LAI - x)} = e^{-lam_i LAI} e^{+lam_i x}
-            double m0, p0, m1, p1;
-            if (k[v].lam[0] * s.L_T < 600.0) {  // lam[0] is the larger eigenvalue; product form cannot overflow
-                exp_pm(k[v].lam[0] * x, m0, p0);
-                exp_pm(k[v].lam[1] * x, m1, p1);
-                p0 *= k[v].g[0];
-                p1 *= k[v].g[1];
-            } else {
-                m0 = exp(-k[v].lam[0] * x); p0 = exp(-k[v].lam[0] * xr);
-                m1 = exp(-k[v].lam[1] * x); p1 = exp(-k[v].lam[1] * xr);
+            rec[v] = uniform && k[v].lam[0] > 0.0;
+            if (rec[v]) {
+                exp_pm(k[v].lam[0] * L[j0], m0[v], p0[v]);
+                exp_pm(k[v].lam[1] * L[j0], m1[v], p1[v]);
+                exp_pm(k[v].lam[0] * dL, qd0[v], qi0[v]);  // x shrinks by dL per level: m grows, p decays
+                exp_pm(k[v].lam[1] * dL, qd1[v], qi1[v]);
             }
-            dn[v] = k[v].dnK * eKj + (k[v].dnP[0] * p0 + k[v].dnM[0] * m0) + (k[v].dnP[1] * p1 + k[v].dnM[1] * m1);
-            up[v] = k[v].upK * eKj + (k[v].upP[0] * p0 + k[v].upM[0] * m0) + (k[v].upP[1] * p1 + k[v].upM[1] * m1);
-            Idr[v] = k[v].Idr0 * eKj;                                  // ref :284
-            F[v] = Idr[v] * s.inv_mu + 2.0 * up[v] + 2.0 * dn[v];      // ref :290
-            if (j == 0) { gnd[v][0] = Idr[v]; gnd[v][1] = dn[v]; gnd[v][2] = up[v]; }
-            if (j == n_z - 1) absorbed[v] = absorbed_from_ends(Idr[v], gnd[v][0], dn[v], gnd[v][1], up[v], gnd[v][2]);
         }
-        out.st(F_IDR, j, Idr);
-        out.st(F_DN, j, dn);
-        out.st(F_UP, j, up);
-        out.st(F_F, j, F);
+        for (int j = j0; j < j1; ++j) {
+            double Idr[VEC], dn[VEC], up[VEC], F[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                if (rec[v]) {
+                    level_4s_e(s, k[v], eK[j], m0[v], p0[v], m1[v], p1[v], Idr[v], dn[v], up[v], F[v]);
+                    m0[v] *= qi0[v];
+                    p0[v] *= qd0[v];
+                    m1[v] *= qi1[v];
+                    p1[v] *= qd1[v];
+                } else {
+                    level_4s(s, k[v], L[j], eK[j], Idr[v], dn[v], up[v], F[v]);
+                }
+                if (j == 0) { gnd[v][0] = Idr[v]; gnd[v][1] = dn[v]; gnd[v][2] = up[v]; }
+                if (j == n_z - 1) absorbed[v] = absorbed_from_ends(Idr[v], gnd[v][0], dn[v], gnd[v][1], up[v], gnd[v][2]);
+            }
+            out.st(F_IDR, j, Idr);
+            out.st(F_DN, j, dn);
+            out.st(F_UP, j, up);
+            out.st(F_F, j, F);
+        }
     }
 }
 

@@ -614,6 +614,206 @@ static cudaError_t launch_rows_2s(const crt1d_batch& in, const crt1d_out& out, c
                : launch_rows_2s_t<VEC, 4, 512, false>(in, out, th > 512 ? 512 : th, stream);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Generic row-sweep kernel for the other pattern-bound closed-form schemes (bl, bf, g77; 4s is FP64-bound
+// and gains nothing from it -- measured 0.680 vs 0.684 of HBM peak): same structure as
+// solve_2s_rows_kernel -- one CTA per scenario, folded per-band coefficients in shared memory (I_dr0
+// comes from the spectra library through L1), row-major work items -- without the level recurrence.
+// ---------------------------------------------------------------------------------------------
+template <int SCHEME>
+struct RowsTraits;
+
+template <>
+struct RowsTraits<CRT1D_SCHEME_BL> {
+    static constexpr int NC = 2, NF = 4;
+    using Scen = ScenBl;
+    using Coef = CoefBl;
+    static __device__ __forceinline__ Scen scen(const crt1d_batch& in, int64_t s, const double*) {
+        Scen sc;
+        sc.K_b = in.K_b[s];
+        sc.inv_mu = 1.0 / cos(in.psi[s]);
+        return sc;
+    }
+    static __device__ __forceinline__ Coef coef(const Scen& sc, const BandIn<1>& b) {
+        return coef_bl(sc, b.leaf_r[0], b.leaf_t[0], b.Idr0[0], b.Idf0[0]);
+    }
+    static __device__ __forceinline__ void pack(const Coef& k, double (&a)[NC]) { a[0] = k.Kg; a[1] = k.Idf0; }
+    static __device__ __forceinline__ Coef unpack(const double (&a)[NC], double Idr0) { return {a[0], Idr0, a[1]}; }
+    static __device__ __forceinline__ double rho_c(const Coef&) { return 0.0; }
+    static __device__ __forceinline__ void level(const Scen& sc, const Coef& k, const double* tab, int n_z, int j,
+                                                 double (&f)[NF]) {
+        level_bl(sc, k, tab[j], tab[n_z + j], tab[2 * n_z + j], f[0], f[1], f[2], f[3]);
+    }
+};
+
+template <bool G77>
+struct RowsTraitsBfg {
+    static constexpr int NC = 10, NF = 7;
+    using Scen = ScenBf;
+    using Coef = CoefBf;
+    static __device__ __forceinline__ Scen scen(const crt1d_batch& in, int64_t s, const double* tab) {
+        return scen_bf(in.psi[s], in.K_b[s], tab[0]);
+    }
+    static __device__ __forceinline__ Coef coef(const Scen& sc, const BandIn<1>& b) {
+        return G77 ? coef_g77(sc, b.leaf_r[0], b.leaf_t[0], b.soil_r[0], b.Idr0[0], b.Idf0[0])
+                   : coef_bf(sc, b.leaf_r[0], b.leaf_t[0], b.soil_r[0], b.Idr0[0], b.Idf0[0]);
+    }
+    static __device__ __forceinline__ void pack(const Coef& k, double (&a)[NC]) {
+        a[0] = k.k_d; a[1] = k.ed0; a[2] = k.adf; a[3] = k.a1; a[4] = k.a2;
+        a[5] = k.soil; a[6] = k.c1; a[7] = k.c2; a[8] = k.c3; a[9] = k.kg;
+    }
+    static __device__ __forceinline__ Coef unpack(const double (&a)[NC], double Idr0) {
+        Coef k;
+        k.k_d = a[0]; k.ed0 = a[1]; k.adf = a[2]; k.Idr0 = Idr0; k.a1 = a[3]; k.a2 = a[4];
+        k.soil = a[5]; k.c1 = a[6]; k.c2 = a[7]; k.c3 = a[8]; k.kg = a[9]; k.rho_c = 0.0;
+        return k;
+    }
+    static __device__ __forceinline__ double rho_c(const Coef& k) { return k.rho_c; }
+    static __device__ __forceinline__ void level(const Scen& sc, const Coef& k, const double* tab, int n_z, int j,
+                                                 double (&f)[NF]) {
+        level_bfg<G77>(sc, k, tab[j], tab[n_z + j], f);
+    }
+};
+template <>
+struct RowsTraits<CRT1D_SCHEME_BF> : RowsTraitsBfg<false> {};
+template <>
+struct RowsTraits<CRT1D_SCHEME_G77> : RowsTraitsBfg<true> {};
+
+template <int SCHEME, int VEC, int LV, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) solve_rows_kernel(const crt1d_batch in, const crt1d_out out) {
+    using TR = RowsTraits<SCHEME>;
+    constexpr int NC = TR::NC, NF = TR::NF;
+    extern __shared__ double sm[];
+    __shared__ double red[MAXT / 32][4];
+    __shared__ int counter;
+
+    const int64_t s = blockIdx.x;
+    const int n_z = in.n_z, n_wl = in.n_wl, T = blockDim.x;
+    const int ld = (n_wl + 1) & ~1;
+    const int n_tab = n_level_tables(SCHEME) * n_z;
+    double* cf = sm + n_tab + (n_tab & 1);  // [NC][ld], 16-byte aligned
+
+    for (int j = threadIdx.x; j < n_z; j += T) fill_level_tables<SCHEME>(in, s, j, sm);
+    if (threadIdx.x == 0) counter = 0;
+    __syncthreads();
+
+    // ---- phase B: coefficients -> shared memory; ground/top levels for the absorbed reduction
+    const typename TR::Scen sc = TR::scen(in, s, sm);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int c = threadIdx.x; c < n_wl; c += T) {
+        const BandIn<1> b = load_bands<1>(in, s, c);
+        const typename TR::Coef k = TR::coef(sc, b);
+        double a[NC];
+        TR::pack(k, a);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) cf[i * ld + c] = a[i];
+        if (SCHEME == CRT1D_SCHEME_BF && out.rho_c) out.rho_c[s * n_wl + c] = TR::rho_c(k);
+        if (out.absorbed) {
+            double g[NF], t[NF];
+            TR::level(sc, k, sm, n_z, 0, g);
+            TR::level(sc, k, sm, n_z, n_z - 1, t);
+            const double ab = absorbed_from_ends(t[0], g[0], t[1], g[1], t[2], g[2]);
+            for (int q = 0; q < out.n_bw; ++q) acc[q] += out.band_w[(int64_t)q * n_wl + c] * ab;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: row-major work items (LV levels x 32*VEC bands)
+    const int64_t prof = (int64_t)n_z * n_wl;
+    double* pf[7] = {out.I_dr, out.I_df_d, out.I_df_u, out.F, out.x0, out.x1, out.x2};
+#pragma unroll
+    for (int q = 0; q < 7; ++q) pf[q] = pf[q] ? pf[q] + s * prof : nullptr;
+    const double* idr0 = in.I_dr0_lib + (int64_t)in.sky_idx[s] * n_wl;
+    const int n_grp = n_wl / VEC;
+    const int n_chunks = (n_grp + 31) / 32;
+    const int n_items = n_chunks * ((n_z + LV - 1) / LV);
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(&counter, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const int lg = item / n_chunks, g = (item - lg * n_chunks) * 32 + lane;
+        if (g >= n_grp) continue;
+        const int c0 = g * VEC;
+        typename TR::Coef k[VEC];
+        {
+            double a[VEC][NC];
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                if constexpr (VEC == 2) {
+                    const double2 t = *reinterpret_cast<const double2*>(cf + i * ld + c0);
+                    a[0][i] = t.x;
+                    a[1][i] = t.y;
+                } else {
+                    a[0][i] = cf[i * ld + c0];
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) k[v] = TR::unpack(a[v], __ldg(idr0 + c0 + v));
+        }
+        const int j0 = lg * LV, j1 = min(n_z, j0 + LV);
+        for (int j = j0; j < j1; ++j) {
+            double o[NF][VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                double f[NF];
+                TR::level(sc, k[v], sm, n_z, j, f);
+#pragma unroll
+                for (int q = 0; q < NF; ++q) o[q][v] = f[q];
+            }
+            const int64_t off = (int64_t)j * n_wl + c0;
+#pragma unroll
+            for (int q = 0; q < NF; ++q) st_vec<VEC>(pf[q], off, o[q]);
+        }
+    }
+
+    if (out.absorbed) {  // fixed-order block reduction (deterministic)
+        const int warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            double v = acc[q];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            if (lane == 0) red[warp][q] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < out.n_bw) {
+            double v = 0.0;
+            for (int w = 0; w < (T + 31) / 32; ++w) v += red[w][threadIdx.x];
+            out.absorbed[s * out.n_bw + threadIdx.x] = v;
+        }
+    }
+}
+
+template <int SCHEME>
+static size_t rows_shared_bytes(int n_z, int n_wl) {
+    const int ld = (n_wl + 1) & ~1;
+    const int n_tab = n_level_tables(SCHEME) * n_z;
+    return (size_t)(n_tab + (n_tab & 1) + RowsTraits<SCHEME>::NC * ld) * sizeof(double);
+}
+
+template <int SCHEME, int MAXT>
+static cudaError_t launch_rows(const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream) {
+    const size_t smem = rows_shared_bytes<SCHEME>(in.n_z, in.n_wl);
+    int th = MAXT;
+    const char* env = getenv("CRT1D_B200_ROWS_THREADS");
+    if (env && atoi(env) >= 64 && atoi(env) <= MAXT && atoi(env) % 32 == 0) th = atoi(env);
+    cudaError_t e;
+    if (vec2) {
+        auto kern = solve_rows_kernel<SCHEME, 2, 6, MAXT>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)in.n_scen, th, smem, stream>>>(in, out);
+    } else {
+        auto kern = solve_rows_kernel<SCHEME, 1, 6, MAXT>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)in.n_scen, th, smem, stream>>>(in, out);
+    }
+    return cudaGetLastError();
+}
+
 // Batches with at least this many scenarios go to the scenario-CTA kernel (one CTA per SM needs >= n_SM
 // scenarios in flight); smaller ones (the single-scenario plugin path) use the band-tile kernel.
 static int64_t scen_kernel_min_batch() {
@@ -629,6 +829,21 @@ cudaError_t launch_solve(int scheme, const crt1d_batch& in, const crt1d_out& out
             return vec2 ? launch_rows_2s<2>(in, out, stream) : launch_rows_2s<1>(in, out, stream);
         if (mode != nullptr && mode[0] == 's')
             return vec2 ? launch_scen_cfg<CRT1D_SCHEME_2S, 2>(in, out, stream) : launch_scen_cfg<CRT1D_SCHEME_2S, 1>(in, out, stream);
+    }
+    if (in.n_scen >= scen_kernel_min_batch() && getenv("CRT1D_B200_NO_ROWS") == nullptr) {
+        const size_t cap = 227u * 1024u - 2048u;  // dynamic + static shared memory of one CTA
+        switch (scheme) {
+            case CRT1D_SCHEME_BL:
+                if (rows_shared_bytes<CRT1D_SCHEME_BL>(in.n_z, in.n_wl) <= cap) return launch_rows<CRT1D_SCHEME_BL, 512>(in, out, vec2, stream);
+                break;
+            case CRT1D_SCHEME_BF:
+                if (rows_shared_bytes<CRT1D_SCHEME_BF>(in.n_z, in.n_wl) <= cap) return launch_rows<CRT1D_SCHEME_BF, 512>(in, out, vec2, stream);
+                break;
+            case CRT1D_SCHEME_G77:
+                if (rows_shared_bytes<CRT1D_SCHEME_G77>(in.n_z, in.n_wl) <= cap) return launch_rows<CRT1D_SCHEME_G77, 512>(in, out, vec2, stream);
+                break;
+            default: break;
+        }
     }
     switch (scheme) {
         case CRT1D_SCHEME_2S: return launch_vec<CRT1D_SCHEME_2S>(in, out, vec2, stream);

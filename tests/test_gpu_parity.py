@@ -435,3 +435,56 @@ def test_deep_canopy_nz1000():
     sol = crt.solvers.solve_4s(**_args("4s", q2))
     for k in ref:
         assert_close_4s(sol[k], ref[k], f"deep 4s.{k}")
+
+
+@pytest.mark.parametrize("scheme", ["bl", "bf", "g77"])
+def test_rows_kernel_other_schemes(scheme, monkeypatch):
+    """bl, bf, g77 on batches >= 148 scenarios use the generic row-sweep kernel; it must agree with the
+    band-tile kernel (same coef_/level_ functions, different instantiation) and with the oracle."""
+    import copy
+
+    import torch
+
+    from crt1d_b200 import engine
+    from crt1d_b200 import sweep
+
+    spec = sweep.synthetic_sweep_spec(seed=0)
+    sub = spec.slice(255500, 255500 + 150)
+    bw = np.stack([np.ones(spec.n_wl), np.linspace(0, 1, spec.n_wl)])
+    monkeypatch.setenv("CRT1D_B200_NO_ROWS", "1")
+    a = engine.solve(sub, scheme, band_w=bw)
+    torch.cuda.synchronize()
+    monkeypatch.delenv("CRT1D_B200_NO_ROWS")
+    b = engine.solve(sub, scheme, band_w=bw)
+    torch.cuda.synchronize()
+    for k in a:
+        assert_close(b[k].cpu().numpy(), a[k].cpu().numpy(), 1e-11 if k == "absorbed" else 1e-12, f"rows vs tile {scheme}.{k}",
+                     atol=1e-300)
+    for i in (0, 77, 149):
+        q = sub.scenario_params(i)
+        if scheme == "4s":
+            qs = dict(q)
+            for k in ("leaf_t", "leaf_r", "soil_r", "I_dr0_all", "I_df0_all"):
+                qs[k] = q[k][::300].copy()
+            ref = oracle.solve_4s_tight(**{k: qs[k] for k in oracle.ARGS["4s"]})
+            for k in ("I_dr", "I_df_d", "I_df_u", "F"):
+                assert_close_4s(b[k][i].cpu().numpy()[:, ::300], ref[k], f"rows 4s[{i}].{k}")
+        else:
+            # device Gauss-Legendre tau_d vs host quad for bl (1e-8, see test_batched_equals_plugin_path)
+            ref = oracle.run(scheme, q)
+            for k in ref:
+                if k == "rho_c":
+                    continue
+                assert_close(b[k][i].cpu().numpy(), ref[k], 1e-8 if scheme == "bl" else RTOL, f"rows {scheme}[{i}].{k}", atol=1e-300)
+    # odd band count -> VEC = 1
+    odd = copy.copy(sub)
+    for k in ("leaf_r_lib", "leaf_t_lib", "soil_r_lib", "I_dr0_lib", "I_df0_lib"):
+        setattr(odd, k, np.ascontiguousarray(getattr(sub, k)[:, :401]))
+    odd.wl, odd.dwl = sub.wl[:401], sub.dwl[:401]
+    monkeypatch.setenv("CRT1D_B200_NO_ROWS", "1")
+    a = engine.solve(odd, scheme)
+    monkeypatch.delenv("CRT1D_B200_NO_ROWS")
+    b = engine.solve(odd, scheme)
+    torch.cuda.synchronize()
+    for k in a:
+        assert_close(b[k].cpu().numpy(), a[k].cpu().numpy(), 1e-12, f"rows vs tile odd {scheme}.{k}", atol=1e-300)

@@ -179,3 +179,26 @@ def test_exp_pm_accuracy():
     L.hostcheck_exp_pm(big.size, big.ctypes.data, em.ctypes.data, ep.ctypes.data)
     with np.errstate(over="ignore"):
         assert np.array_equal(em, np.exp(-big)) and np.array_equal(ep, np.exp(big))
+
+
+def test_4s_irregular_levels_and_huge_lai(default_p):
+    """4s paths the default cases never reach: irregularly spaced levels (no recurrence) vs the tight
+    oracle, and lam * LAI >= 600 (unscaled coefficients + direct exponentials): finite, and the boundary
+    conditions of ref _solve_4s.py:99-138 hold (downward diffuse at the top = sky diffuse; upward at the
+    ground = soil reflection of what arrives there)."""
+    sub = {k: (v[::40].copy() if isinstance(v, np.ndarray) and v.shape == (107,) else v) for k, v in default_p.items()}
+    q = dict(sub, lai=np.linspace(1, 0, 37) ** 2 * 5.0)
+    ref = oracle.solve_4s_tight(**{k: q[k] for k in oracle.ARGS["4s"]})
+    sol = _solve(q, "4s")
+    for k in ref:
+        assert_close_4s(sol[k], ref[k], f"irregular 4s.{k}")
+    big = dict(sub, lai=np.linspace(1, 0, 50) * 400.0)
+    sol = _solve(big, "4s")
+    for k in ("I_dr", "I_df_d", "I_df_u", "F"):
+        assert np.all(np.isfinite(sol[k])), k
+    assert_close(sol["I_df_d"][-1], big["I_df0_all"], 1e-9, "top boundary: I_df_d = I_df0")
+    assert_close(sol["I_df_u"][0], big["soil_r"] * (sol["I_df_d"][0] + sol["I_dr"][0]), 1e-9, "soil boundary", atol=1e-300)
+    # moderately deep canopy straddling the switch: same physics from both code paths
+    a = _solve(dict(sub, lai=np.linspace(1, 0, 50) * 300.0), "4s")   # lam0 * LAI < 600 for these bands? checked below
+    b = _solve(dict(sub, lai=np.linspace(1, 0, 50) * 300.0 * (1 + 1e-12)), "4s")
+    assert_close(a["I_df_d"][-5:], b["I_df_d"][-5:], 1e-8, "continuity in LAI")
