@@ -890,6 +890,8 @@ CRT_HD void column_zq_pa(const ScenZqPa& s, const double* lai, const double* eK,
 struct Scen4s {
     double mu0, inv_mu, kappa, L_T, eKT;  // cos psi, 1/cos psi, K_b = G/mu0, total LAI, exp(-kappa L_T)
     double mu_s, m1, m2, G1, G2;          // sector cosine, mu_1, mu_2 (ref :188-189), G sector integrals (ref :148-149)
+    // band-independent reciprocals, hoisted out of the per-band coefficient stage
+    double inv_m1, inv_m2, q0, q1, inv_q0, inv_q1, inv_pi_mu0;
 };
 
 CRT_HD Scen4s scen_4s(double psi, double K_b, double G1, double G2, double mu_s, double L_T) {
@@ -904,12 +906,20 @@ CRT_HD Scen4s scen_4s(double psi, double K_b, double G1, double G2, double mu_s,
     s.m2 = 0.5 * (1.0 - mu_s * mu_s);
     s.G1 = G1;
     s.G2 = G2;
+    s.inv_m1 = 1.0 / s.m1;
+    s.inv_m2 = 1.0 / s.m2;
+    s.q0 = G2 * s.inv_m2;  // -(P - Q) diagonal: k2/mu2, k1/mu1
+    s.q1 = G1 * s.inv_m1;
+    s.inv_q0 = 1.0 / s.q0;
+    s.inv_q1 = 1.0 / s.q1;
+    s.inv_pi_mu0 = 1.0 / (CRT_PI * s.mu0);
     return s;
 }
 
 // 4x4 Gaussian elimination with partial pivoting, written with compare-and-swap so that everything
 // stays in registers on the device.
 CRT_HD void solve4(double (&A)[4][4], double (&b)[4]) {
+    double inv[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
 #pragma unroll
@@ -925,10 +935,10 @@ CRT_HD void solve4(double (&A)[4][4], double (&b)[4]) {
             b[c] = sw ? b[r] : tb;
             b[r] = sw ? tb : b[r];
         }
-        const double inv = 1.0 / A[c][c];
+        inv[c] = 1.0 / A[c][c];
 #pragma unroll
         for (int r = c + 1; r < 4; ++r) {
-            const double f = A[r][c] * inv;
+            const double f = A[r][c] * inv[c];
 #pragma unroll
             for (int k = c + 1; k < 4; ++k) A[r][k] -= f * A[c][k];
             b[r] -= f * b[c];
@@ -939,7 +949,7 @@ CRT_HD void solve4(double (&A)[4][4], double (&b)[4]) {
         double acc = b[r];
 #pragma unroll
         for (int k = r + 1; k < 4; ++k) acc -= A[r][k] * b[k];
-        b[r] = acc / A[r][r];
+        b[r] = acc * inv[r];
     }
 }
 
@@ -954,8 +964,8 @@ struct Coef4s {
 
 CRT_HD Coef4s coef_4s(const Scen4s& s, double r, double t, double rho, double Idr0, double Idf0) {
     const double omega = r + t;                                   // ref :180
-    const double R_dr0 = Idr0 / (CRT_PI * s.mu0);                 // ref :169
-    const double R_df0 = Idf0 / CRT_PI;                           // ref :170
+    const double R_dr0 = Idr0 * s.inv_pi_mu0;                     // I / (pi mu): irradiance -> radiance (ref :169)
+    const double R_df0 = Idf0 * (1.0 / CRT_PI);                   // ref :170
     const double al = 0.5 * omega * (1.0 - s.mu_s) * s.G2;        // alpha_p = alpha_m (ref :190-191), P = 1
     const double be = 0.5 * omega * (1.0 - s.mu_s) * s.G1;        // beta  (ref :192-193)
     const double ga = 0.5 * omega * s.mu_s * s.G1;                // gamma (ref :194-195)
@@ -963,12 +973,12 @@ CRT_HD Coef4s coef_4s(const Scen4s& s, double r, double t, double rho, double Id
     const double e2 = 0.25 * omega * R_dr0 * (1.0 - s.mu_s);      // eps_2 (ref :198-199)
     const double m1 = s.m1, m2 = s.m2;
     // index 0 <-> sector 2 (|mu| in [mu_s, 1]), index 1 <-> sector 1
-    const double q0 = s.G2 / m2, q1 = s.G1 / m1;                  // -(P - Q) diagonal
-    const double T00 = (2.0 * al - s.G2) / m2, T01 = 2.0 * be / m2;
-    const double T10 = 2.0 * be / m1, T11 = (2.0 * ga - s.G1) / m1;
+    const double q0 = s.q0, q1 = s.q1;                            // -(P - Q) diagonal
+    const double T00 = (2.0 * al - s.G2) * s.inv_m2, T01 = 2.0 * be * s.inv_m2;
+    const double T10 = 2.0 * be * s.inv_m1, T11 = (2.0 * ga - s.G1) * s.inv_m1;
     const double N00 = -q0 * T00, N01 = -q0 * T01, N10 = -q1 * T10, N11 = -q1 * T11;
     const double G = s.kappa * s.mu0;
-    const double vD0 = G * e2 / m2, vD1 = G * e1 / m1;            // forcing of rows 1, 2 (ref :80-87)
+    const double vD0 = G * e2 * s.inv_m2, vD1 = G * e1 * s.inv_m1;  // forcing of rows 1, 2 (ref :80-87)
 
     // eigenpairs of N (real: N01 N10 >= 0)
     const double tr = N00 + N11, dif = N00 - N11;
@@ -993,17 +1003,17 @@ CRT_HD Coef4s coef_4s(const Scen4s& s, double r, double t, double rho, double Id
         phi[i][0] *= nrm;
         phi[i][1] *= nrm;
         k.lam[i] = sqrt(l2[i]);
-        psi_[i][0] = -k.lam[i] * phi[i][0] / q0;   // (P-Q)^{-1} phi lambda
-        psi_[i][1] = -k.lam[i] * phi[i][1] / q1;
+        psi_[i][0] = -k.lam[i] * phi[i][0] * s.inv_q0;   // (P-Q)^{-1} phi lambda
+        psi_[i][1] = -k.lam[i] * phi[i][1] * s.inv_q1;
         g[i] = exp(-k.lam[i] * s.L_T);
     }
     // particular solution of the direct problem: (kappa^2 I - N) s_p = 2 (P-Q) vD
     const double kap = s.kappa, k2 = kap * kap;
     const double B00 = k2 - N00, B01 = -N01, B10 = -N10, B11 = k2 - N11;
     const double r0 = -2.0 * q0 * vD0, r1 = -2.0 * q1 * vD1;
-    const double dB = B00 * B11 - B01 * B10;
-    const double sp0 = (r0 * B11 - B01 * r1) / dB, sp1 = (B00 * r1 - B10 * r0) / dB;
-    const double wp0 = kap * sp0 / q0, wp1 = kap * sp1 / q1;       // (P-Q)^{-1} (-kappa s_p)
+    const double idB = 1.0 / (B00 * B11 - B01 * B10);
+    const double sp0 = (r0 * B11 - B01 * r1) * idB, sp1 = (B00 * r1 - B10 * r0) * idB;
+    const double wp0 = kap * sp0 * s.inv_q0, wp1 = kap * sp1 * s.inv_q1;  // (P-Q)^{-1} (-kappa s_p)
     const double Dp0 = 0.5 * (sp0 + wp0), Dp1 = 0.5 * (sp1 + wp1);
     const double Up0 = 0.5 * (sp0 - wp0), Up1 = 0.5 * (sp1 - wp1);
 

@@ -184,15 +184,16 @@ static int tile_cfg_id(int scheme) {
     const char* env = getenv("CRT1D_B200_TILE_CFG");
     if (env) {
         int b = 0, m = 0;
-        if (sscanf(env, "%d,%d", &b, &m) == 2) return b == 256 ? 2 : (m >= 4 ? 1 : 0);
+        if (sscanf(env, "%d,%d", &b, &m) == 2) return b == 256 ? 2 : (m >= 4 ? 1 : (m == 3 ? 4 : (m == 2 ? 3 : 0)));
     }
     switch (scheme) {  // measured: profiles/r01_tile_kernel_config_all_schemes.txt
         case CRT1D_SCHEME_2S:   // 256-thread tiles write 4 KB row fragments: +7 % (0.79 -> 0.85 of HBM peak)
         case CRT1D_SCHEME_BL:   // +9 %  (0.80 -> 0.87)
         case CRT1D_SCHEME_BF:   // +3.5 %
         case CRT1D_SCHEME_G77:  // +3.4 %
-        case CRT1D_SCHEME_4S:   // 176 -> 128 registers and bigger tiles: +26 % (0.51 -> 0.64)
             return 2;
+        case CRT1D_SCHEME_4S:   // with the level recurrence 4s wants its 212 registers: 0.75 (0.70 when capped at 128)
+            return 0;
         case CRT1D_SCHEME_ZQ:   // 128 registers, 4 CTAs/SM hide the Thomas recurrence latency: +14 %
         case CRT1D_SCHEME_N79:  // +22 %
             return 1;
@@ -205,6 +206,8 @@ static cudaError_t launch_vec(const crt1d_batch& in, const crt1d_out& out, bool 
     switch (tile_cfg_id(SCHEME)) {
         case 1: return vec2 ? launch_one<SCHEME, 2, 128, 4>(in, out, stream) : launch_one<SCHEME, 1, 128, 4>(in, out, stream);
         case 2: return vec2 ? launch_one<SCHEME, 2, 256, 2>(in, out, stream) : launch_one<SCHEME, 1, 256, 2>(in, out, stream);
+        case 3: return vec2 ? launch_one<SCHEME, 2, 128, 2>(in, out, stream) : launch_one<SCHEME, 1, 128, 2>(in, out, stream);
+        case 4: return vec2 ? launch_one<SCHEME, 2, 128, 3>(in, out, stream) : launch_one<SCHEME, 1, 128, 3>(in, out, stream);
         default: return vec2 ? launch_one<SCHEME, 2, 128, 1>(in, out, stream) : launch_one<SCHEME, 1, 128, 1>(in, out, stream);
     }
 }
@@ -822,6 +825,7 @@ static int64_t scen_kernel_min_batch() {
 }
 
 cudaError_t launch_solve(int scheme, const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream) {
+    if (getenv("CRT1D_B200_FORCE_VEC1") != nullptr) vec2 = false;  // tuning experiments
     if (scheme == CRT1D_SCHEME_2S && in.n_scen >= scen_kernel_min_batch()) {
         const char* mode = getenv("CRT1D_B200_2S_KERNEL");  // "rows" (default) | "scen" | "tile" (tuning / tests)
         const bool rows_fit = rows_2s_shared_bytes(in.n_z, in.n_wl) <= 227u * 1024u;
