@@ -421,9 +421,9 @@ def test_deep_canopy_nz1000():
     """BASELINE.json configs[4]: n_z = 1000, LAI = 6 -- the 2002-unknown zq tridiagonal, n79, the closed
     forms, and 4s (vs the tight-tolerance oracle) through the plugin API."""
     import crt1d_b200 as crt
-    from test_hostmath import _deep_case
+    from util import deep_case
 
-    q = _deep_case()
+    q = deep_case()
     for scheme in ("2s", "bf", "g77", "zq", "zq_pa", "n79"):
         kw = {"tau_d_method": "9sky"} if scheme == "n79" else {}
         ref = oracle.run(scheme, q, **kw)
@@ -437,9 +437,9 @@ def test_deep_canopy_nz1000():
         assert_close_4s(sol[k], ref[k], f"deep 4s.{k}")
 
 
-@pytest.mark.parametrize("scheme", ["bl", "bf", "g77"])
+@pytest.mark.parametrize("scheme", ["bl", "bf", "g77", "4s"])
 def test_rows_kernel_other_schemes(scheme, monkeypatch):
-    """bl, bf, g77 on batches >= 148 scenarios use the generic row-sweep kernel; it must agree with the
+    """bl, bf, g77, 4s on batches >= 148 scenarios use the generic row-sweep kernel; it must agree with the
     band-tile kernel (same coef_/level_ functions, different instantiation) and with the oracle."""
     import copy
 
@@ -457,9 +457,11 @@ def test_rows_kernel_other_schemes(scheme, monkeypatch):
     monkeypatch.delenv("CRT1D_B200_NO_ROWS")
     b = engine.solve(sub, scheme, band_w=bw)
     torch.cuda.synchronize()
+    # 4s: the 4x4 boundary solve amplifies FMA-contraction differences between instantiations (~1e-11 seen)
+    tol = 1e-9 if scheme == "4s" else 1e-12
     for k in a:
-        assert_close(b[k].cpu().numpy(), a[k].cpu().numpy(), 1e-11 if k == "absorbed" else 1e-12, f"rows vs tile {scheme}.{k}",
-                     atol=1e-300)
+        assert_close(b[k].cpu().numpy(), a[k].cpu().numpy(), max(tol, 1e-11) if k == "absorbed" else tol,
+                     f"rows vs tile {scheme}.{k}", atol=1e-300)
     for i in (0, 77, 149):
         q = sub.scenario_params(i)
         if scheme == "4s":
@@ -487,4 +489,4 @@ def test_rows_kernel_other_schemes(scheme, monkeypatch):
     b = engine.solve(odd, scheme)
     torch.cuda.synchronize()
     for k in a:
-        assert_close(b[k].cpu().numpy(), a[k].cpu().numpy(), 1e-12, f"rows vs tile odd {scheme}.{k}", atol=1e-300)
+        assert_close(b[k].cpu().numpy(), a[k].cpu().numpy(), tol, f"rows vs tile odd {scheme}.{k}", atol=1e-300)

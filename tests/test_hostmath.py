@@ -13,6 +13,7 @@ from util import RTOL_4S_TIGHT
 from util import VARIANTS
 from util import assert_close
 from util import assert_close_4s
+from util import deep_case as _deep_case
 from util import golden
 from util import variant_case
 
@@ -130,19 +131,6 @@ def test_leaf_angle_device_functions():
     assert abs(L.hostcheck_leaf_integral(la.family_id, la.param, 0.501, 32, 0) - common.mu_bar_fn(la.G_fn)) < 1e-13
     assert abs(L.hostcheck_leaf_integral(la.family_id, la.param, 0.501, 32, 1) - g1) < 1e-13
     assert abs(L.hostcheck_leaf_integral(la.family_id, la.param, 0.501, 32, 2) - g2) < 1e-13
-
-
-def _deep_case(n_bands=6):
-    """BASELINE.json configs[4]: deep canopy, n_z = 1000, LAI = 6 (SURVEY.md section 8d cfg 5)."""
-    from crt1d_b200 import cases
-    from util import with_callables
-
-    q = dict(cases.load_default_case(1000))
-    q["lai"] = np.linspace(1, 0, 1000) * 6.0
-    step = 107 // n_bands
-    for k in ("leaf_t", "leaf_r", "soil_r", "I_dr0_all", "I_df0_all", "wl", "dwl", "wl_leafsoil"):
-        q[k] = q[k][::step][:n_bands].copy()
-    return with_callables(q)
 
 
 def test_kernel_math_deep_canopy_nz1000():

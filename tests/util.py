@@ -105,3 +105,15 @@ def assert_close_conditioned(x, ref, base_rtol, sigma_rel, what=""):
         i = np.unravel_index(np.argmax(err / tol), err.shape)
         raise AssertionError(f"{what}: rel err {err[i]:.3e} > tol {tol[i[0], 0, i[2]]:.3e} at {i} "
                              f"(sigma_rel {sigma_rel[i[0], i[2]]:.2e}); {bad.sum()} elements out of tolerance")
+
+
+def deep_case(n_bands=6):
+    """BASELINE.json configs[4]: deep canopy, n_z = 1000, LAI = 6 (SURVEY.md section 8d cfg 5)."""
+    from crt1d_b200 import cases
+
+    q = dict(cases.load_default_case(1000))
+    q["lai"] = np.linspace(1, 0, 1000) * 6.0
+    step = 107 // n_bands
+    for k in ("leaf_t", "leaf_r", "soil_r", "I_dr0_all", "I_df0_all", "wl", "dwl", "wl_leafsoil"):
+        q[k] = q[k][::step][:n_bands].copy()
+    return with_callables(q)
