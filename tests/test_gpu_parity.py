@@ -490,3 +490,30 @@ def test_rows_kernel_other_schemes(scheme, monkeypatch):
     torch.cuda.synchronize()
     for k in a:
         assert_close(b[k].cpu().numpy(), a[k].cpu().numpy(), tol, f"rows vs tile odd {scheme}.{k}", atol=1e-300)
+
+
+def test_plain_c_caller(tmp_path, default_p):
+    """The boundary is a C ABI: a plain-C program (gcc, no CUDA headers, no Python) links the library,
+    solves the default case with host buffers and must reproduce the oracle."""
+    import os
+    import struct
+    import subprocess
+
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    exe = tmp_path / "c_abi_example"
+    libdir = os.path.join(root, "crt1d_b200")
+    subprocess.check_call(["gcc", "-O1", "-o", str(exe), os.path.join(root, "tests", "c_abi_example.c"),
+                           "-L" + libdir, "-lcrt1d_b200", "-Wl,-rpath," + libdir])
+    p = default_p
+    nz, nb = p["lai"].size, p["wl"].size
+    with open(tmp_path / "in.bin", "wb") as f:
+        f.write(struct.pack("<ii", nz, nb))
+        f.write(struct.pack("<dddd", p["psi"], p["K_b"], oracle.mu_bar_quad(p["G_fn"]), float(p["mla"])))
+        for k in ("lai", "leaf_r", "leaf_t", "soil_r", "I_dr0_all", "I_df0_all"):
+            f.write(np.ascontiguousarray(p[k], dtype="<f8").tobytes())
+    out = subprocess.check_output([str(exe), str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], text=True)
+    assert out.startswith("ok")
+    res = np.fromfile(tmp_path / "out.bin", dtype="<f8").reshape(4, nz, nb)
+    ref = oracle.run("2s", p)
+    for i, k in enumerate(("I_dr", "I_df_d", "I_df_u", "F")):
+        assert_close(res[i], ref[k], RTOL, f"C caller {k}")
