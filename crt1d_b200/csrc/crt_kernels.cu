@@ -178,235 +178,23 @@ static cudaError_t launch_one(const crt1d_batch& in, const crt1d_out& out, cudaS
 }
 
 // Tile-kernel launch configuration per scheme: (threads per CTA, resident CTAs per SM the register
-// allocator must allow).  Defaults = best of the variant sweep in profiles/; "block,minblocks" in
-// CRT1D_B200_TILE_CFG overrides (tuning experiments): 128,1 | 128,4 | 256,2.
-static int tile_cfg_id(int scheme) {
-    const char* env = getenv("CRT1D_B200_TILE_CFG");
-    if (env) {
-        int b = 0, m = 0;
-        if (sscanf(env, "%d,%d", &b, &m) == 2) return b == 256 ? 2 : (m >= 4 ? 1 : (m == 3 ? 4 : (m == 2 ? 3 : 0)));
-    }
-    switch (scheme) {  // measured: profiles/r01_tile_kernel_config_all_schemes.txt
-        case CRT1D_SCHEME_2S:   // 256-thread tiles write 4 KB row fragments: +7 % (0.79 -> 0.85 of HBM peak)
-        case CRT1D_SCHEME_BL:   // +9 %  (0.80 -> 0.87)
-        case CRT1D_SCHEME_BF:   // +3.5 %
-        case CRT1D_SCHEME_G77:  // +3.4 %
-            return 2;
-        case CRT1D_SCHEME_4S:   // with the level recurrence 4s wants its 212 registers: 0.75 (0.70 when capped at 128)
-            return 0;
-        case CRT1D_SCHEME_ZQ:   // 128 registers, 4 CTAs/SM hide the Thomas recurrence latency: +14 %
-        case CRT1D_SCHEME_N79:  // +22 %
-            return 1;
-        default: return 0;      // zq_pa: local-memory bound, insensitive
-    }
-}
+// allocator must allow), the best of the measured sweep in profiles/r01_tile_kernel_config_all_schemes.txt
+// (128,1 | 128,4 | 256,2 tried for every scheme).  Only the chosen one is compiled.
+template <int SCHEME>
+struct TileCfg {
+    static constexpr int BLK = 128, MINB = 1;  // zq_pa (local-memory bound, insensitive); 4s (wants its 212 registers)
+};
+template <> struct TileCfg<CRT1D_SCHEME_2S> { static constexpr int BLK = 256, MINB = 2; };   // 4 KB row fragments: 0.79 -> 0.85
+template <> struct TileCfg<CRT1D_SCHEME_BL> { static constexpr int BLK = 256, MINB = 2; };   // 0.80 -> 0.87
+template <> struct TileCfg<CRT1D_SCHEME_BF> { static constexpr int BLK = 256, MINB = 2; };   // +3.5 %
+template <> struct TileCfg<CRT1D_SCHEME_G77> { static constexpr int BLK = 256, MINB = 2; };  // +3.4 %
+template <> struct TileCfg<CRT1D_SCHEME_ZQ> { static constexpr int BLK = 128, MINB = 4; };   // 4 CTAs/SM hide the Thomas latency: +14 %
+template <> struct TileCfg<CRT1D_SCHEME_N79> { static constexpr int BLK = 128, MINB = 4; };  // +22 %
 
 template <int SCHEME>
 static cudaError_t launch_vec(const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream) {
-    switch (tile_cfg_id(SCHEME)) {
-        case 1: return vec2 ? launch_one<SCHEME, 2, 128, 4>(in, out, stream) : launch_one<SCHEME, 1, 128, 4>(in, out, stream);
-        case 2: return vec2 ? launch_one<SCHEME, 2, 256, 2>(in, out, stream) : launch_one<SCHEME, 1, 256, 2>(in, out, stream);
-        case 3: return vec2 ? launch_one<SCHEME, 2, 128, 2>(in, out, stream) : launch_one<SCHEME, 1, 128, 2>(in, out, stream);
-        case 4: return vec2 ? launch_one<SCHEME, 2, 128, 3>(in, out, stream) : launch_one<SCHEME, 1, 128, 3>(in, out, stream);
-        default: return vec2 ? launch_one<SCHEME, 2, 128, 1>(in, out, stream) : launch_one<SCHEME, 1, 128, 1>(in, out, stream);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// scenario-CTA kernel: ONE CTA = one whole scenario (all bands, all levels), one resident CTA per SM.
-//
-// Why: the output stream decides the speed of this path, and HBM write efficiency depends on how
-// many distinct rows are "open" at once.  Measured on B200 with a store-only microbenchmark
-// (tools/micro/wbw.cu, profiles/README.md): the tile decomposition above (444 resident CTAs, each
-// walking 2-4 KB row fragments 16.8 KB apart) tops out at 5.1 TB/s no matter how little arithmetic
-// it does, whereas 148 resident CTAs that each sweep complete 16.8 KB band rows, level after level,
-// reach 6.8-7.0 TB/s (a linear memset gets 6.9).  So here every thread owns SLOTS groups of VEC
-// adjacent bands spaced blockDim.x*VEC bands apart; at each level the CTA's warps emit the whole band
-// row of every field back to back.
-// ---------------------------------------------------------------------------------------------
-template <int VEC, int SLOTS>
-struct SplitOut {
-    double* p[N_FIELDS];  // pre-offset to (scenario, level 0, band 0); nullptr = field not requested
-    int64_t stride;       // doubles between levels (= n_wl)
-    int off[SLOTS];       // first band of each slot, or -1 if the slot is past the end of the row
-
-    __device__ __forceinline__ void st(int f, int j, const double (&x)[VEC * SLOTS]) const {
-        double* q = p[f];
-        if (q == nullptr) return;
-        q += (int64_t)j * stride;
-#pragma unroll
-        for (int k = 0; k < SLOTS; ++k) {
-            if (off[k] < 0) continue;
-            if constexpr (VEC == 2) {
-                __stcs(reinterpret_cast<double2*>(q + off[k]), make_double2(x[2 * k], x[2 * k + 1]));
-            } else {
-                __stcs(q + off[k], x[k]);
-            }
-        }
-    }
-    __device__ __forceinline__ void st_tmp(int f, int j, const double (&x)[VEC * SLOTS]) const {
-        double* q = p[f] + (int64_t)j * stride;
-#pragma unroll
-        for (int k = 0; k < SLOTS; ++k) {
-            if (off[k] < 0) continue;
-            if constexpr (VEC == 2) {
-                *reinterpret_cast<double2*>(q + off[k]) = make_double2(x[2 * k], x[2 * k + 1]);
-            } else {
-                q[off[k]] = x[k];
-            }
-        }
-    }
-    __device__ __forceinline__ void ld_tmp(int f, int j, double (&x)[VEC * SLOTS]) const {
-        const double* q = p[f] + (int64_t)j * stride;
-#pragma unroll
-        for (int k = 0; k < SLOTS; ++k) {
-            if (off[k] < 0) {
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) x[k * VEC + v] = 1.0;
-                continue;
-            }
-            if constexpr (VEC == 2) {
-                const double2 t = __ldcs(reinterpret_cast<const double2*>(q + off[k]));
-                x[2 * k] = t.x;
-                x[2 * k + 1] = t.y;
-            } else {
-                x[k] = __ldcs(q + off[k]);
-            }
-        }
-    }
-};
-
-template <int SCHEME, int VEC, int SLOTS, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) solve_scen_kernel(const crt1d_batch in, const crt1d_out out) {
-    extern __shared__ double tab[];
-    __shared__ double red[MAXT / 32][4];
-    constexpr int W = VEC * SLOTS;  // columns per thread per sweep
-
-    const int64_t s = blockIdx.x;
-    const int n_z = in.n_z, n_wl = in.n_wl, T = blockDim.x;
-    for (int j = threadIdx.x; j < n_z; j += T) fill_level_tables<SCHEME>(in, s, j, tab);
-    __syncthreads();
-
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    const int64_t prof = (int64_t)n_z * n_wl;
-    const int64_t xprof = (int64_t)extra_rows(SCHEME, n_z) * n_wl;
-    SplitOut<VEC, SLOTS> o;
-    o.stride = n_wl;
-    o.p[F_IDR] = out.I_dr ? out.I_dr + s * prof : nullptr;
-    o.p[F_DN] = out.I_df_d ? out.I_df_d + s * prof : nullptr;
-    o.p[F_UP] = out.I_df_u ? out.I_df_u + s * prof : nullptr;
-    o.p[F_F] = out.F ? out.F + s * prof : nullptr;
-    o.p[F_X0] = out.x0 ? out.x0 + s * xprof : nullptr;
-    o.p[F_X1] = out.x1 ? out.x1 + s * xprof : nullptr;
-    o.p[F_X2] = out.x2 ? out.x2 + s * xprof : nullptr;
-
-    const int n_grp = n_wl / VEC;  // launcher guarantees n_wl % VEC == 0
-    for (int base = 0; base < n_grp; base += SLOTS * T) {
-        if (base + (int)threadIdx.x >= n_grp) break;  // slot 0 invalid => all slots invalid
-        BandIn<W> b;
-#pragma unroll
-        for (int k = 0; k < SLOTS; ++k) {
-            const int g = base + k * T + threadIdx.x;
-            o.off[k] = g < n_grp ? g * VEC : -1;
-            const BandIn<VEC> bk = load_bands<VEC>(in, s, (g < n_grp ? g : base + (int)threadIdx.x) * VEC);
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                b.leaf_r[k * VEC + v] = bk.leaf_r[v];
-                b.leaf_t[k * VEC + v] = bk.leaf_t[v];
-                b.soil_r[k * VEC + v] = bk.soil_r[v];
-                b.Idr0[k * VEC + v] = bk.Idr0[v];
-                b.Idf0[k * VEC + v] = bk.Idf0[v];
-            }
-        }
-        double rho_c[W], ab[W];
-        solve_column_group<SCHEME, W>(in, s, tab, b, o, rho_c, ab);
-#pragma unroll
-        for (int k = 0; k < SLOTS; ++k) {
-            if (o.off[k] < 0) continue;
-            if constexpr (SCHEME == CRT1D_SCHEME_BF) {
-                if (out.rho_c) {
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) out.rho_c[s * n_wl + o.off[k] + v] = rho_c[k * VEC + v];
-                }
-            }
-            if (out.absorbed) {
-                for (int q = 0; q < out.n_bw; ++q) {
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) acc[q] += out.band_w[(int64_t)q * n_wl + o.off[k] + v] * ab[k * VEC + v];
-                }
-            }
-        }
-    }
-
-    if (out.absorbed) {  // fixed-order block reduction (deterministic)
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            double v = acc[k];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-            if (lane == 0) red[warp][k] = v;
-        }
-        __syncthreads();
-        if (threadIdx.x < out.n_bw) {
-            double v = 0.0;
-            for (int w = 0; w < (T + 31) / 32; ++w) v += red[w][threadIdx.x];
-            out.absorbed[s * out.n_bw + threadIdx.x] = v;
-        }
-    }
-}
-
-template <int SCHEME, int VEC, int SLOTS, int MAXT>
-static cudaError_t launch_scen(const crt1d_batch& in, const crt1d_out& out, int threads, cudaStream_t stream) {
-    if (in.n_scen > 2147483647LL) return cudaErrorInvalidConfiguration;
-    const size_t smem = (size_t)n_level_tables(SCHEME) * in.n_z * sizeof(double);
-    auto kern = solve_scen_kernel<SCHEME, VEC, SLOTS, MAXT>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    kern<<<(unsigned)in.n_scen, threads, smem, stream>>>(in, out);
-    return cudaGetLastError();
-}
-
-// Pick (SLOTS, threads) for the scenario-CTA kernel: cover the n_wl/VEC column groups of a row with as
-// little idle lane time as possible, within the register budget of each instantiation.
-struct ScenCfg {
-    int slots, threads;
-};
-static ScenCfg pick_scen_cfg(int n_grp) {
-    const char* env = getenv("CRT1D_B200_SCEN_CFG");  // "slots,threads" (tuning experiments only)
-    if (env) {
-        int sl = 0, th = 0;
-        if (sscanf(env, "%d,%d", &sl, &th) == 2 && sl >= 1 && sl <= 3 && th >= 32 && th % 32 == 0) return {sl, th};
-    }
-    const int max_t[4] = {0, 1024, 512, 352};
-    ScenCfg best = {1, 32};
-    double best_cost = 1e30;
-    for (int sl = 1; sl <= 3; ++sl) {
-        for (int th = 64; th <= max_t[sl]; th += 32) {
-            const int sweeps = (n_grp + sl * th - 1) / (sl * th);
-            // cost ~ lane-time: every sweep occupies the CTA for (slots columns) whether lanes are valid or not;
-            // prefer >= 8 warps so a lone CTA per SM can hide FP64 latency
-            double cost = (double)sweeps * sl * th / n_grp;
-            if (th < 256) cost *= 1.0 + (256 - th) / 512.0;
-            if (cost < best_cost - 1e-9) {
-                best_cost = cost;
-                best = {sl, th};
-            }
-        }
-    }
-    return best;
-}
-
-template <int SCHEME, int VEC>
-static cudaError_t launch_scen_cfg(const crt1d_batch& in, const crt1d_out& out, cudaStream_t stream) {
-    const ScenCfg c = pick_scen_cfg(in.n_wl / VEC);
-    switch (c.slots) {
-        case 1: return launch_scen<SCHEME, VEC, 1, 1024>(in, out, c.threads, stream);
-        case 2: return launch_scen<SCHEME, VEC, 2, 512>(in, out, c.threads > 512 ? 512 : c.threads, stream);
-        default: return launch_scen<SCHEME, VEC, 3, 352>(in, out, c.threads > 352 ? 352 : c.threads, stream);
-    }
+    constexpr int B = TileCfg<SCHEME>::BLK, M = TileCfg<SCHEME>::MINB;
+    return vec2 ? launch_one<SCHEME, 2, B, M>(in, out, stream) : launch_one<SCHEME, 1, B, M>(in, out, stream);
 }
 
 size_t solve_shared_bytes(int scheme, int n_z) { return (size_t)n_level_tables(scheme) * n_z * sizeof(double); }
@@ -586,35 +374,23 @@ static cudaError_t launch_rows_2s_t(const crt1d_batch& in, const crt1d_out& out,
     return cudaGetLastError();
 }
 
-// rows-kernel configuration "LV,threads,rec" via CRT1D_B200_ROWS_CFG (tuning experiments); the default
-// is the best measured on B200 (profiles/README.md).
+// rows-kernel configuration: default (LV = 6, 512 threads, recurrence) = best of the measured sweep
+// (profiles/r01_rows_kernel_config_sweep.txt).  "LV,threads,rec" in CRT1D_B200_ROWS_CFG selects one of the few
+// other compiled configurations (tests / tuning): 4,<=512,0|1   10,<=512,1   6,<=512,0   3,<=1024,1.
 template <int VEC>
 static cudaError_t launch_rows_2s(const crt1d_batch& in, const crt1d_out& out, cudaStream_t stream) {
-    int lv = 6, th = 512, rec = 1;  // best of the sweep in profiles/README.md (0.907 of measured HBM peak)
+    int lv = 6, th = 512, rec = 1;
     const char* env = getenv("CRT1D_B200_ROWS_CFG");
     if (env) sscanf(env, "%d,%d,%d", &lv, &th, &rec);
     if (th % 32 != 0 || th < 64 || th > 1024) th = 512;
     if (in.n_z > 1024 * 2) rec = 0;
-    const int bucket = th > 768 ? 1024 : th > 640 ? 768 : th > 512 ? 640 : 512;
-#define CRT_ROWS_LV(LVV)                                                                                   \
-    if (lv == LVV) {                                                                                       \
-        if (bucket == 1024) return rec ? launch_rows_2s_t<VEC, LVV, 1024, true>(in, out, th, stream)       \
-                                       : launch_rows_2s_t<VEC, LVV, 1024, false>(in, out, th, stream);     \
-        if (bucket == 768) return rec ? launch_rows_2s_t<VEC, LVV, 768, true>(in, out, th, stream)         \
-                                      : launch_rows_2s_t<VEC, LVV, 768, false>(in, out, th, stream);       \
-        if (bucket == 640) return rec ? launch_rows_2s_t<VEC, LVV, 640, true>(in, out, th, stream)         \
-                                      : launch_rows_2s_t<VEC, LVV, 640, false>(in, out, th, stream);       \
-        return rec ? launch_rows_2s_t<VEC, LVV, 512, true>(in, out, th, stream)                            \
-                   : launch_rows_2s_t<VEC, LVV, 512, false>(in, out, th, stream);                          \
-    }
-    CRT_ROWS_LV(2)
-    CRT_ROWS_LV(3)
-    CRT_ROWS_LV(4)
-    CRT_ROWS_LV(6)
-    CRT_ROWS_LV(10)
-#undef CRT_ROWS_LV
-    return rec ? launch_rows_2s_t<VEC, 4, 512, true>(in, out, th > 512 ? 512 : th, stream)
-               : launch_rows_2s_t<VEC, 4, 512, false>(in, out, th > 512 ? 512 : th, stream);
+    if (lv == 3 && rec) return launch_rows_2s_t<VEC, 3, 1024, true>(in, out, th, stream);
+    if (th > 512) th = 512;
+    if (lv == 4) return rec ? launch_rows_2s_t<VEC, 4, 512, true>(in, out, th, stream)
+                            : launch_rows_2s_t<VEC, 4, 512, false>(in, out, th, stream);
+    if (lv == 10 && rec) return launch_rows_2s_t<VEC, 10, 512, true>(in, out, th, stream);
+    return rec ? launch_rows_2s_t<VEC, 6, 512, true>(in, out, th, stream)
+               : launch_rows_2s_t<VEC, 6, 512, false>(in, out, th, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -890,7 +666,7 @@ static cudaError_t launch_rows(const crt1d_batch& in, const crt1d_out& out, bool
     return cudaGetLastError();
 }
 
-// Batches with at least this many scenarios go to the scenario-CTA kernel (one CTA per SM needs >= n_SM
+// Batches with at least this many scenarios go to the row-sweep kernels (one CTA per SM needs >= n_SM
 // scenarios in flight); smaller ones (the single-scenario plugin path) use the band-tile kernel.
 static int64_t scen_kernel_min_batch() {
     const char* env = getenv("CRT1D_B200_SCEN_MIN");
@@ -900,12 +676,10 @@ static int64_t scen_kernel_min_batch() {
 cudaError_t launch_solve(int scheme, const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream) {
     if (getenv("CRT1D_B200_FORCE_VEC1") != nullptr) vec2 = false;  // tuning experiments
     if (scheme == CRT1D_SCHEME_2S && in.n_scen >= scen_kernel_min_batch()) {
-        const char* mode = getenv("CRT1D_B200_2S_KERNEL");  // "rows" (default) | "scen" | "tile" (tuning / tests)
-        const bool rows_fit = rows_2s_shared_bytes(in.n_z, in.n_wl) <= 227u * 1024u;
+        const char* mode = getenv("CRT1D_B200_2S_KERNEL");  // "rows" (default) | "tile" (tuning / tests)
+        const bool rows_fit = rows_2s_shared_bytes(in.n_z, in.n_wl) <= 227u * 1024u - 4096u;
         if ((mode == nullptr || mode[0] == 'r') && rows_fit)
             return vec2 ? launch_rows_2s<2>(in, out, stream) : launch_rows_2s<1>(in, out, stream);
-        if (mode != nullptr && mode[0] == 's')
-            return vec2 ? launch_scen_cfg<CRT1D_SCHEME_2S, 2>(in, out, stream) : launch_scen_cfg<CRT1D_SCHEME_2S, 1>(in, out, stream);
     }
     if (in.n_scen >= scen_kernel_min_batch() && getenv("CRT1D_B200_NO_ROWS") == nullptr) {
         const size_t cap = 227u * 1024u - 2048u;  // dynamic + static shared memory of one CTA
