@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--scenarios", type=int, default=1_000_000, help="scenarios per GPU (cross product is truncated)")
     ap.add_argument("--chunk", type=int, default=4144, help="scenarios per kernel launch")
     ap.add_argument("--cpu-sample", type=int, default=0, help="scenarios in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): every rank runs its own --scenarios sweep; strong: ONE sweep of --scenarios "
+                         "block-partitioned over the ranks (BASELINE.json configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -211,18 +214,32 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    spec = make_spec(rank, args.scenarios)  # weak scaling: every rank owns a full sweep (seed = rank)
+    if args.scaling == "strong":  # one sweep, contiguous scenario blocks per rank (distributed.shard_batch)
+        full = make_spec(0, args.scenarios)
+        spec, _ = cdist.shard_batch(full, world, rank)
+        n_total_strong = full.n_scen
+    else:  # weak scaling: every rank owns a full sweep (seed = rank)
+        spec = make_spec(rank, args.scenarios)
+        n_total_strong = None
     runner = sweep.SweepRunner(spec, args.scheme, chunk=args.chunk, device=dev)
     runner.upload()
     S = spec.n_scen
     n_bw = runner.band_w.shape[0]
-    gathered = torch.empty((world * S, n_bw), dtype=torch.float64, device=dev) if world > 1 else None
+    S_total = n_total_strong if args.scaling == "strong" else world * S
+    gathered = None
 
     def one_step(events=None):
+        nonlocal gathered
         n = runner.step(events)
         if world > 1:  # diagnostics of every rank's scenarios on every rank (2 doubles per scenario)
-            dist.all_gather_into_tensor(gathered, runner.absorbed)
+            gathered = cdist.all_gather_rows(runner.absorbed, S_total, world) if args.scaling == "strong" else _gather_equal()
         return n
+
+    _gbuf = torch.empty((world * S, n_bw), dtype=torch.float64, device=dev) if world > 1 and args.scaling == "weak" else None
+
+    def _gather_equal():
+        dist.all_gather_into_tensor(_gbuf, runner.absorbed)
+        return _gbuf
 
     for _ in range(args.warmup):
         one_step()
@@ -244,7 +261,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_total = cdist.max_over_ranks(e0.elapsed_time(e1), device=dev)
     ms_per_step = ms_total / args.steps
-    units_per_step = runner.units_per_step * world
+    units_per_step = S_total * spec.n_z * spec.n_wl  # all ranks' scenarios
     value = units_per_step / (ms_per_step * 1e-3)
 
     # dominant kernel: average launch duration from the per-launch CUDA event pairs of the timed region
@@ -313,7 +330,7 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": workload_name(args), "scheme": args.scheme, "scenarios_per_gpu": S, "n_z": spec.n_z,

@@ -93,6 +93,9 @@ PROTOTYPES = {
     "crt1d_release_workspace": (C.c_int, []),
     "crt1d_calc_absorption": (
         C.c_int, [C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AbsorptionOut), C.c_void_p]),
+    "crt1d_energy_balance": (
+        C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                  C.c_void_p]),
     "crt1d_leaf_G": (C.c_int, [C.c_int, C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "crt1d_tau_d": (C.c_int, [C.c_int, C.c_double, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "crt1d_leaf_integrals": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),

@@ -198,6 +198,18 @@ int crt1d_calc_absorption(const crt1d_batch* in, const double* I_dr, const doubl
     return CRT1D_OK;
 }
 
+int crt1d_energy_balance(int64_t n_scen, int32_t n_z, int32_t n_wl, const double* I_dr, const double* I_df_d,
+                         const double* I_df_u, const double* band_w, int32_t n_bw, double* ebal, void* stream) {
+    if (n_scen < 0 || n_z < 2 || n_wl < 1) return fail(CRT1D_ERR_INVALID_ARG, "crt1d_energy_balance: bad sizes");
+    if (n_bw < 1 || n_bw > 4) return fail(CRT1D_ERR_INVALID_ARG, "crt1d_energy_balance: n_bw must be in 1..4");
+    if (n_scen == 0) return CRT1D_OK;
+    if (!I_dr || !I_df_d || !I_df_u || !band_w || !ebal) return fail(CRT1D_ERR_NULL_POINTER, "crt1d_energy_balance: NULL argument");
+    cudaError_t e = crt::launch_energy_balance(n_scen, n_z, n_wl, I_dr, I_df_d, I_df_u, band_w, n_bw, ebal,
+                                               static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "launch of energy_balance kernel");
+    return CRT1D_OK;
+}
+
 int crt1d_leaf_G(int family, double param, int64_t n, const double* psi, double* G, double* K_b, void* stream) {
     if (family < 0 || family > CRT1D_G_ELLIPSOIDAL_APPROX_BONAN) return fail(CRT1D_ERR_INVALID_ARG, "unknown leaf-angle family");
     if (n < 0) return fail(CRT1D_ERR_INVALID_ARG, "n < 0");

@@ -12,6 +12,8 @@ size_t solve_shared_bytes(int scheme, int n_z);
 cudaError_t launch_solve(int scheme, const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream);
 cudaError_t launch_absorption(const crt1d_batch& in, const double* I_dr, const double* I_df_d, const double* I_df_u,
                               const crt1d_absorption_out& out, bool vec2, cudaStream_t stream);
+cudaError_t launch_energy_balance(int64_t n_scen, int n_z, int n_wl, const double* I_dr, const double* I_df_d,
+                                  const double* I_df_u, const double* band_w, int n_bw, double* ebal, cudaStream_t stream);
 cudaError_t launch_leaf_G(int family, double param, int64_t n, const double* psi, double* G, double* K_b,
                           cudaStream_t stream);
 cudaError_t launch_tau_d(int family, double param, const QuadRule& rule, int64_t n, const double* L, double* tau_d,

@@ -796,6 +796,60 @@ cudaError_t launch_absorption(const crt1d_batch& in, const double* I_dr, const d
 }
 
 // ---------------------------------------------------------------------------------------------
+// canopy energy balance  (ref ../diagnostics.py:476-530 with the band weights of :56-81)
+// one CTA per scenario; threads stride over bands reading the ground and top rows only; fixed-order
+// block reduction of 4 x n_bw sums (deterministic).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) energy_balance_kernel(int n_z, int n_wl, const double* __restrict__ I_dr,
+                                                             const double* __restrict__ I_df_d,
+                                                             const double* __restrict__ I_df_u,
+                                                             const double* __restrict__ band_w, int n_bw, double* ebal) {
+    __shared__ double red[8][16];
+    const int64_t s = blockIdx.x;
+    const int64_t g0 = s * (int64_t)n_z * n_wl, t0 = g0 + (int64_t)(n_z - 1) * n_wl;
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+    for (int b = threadIdx.x; b < n_wl; b += blockDim.x) {
+        const double drg = I_dr[g0 + b], dng = I_df_d[g0 + b], upg = I_df_u[g0 + b];
+        const double drt = I_dr[t0 + b], dnt = I_df_d[t0 + b], upt = I_df_u[t0 + b];
+        const double incoming = drt + dnt;                                   // ref :512
+        const double outgoing = upt;                                         // ref :513
+        const double soil_abs = (drg + dng) - upg;                           // ref :514-516
+        const double canopy = dnt - upt + drt - drg + -(dng - upg);          // ref :518-524
+        for (int k = 0; k < n_bw; ++k) {
+            const double w = band_w[(int64_t)k * n_wl + b];
+            acc[4 * k + 0] += w * incoming;
+            acc[4 * k + 1] += w * outgoing;
+            acc[4 * k + 2] += w * soil_abs;
+            acc[4 * k + 3] += w * canopy;
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        double v = acc[i];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 * n_bw) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][threadIdx.x];
+        ebal[s * 4 * n_bw + threadIdx.x] = v;
+    }
+}
+
+cudaError_t launch_energy_balance(int64_t n_scen, int n_z, int n_wl, const double* I_dr, const double* I_df_d,
+                                  const double* I_df_u, const double* band_w, int n_bw, double* ebal, cudaStream_t stream) {
+    if (n_scen <= 0) return cudaSuccess;
+    if (n_scen > 2147483647LL) return cudaErrorInvalidConfiguration;
+    energy_balance_kernel<<<(unsigned)n_scen, 256, 0, stream>>>(n_z, n_wl, I_dr, I_df_d, I_df_u, band_w, n_bw, ebal);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // leaf-angle kernels  (ref ../leaf_angle.py:118-202, common.py:11-95)
 // ---------------------------------------------------------------------------------------------
 __global__ void leaf_G_kernel(int family, double param, int64_t n, const double* __restrict__ psi, double* G,

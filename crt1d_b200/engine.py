@@ -285,3 +285,26 @@ def calc_absorption(dbatch: DeviceBatch, I_dr, I_df_d, I_df_u):
                                               I_df_u.data_ptr(), ctypes.byref(ao), _stream_ptr(torch))
     _lib.check(rc)
     return outs
+
+
+EBAL_COLUMNS = ("incoming", "outgoing (reflected)", "soil absorbed", "canopy abs")
+
+
+def energy_balance(I_dr, I_df_d, I_df_u, band_w):
+    """Canopy energy balance per scenario and band group on the GPU (the reference's `compare_ebal`,
+    ref diagnostics.py:476-530, batched): profiles `(S, n_z, n_wl)` torch tensors in HBM, `band_w`
+    `(n_bw, n_wl)` weights (e.g. `spectra.band_weights`, or photon-flux weights).  Returns a tensor
+    `(S, n_bw, 4)` with columns `EBAL_COLUMNS`; `incoming - outgoing - soil` closes against `canopy abs`."""
+    torch = _torch()
+    S, nz, nw = I_dr.shape
+    bw = np.ascontiguousarray(np.atleast_2d(np.asarray(band_w, dtype=np.float64)))
+    if bw.shape[1] != nw or not 1 <= bw.shape[0] <= 4:
+        raise ValueError("band_w must be (1..4, n_wl)")
+    bw_d = torch.as_tensor(bw).to(I_dr.device)
+    out = torch.empty((S, bw.shape[0], 4), dtype=torch.float64, device=I_dr.device)
+    lib = _lib.load()
+    with torch.cuda.device(I_dr.device):
+        rc = lib.crt1d_energy_balance(S, nz, nw, I_dr.data_ptr(), I_df_d.data_ptr(), I_df_u.data_ptr(), bw_d.data_ptr(),
+                                      bw.shape[0], out.data_ptr(), _stream_ptr(torch))
+    _lib.check(rc)
+    return out

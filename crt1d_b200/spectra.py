@@ -52,3 +52,16 @@ def edges_from_centers_widths(wl, dwl):
     wl = np.asarray(wl, dtype=float)
     dwl = np.asarray(dwl, dtype=float)
     return np.r_[wl[0] - 0.5 * dwl[0], wl + 0.5 * dwl]
+
+
+def e_wl_umol(wl_um):
+    """Photon energy, J per micromole of photons, at wavelength `wl_um` (ref spectra.py:30-39).  Dividing
+    band weights by it turns the fused W m-2 reductions into photon flux density (umol m-2 s-1), which --
+    as the reference notes (diagnostics.py:49-51) -- has to happen per wavelength, before integrating."""
+    h, c, N_A = 6.62607015e-34, 299792458.0, 6.02214076e23
+    return h * c / (np.asarray(wl_um, dtype=float) * 1e-6) * N_A * 1e-6
+
+
+def pfd_band_weights(wl, dwl, band_name="PAR"):
+    """Band weights that integrate irradiance to photon flux density in a named band."""
+    return band_weights(edges_from_centers_widths(wl, dwl), band_name) / e_wl_umol(wl)

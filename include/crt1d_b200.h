@@ -170,6 +170,19 @@ typedef struct crt1d_absorption_out {
 CRT1D_API int crt1d_calc_absorption(const crt1d_batch* in, const double* I_dr, const double* I_df_d,
                           const double* I_df_u, const crt1d_absorption_out* out, void* stream);
 
+/* ---- canopy energy balance per scenario and spectral band group ------------------------------
+ * (replaces diagnostics.compare_ebal, crt1d/diagnostics.py:476-530, with the band() weights of
+ * diagnostics.py:56-81).  Reads only the ground and top rows of the three profiles [S][n_z][n_wl].
+ * ebal[S][n_bw][4] = { incoming  = Sum_wl w (I_dr + I_df_d)[top],
+ *                      outgoing  = Sum_wl w  I_df_u[top]            (reflected),
+ *                      soil_abs  = Sum_wl w ((I_dr + I_df_d)[0] - I_df_u[0]),
+ *                      canopy_abs = Sum_wl w (I_df_d[top] - I_df_u[top] + I_dr[top] - I_dr[0] - (I_df_d[0] - I_df_u[0])) }
+ * band_w: [n_bw][n_wl] weights (PAR/NIR/solar fractions, or photon-flux weights w / e_wl_umol); n_bw in 1..4.
+ * Device pointers, asynchronous. */
+CRT1D_API int crt1d_energy_balance(int64_t n_scen, int32_t n_z, int32_t n_wl, const double* I_dr,
+                                   const double* I_df_d, const double* I_df_u, const double* band_w,
+                                   int32_t n_bw, double* ebal, void* stream);
+
 /* ---- leaf-angle kernels (device pointers, asynchronous) -------------------------------------
  * G(psi) and K_b = G/cos(psi) for n angles         (replaces leaf_angle.G_*, model.py:291)       */
 CRT1D_API int crt1d_leaf_G(int family, double param, int64_t n, const double* psi, double* G, double* K_b,

@@ -516,3 +516,34 @@ def test_plain_c_caller(tmp_path, default_p):
     ref = oracle.run("2s", p)
     for i, k in enumerate(("I_dr", "I_df_d", "I_df_u", "F")):
         assert_close(res[i], ref[k], RTOL, f"C caller {k}")
+
+
+def test_energy_balance_kernel(default_p):
+    """crt1d_energy_balance vs the reference's compare_ebal arithmetic (ref diagnostics.py:505-529) on
+    oracle profiles; closure incoming - outgoing - soil = canopy; PFD weights."""
+    import torch
+
+    from crt1d_b200 import engine
+    from crt1d_b200 import spectra
+
+    wle = spectra.edges_from_centers_widths(default_p["wl"], default_p["dwl"])
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bw = np.stack([spectra.band_weights(wle, b) for b in ("PAR", "NIR", "solar")]
+                      + [spectra.pfd_band_weights(default_p["wl"], default_p["dwl"], "PAR")])
+    refs = [oracle.run(sch, default_p) for sch in ("2s", "zq", "bf")]
+    prof = {k: torch.as_tensor(np.stack([r[k] for r in refs])).cuda() for k in ("I_dr", "I_df_d", "I_df_u")}
+    eb = engine.energy_balance(prof["I_dr"], prof["I_df_d"], prof["I_df_u"], bw).cpu().numpy()
+    assert eb.shape == (3, 4, 4)
+    for s, r in enumerate(refs):
+        I_d = r["I_dr"] + r["I_df_d"]
+        for k in range(4):
+            w = bw[k]
+            incoming, outgoing = (I_d[-1] * w).sum(), (r["I_df_u"][-1] * w).sum()
+            soil = (I_d[0] * w).sum() - (r["I_df_u"][0] * w).sum()
+            canopy = ((r["I_df_d"][-1] - r["I_df_u"][-1] + r["I_dr"][-1] - r["I_dr"][0] - (r["I_df_d"][0] - r["I_df_u"][0])) * w).sum()
+            assert_close(eb[s, k], np.array([incoming, outgoing, soil, canopy]), 1e-12, f"ebal scheme {s} band {k}")
+            assert abs(eb[s, k, 0] - eb[s, k, 1] - eb[s, k, 2] - eb[s, k, 3]) < 1e-10 * eb[s, k, 0]
+    assert abs(eb[0, 0, 3] - 357.5632253155) < 1e-6  # 2s canopy-absorbed PAR, SURVEY.md section 8c
+    assert 4.0 < eb[0, 3, 0] / eb[0, 0, 0] < 5.0  # ~4.6 umol photons per J in the PAR band
