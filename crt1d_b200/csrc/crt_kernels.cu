@@ -281,7 +281,10 @@ __global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batc
     const int n_lg = (n_z + LV - 1) / LV;
     const int n_items = n_chunks * n_lg;
     const int lane = threadIdx.x & 31;
-    for (; dbg != 1;) {  // dbg == 1: timing experiment, coefficient phase only
+    // Reduced-diagnostic mode: with no profile requested there is nothing to sweep -- the absorbed reduction only
+    // needs the ground and top levels, which phase B evaluated.
+    const bool any_profile = pI || pD || pU || pF;
+    for (; dbg != 1 && any_profile;) {  // dbg == 1: timing experiment, coefficient phase only
         int item = 0;
         if (lane == 0) item = atomicAdd(&counter, 1);
         item = __shfl_sync(0xffffffffu, item, 0);
@@ -547,7 +550,10 @@ __global__ void __launch_bounds__(MAXT, 1) solve_rows_kernel(const crt1d_batch i
     const int n_chunks = (n_grp + 31) / 32;
     const int n_items = n_chunks * ((n_z + LV - 1) / LV);
     const int lane = threadIdx.x & 31;
-    for (;;) {
+    bool any_profile = false;  // reduced-diagnostic mode: nothing to sweep if no profile is requested
+#pragma unroll
+    for (int q = 0; q < NF; ++q) any_profile = any_profile || pf[q] != nullptr;
+    for (; any_profile;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(&counter, 1);
         item = __shfl_sync(0xffffffffu, item, 0);

@@ -547,3 +547,30 @@ def test_energy_balance_kernel(default_p):
             assert abs(eb[s, k, 0] - eb[s, k, 1] - eb[s, k, 2] - eb[s, k, 3]) < 1e-10 * eb[s, k, 0]
     assert abs(eb[0, 0, 3] - 357.5632253155) < 1e-6  # 2s canopy-absorbed PAR, SURVEY.md section 8c
     assert 4.0 < eb[0, 3, 0] / eb[0, 0, 0] < 5.0  # ~4.6 umol photons per J in the PAR band
+
+
+@pytest.mark.parametrize("scheme", ["2s", "4s", "bl", "bf", "g77", "zq"])
+def test_reduced_diagnostic_mode(scheme):
+    """Profiles are optional outputs for the closed-form schemes (NULL pointers in crt1d_out): the fused
+    canopy-absorbed reduction must come out bit-identical with or without them (row-sweep kernels skip the
+    level sweep entirely in that mode).  zq/n79 use the profiles as scratch and must refuse loudly."""
+    import torch
+
+    from crt1d_b200 import _lib
+    from crt1d_b200 import engine
+    from crt1d_b200 import sweep
+
+    spec = sweep.synthetic_sweep_spec(seed=0)
+    sub = spec.slice(123000, 123000 + 200)
+    bw = np.stack([np.ones(spec.n_wl), np.linspace(0, 1, spec.n_wl)])
+    db = engine.DeviceBatch(sub, scheme)
+    ob = engine.OutputBuffers(scheme, sub.n_scen, sub.n_z, sub.n_wl, device=db.device, fields=(), extras=False, band_w=bw)
+    if scheme == "zq":
+        with pytest.raises(_lib.Crt1dB200Error) as ei:
+            engine.solve_into(db, ob)
+        assert "scratch" in str(ei.value)
+        return
+    engine.solve_into(db, ob)
+    full = engine.solve(db, scheme, band_w=bw)
+    torch.cuda.synchronize()
+    assert torch.equal(ob.t["absorbed"], full["absorbed"])
