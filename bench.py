@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default): every rank runs its own --scenarios sweep; strong: ONE sweep of --scenarios "
                          "block-partitioned over the ranks (BASELINE.json configs[3])")
+    ap.add_argument("--profile-dtype", default="f64", choices=["f64", "f32"],
+                    help="storage type of the profiles in HBM (arithmetic is always float64); f32 = the optional "
+                         "reduced-precision path of BASELINE.json, NOT the headline configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -221,7 +224,8 @@ def main():
     else:  # weak scaling: every rank owns a full sweep (seed = rank)
         spec = make_spec(rank, args.scenarios)
         n_total_strong = None
-    runner = sweep.SweepRunner(spec, args.scheme, chunk=args.chunk, device=dev)
+    pdt = torch.float32 if args.profile_dtype == "f32" else None
+    runner = sweep.SweepRunner(spec, args.scheme, chunk=args.chunk, device=dev, profile_dtype=pdt)
     runner.upload()
     S = spec.n_scen
     n_bw = runner.band_w.shape[0]
@@ -277,7 +281,7 @@ def main():
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and args.profile_dtype == "f64":
         try:
             traffic = json.load(open(tpath)).get(f"{args.scheme}_chunk{runner.chunk}")
         except Exception:
@@ -296,7 +300,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         pinned_out = torch.empty((S, n_bw), dtype=torch.float64).pin_memory()
-        r2 = sweep.SweepRunner(spec, args.scheme, chunk=args.chunk, device=dev)
+        r2 = sweep.SweepRunner(spec, args.scheme, chunk=args.chunk, device=dev, profile_dtype=pdt)
         r2.ring = runner.ring  # reuse the HBM profile ring (allocation is not part of a step)
         r2.pin_host()          # inputs staged once in pinned host memory; every step copies them H2D
         r2.band_w_d, r2.absorbed = runner.band_w_d, runner.absorbed
@@ -335,9 +339,10 @@ def main():
             "config": {
                 "workload": workload_name(args), "scheme": args.scheme, "scenarios_per_gpu": S, "n_z": spec.n_z,
                 "n_wl": spec.n_wl, "chunk": runner.chunk, "launches_per_step": runner.n_chunks,
-                "profile_bytes_per_step_per_gpu": int(S * spec.n_z * spec.n_wl * 32),
+                "profile_bytes_per_step_per_gpu": int(S * spec.n_z * spec.n_wl * (bpu - 5 * 8.0 / spec.n_z - 8.0 / spec.n_wl)),
+                "profile_storage": args.profile_dtype,
                 "l2": "no flush needed: each launch writes a %.1f GB profile chunk (>> 126 MB L2), 2-buffer ring" % (
-                    runner.chunk * spec.n_z * spec.n_wl * 32 / 1e9),
+                    runner.chunk * spec.n_z * spec.n_wl * bpu / 1e9),
                 "parallelism": f"scenario-sharded x{world}, no data-path collective; NCCL all-gather of absorbed[S,2]",
             },
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

@@ -1,7 +1,7 @@
 """ctypes mirror of include/crt1d_b200.h (structs, constants, function prototypes)."""
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK = 0
 ERR_INVALID_ARG = -1
@@ -65,6 +65,7 @@ class Out(C.Structure):
         ("band_w", _pd),
         ("n_bw", C.c_int32),
         ("absorbed", _pd),
+        ("profile_f32", C.c_int32),
     ]
 
 

@@ -72,6 +72,9 @@ int validate(int scheme, const crt1d_batch* in, const crt1d_out* out) {
         if (!out->I_dr || !out->I_df_d || !out->I_df_u || !out->F)
             return fail(CRT1D_ERR_NULL_POINTER, sn + ": I_dr, I_df_d, I_df_u and F are all required (used as elimination scratch)");
     }
+    if (out->profile_f32 != 0 && out->profile_f32 != 1) return fail(CRT1D_ERR_INVALID_ARG, "crt1d_out.profile_f32 must be 0 or 1");
+    if (out->profile_f32 && (scheme == CRT1D_SCHEME_N79 || scheme == CRT1D_SCHEME_ZQ || scheme == CRT1D_SCHEME_ZQ_PA))
+        return fail(CRT1D_ERR_UNSUPPORTED, sn + ": float32 profile storage is not available (float64 elimination scratch lives in the profile arrays)");
     if (out->n_bw < 0 || out->n_bw > 4) return fail(CRT1D_ERR_INVALID_ARG, "crt1d_out.n_bw must be in 0..4");
     if (out->absorbed != nullptr && (out->band_w == nullptr || out->n_bw == 0))
         return fail(CRT1D_ERR_NULL_POINTER, "crt1d_out.absorbed needs band_w and n_bw >= 1");
@@ -84,7 +87,7 @@ bool can_vec2(const crt1d_batch* in, const crt1d_out* out) {
     if (in->n_wl % 2 != 0) return false;
     const void* ptrs[] = {out->I_dr, out->I_df_d, out->I_df_u, out->F, out->x0, out->x1, out->x2};
     for (const void* p : ptrs)
-        if (p != nullptr && !aligned16(p)) return false;
+        if (p != nullptr && !aligned16(p)) return false;  // (8-byte alignment would do for float pairs; keep one rule)
     return true;
 }
 
@@ -313,6 +316,13 @@ int crt1d_solve_host(int scheme, const crt1d_batch* in, const crt1d_out* out, in
             if (pass == 1) d2h.push_back({dst, d, count * sizeof(double)});
             return d;
         };
+        const size_t esz = out->profile_f32 ? sizeof(float) : sizeof(double);
+        auto out_p = [&](double* dst, size_t count) -> double* {  // profile in the requested storage type
+            if (dst == nullptr) return nullptr;
+            double* d = reinterpret_cast<double*>(cv.take<char>(count * esz));
+            if (pass == 1) d2h.push_back({dst, d, count * esz});
+            return d;
+        };
         din.psi = in_d(in->psi, S);
         din.K_b = in_d(in->K_b, S);
         din.G = in_d(in->G, S);
@@ -332,13 +342,13 @@ int crt1d_solve_host(int scheme, const crt1d_batch* in, const crt1d_out* out, in
         din.I_dr0_lib = in_d(in->I_dr0_lib, (size_t)in->n_sky * nw);
         din.I_df0_lib = in_d(in->I_df0_lib, (size_t)in->n_sky * nw);
         dout.band_w = in_d(out->band_w, (size_t)out->n_bw * nw);
-        dout.I_dr = out_d(out->I_dr, prof);
-        dout.I_df_d = out_d(out->I_df_d, prof);
-        dout.I_df_u = out_d(out->I_df_u, prof);
-        dout.F = out_d(out->F, prof);
-        dout.x0 = out_d(out->x0, xprof);
-        dout.x1 = out_d(out->x1, xprof);
-        dout.x2 = out_d(out->x2, xprof);
+        dout.I_dr = out_p(out->I_dr, prof);
+        dout.I_df_d = out_p(out->I_df_d, prof);
+        dout.I_df_u = out_p(out->I_df_u, prof);
+        dout.F = out_p(out->F, prof);
+        dout.x0 = out_p(out->x0, xprof);
+        dout.x1 = out_p(out->x1, xprof);
+        dout.x2 = out_p(out->x2, xprof);
         dout.rho_c = out_d(out->rho_c, S * nw);
         dout.absorbed = out_d(out->absorbed, S * (size_t)out->n_bw);
         need = cv.off;

@@ -26,12 +26,23 @@ constexpr int BLOCK = 128;  // threads per CTA of the elementwise kernels (absor
 template <int VEC>
 struct GlobalOut {
     double* p[N_FIELDS];  // pre-offset to (scenario, level 0, first band of this thread); nullptr = skip
-    int64_t stride;       // doubles between consecutive levels (= n_wl)
+    int64_t stride;       // elements between consecutive levels (= n_wl)
+    bool f32;             // float32 storage: p[] really are float* (pre-offset in floats)
 
     // final results: written once, never re-read by this kernel -> streaming (evict-first) stores
     __device__ __forceinline__ void st(int f, int j, const double (&x)[VEC]) const {
         double* q = p[f];
         if (q == nullptr) return;
+        if (f32) {
+            float* qf = reinterpret_cast<float*>(q) + (int64_t)j * stride;
+            if constexpr (VEC == 2) {
+                __stcs(reinterpret_cast<float2*>(qf), make_float2((float)x[0], (float)x[1]));
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) __stcs(qf + v, (float)x[v]);
+            }
+            return;
+        }
         q += (int64_t)j * stride;
         if constexpr (VEC == 2) {
             __stcs(reinterpret_cast<double2*>(q), make_double2(x[0], x[1]));
@@ -42,7 +53,7 @@ struct GlobalOut {
     }
     // one column at a time (zq_pa finishes each column before starting the next)
     __device__ __forceinline__ void st1(int f, int j, int v, double x) const {
-        if (p[f] != nullptr) __stcs(p[f] + (int64_t)j * stride + v, x);
+        if (p[f] != nullptr) __stcs(p[f] + (int64_t)j * stride + v, x);  // zq_pa: float64 only
     }
     // elimination scratch parked in the output arrays: re-read by the same thread during
     // back-substitution -> default (write-back, L2-resident) stores
@@ -79,6 +90,31 @@ __device__ __forceinline__ void ld_vec(const double* q, double (&x)[VEC]) {
         x[0] = __ldcs(q);
     }
 }
+// profile store honouring crt1d_out.profile_f32: `base` points at the scenario's field in its own dtype
+template <int VEC>
+__device__ __forceinline__ void st_prof(void* base, bool f32, int64_t off, const double (&x)[VEC]) {
+    if (base == nullptr) return;
+    if (f32) {
+        float* q = static_cast<float*>(base) + off;
+        if constexpr (VEC == 2) {
+            __stcs(reinterpret_cast<float2*>(q), make_float2((float)x[0], (float)x[1]));
+        } else {
+            __stcs(q, (float)x[0]);
+        }
+    } else {
+        double* q = static_cast<double*>(base) + off;
+        if constexpr (VEC == 2) {
+            __stcs(reinterpret_cast<double2*>(q), make_double2(x[0], x[1]));
+        } else {
+            __stcs(q, x[0]);
+        }
+    }
+}
+__device__ __forceinline__ void* prof_base(double* ptr, bool f32, int64_t elem_off) {
+    if (ptr == nullptr) return nullptr;
+    return f32 ? static_cast<void*>(reinterpret_cast<float*>(ptr) + elem_off) : static_cast<void*>(ptr + elem_off);
+}
+
 template <int VEC>
 __device__ __forceinline__ void st_vec(double* base, int64_t off, const double (&x)[VEC]) {
     if (base == nullptr) return;
@@ -117,13 +153,14 @@ __global__ void __launch_bounds__(BLK, MINB) solve_kernel(const crt1d_batch in, 
         const BandIn<VEC> b = load_bands<VEC>(in, s, b0);
         GlobalOut<VEC> o;
         o.stride = n_wl;
-        o.p[F_IDR] = out.I_dr ? out.I_dr + s * prof + b0 : nullptr;
-        o.p[F_DN] = out.I_df_d ? out.I_df_d + s * prof + b0 : nullptr;
-        o.p[F_UP] = out.I_df_u ? out.I_df_u + s * prof + b0 : nullptr;
-        o.p[F_F] = out.F ? out.F + s * prof + b0 : nullptr;
-        o.p[F_X0] = out.x0 ? out.x0 + s * xprof + b0 : nullptr;
-        o.p[F_X1] = out.x1 ? out.x1 + s * xprof + b0 : nullptr;
-        o.p[F_X2] = out.x2 ? out.x2 + s * xprof + b0 : nullptr;
+        o.f32 = out.profile_f32 != 0;
+        o.p[F_IDR] = static_cast<double*>(prof_base(out.I_dr, o.f32, s * prof + b0));
+        o.p[F_DN] = static_cast<double*>(prof_base(out.I_df_d, o.f32, s * prof + b0));
+        o.p[F_UP] = static_cast<double*>(prof_base(out.I_df_u, o.f32, s * prof + b0));
+        o.p[F_F] = static_cast<double*>(prof_base(out.F, o.f32, s * prof + b0));
+        o.p[F_X0] = static_cast<double*>(prof_base(out.x0, o.f32, s * xprof + b0));
+        o.p[F_X1] = static_cast<double*>(prof_base(out.x1, o.f32, s * xprof + b0));
+        o.p[F_X2] = static_cast<double*>(prof_base(out.x2, o.f32, s * xprof + b0));
         double rho_c[VEC], ab[VEC];
         solve_column_group<SCHEME, VEC>(in, s, tab, b, o, rho_c, ab);
         if constexpr (SCHEME == CRT1D_SCHEME_BF) {
@@ -272,10 +309,11 @@ __global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batc
 
     // ---- phase C: row-major work items
     const int64_t prof = (int64_t)n_z * n_wl;
-    double* pI = out.I_dr ? out.I_dr + s * prof : nullptr;
-    double* pD = out.I_df_d ? out.I_df_d + s * prof : nullptr;
-    double* pU = out.I_df_u ? out.I_df_u + s * prof : nullptr;
-    double* pF = out.F ? out.F + s * prof : nullptr;
+    const bool f32 = out.profile_f32 != 0;
+    void* pI = prof_base(out.I_dr, f32, s * prof);
+    void* pD = prof_base(out.I_df_d, f32, s * prof);
+    void* pU = prof_base(out.I_df_u, f32, s * prof);
+    void* pF = prof_base(out.F, f32, s * prof);
     const int n_grp = n_wl / VEC;
     const int n_chunks = (n_grp + 31) / 32;
     const int n_lg = (n_z + LV - 1) / LV;
@@ -336,10 +374,10 @@ __global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batc
                 }
             }
             const int64_t o = (int64_t)j * n_wl + c0;
-            st_vec<VEC>(pI, o, Idr);
-            st_vec<VEC>(pD, o, dn);
-            st_vec<VEC>(pU, o, up);
-            st_vec<VEC>(pF, o, F);
+            st_prof<VEC>(pI, f32, o, Idr);
+            st_prof<VEC>(pD, f32, o, dn);
+            st_prof<VEC>(pU, f32, o, up);
+            st_prof<VEC>(pF, f32, o, F);
         }
     }
 
@@ -542,9 +580,11 @@ __global__ void __launch_bounds__(MAXT, 1) solve_rows_kernel(const crt1d_batch i
 
     // ---- phase C: row-major work items (LV levels x 32*VEC bands)
     const int64_t prof = (int64_t)n_z * n_wl;
-    double* pf[7] = {out.I_dr, out.I_df_d, out.I_df_u, out.F, out.x0, out.x1, out.x2};
+    const bool f32 = out.profile_f32 != 0;
+    double* praw[7] = {out.I_dr, out.I_df_d, out.I_df_u, out.F, out.x0, out.x1, out.x2};
+    void* pf[7];
 #pragma unroll
-    for (int q = 0; q < 7; ++q) pf[q] = pf[q] ? pf[q] + s * prof : nullptr;
+    for (int q = 0; q < 7; ++q) pf[q] = prof_base(praw[q], f32, s * prof);
     const double* idr0 = in.I_dr0_lib + (int64_t)in.sky_idx[s] * n_wl;
     const int n_grp = n_wl / VEC;
     const int n_chunks = (n_grp + 31) / 32;
@@ -622,7 +662,7 @@ __global__ void __launch_bounds__(MAXT, 1) solve_rows_kernel(const crt1d_batch i
             }
             const int64_t off = (int64_t)j * n_wl + c0;
 #pragma unroll
-            for (int q = 0; q < NF; ++q) st_vec<VEC>(pf[q], off, o[q]);
+            for (int q = 0; q < NF; ++q) st_prof<VEC>(pf[q], f32, off, o[q]);
         }
     }
 

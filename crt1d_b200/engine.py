@@ -207,17 +207,28 @@ class DeviceBatch:
 class OutputBuffers:
     """Preallocated HBM outputs for up to `capacity` scenarios; reusable across chunks of a sweep."""
 
-    def __init__(self, scheme, capacity, n_z, n_wl, *, device, fields=MAIN_NAMES, extras=True, band_w=None):
+    def __init__(self, scheme, capacity, n_z, n_wl, *, device, fields=MAIN_NAMES, extras=True, band_w=None,
+                 profile_dtype=None):
         torch = _torch()
         self.scheme, self.capacity, self.n_z, self.n_wl = scheme, int(capacity), int(n_z), int(n_wl)
         f64 = dict(dtype=torch.float64, device=device)
+        pdt = torch.float64 if profile_dtype in (None, "f64", torch.float64) else profile_dtype
+        if pdt in ("f32", torch.float32):
+            pdt = torch.float32
+            if scheme in ("n79", "zq", "zq_pa"):
+                raise ValueError(f"{scheme}: float32 profile storage is not available (the tridiagonal schemes park "
+                                 "float64 elimination scratch in the profile arrays)")
+        elif pdt is not torch.float64:
+            raise ValueError("profile_dtype must be float64 (default) or float32")
+        self.profile_f32 = pdt is torch.float32
+        prof = dict(dtype=pdt, device=device)
         self.t = {}
         for k in fields:
-            self.t[k] = torch.empty((self.capacity, n_z, n_wl), **f64)
+            self.t[k] = torch.empty((self.capacity, n_z, n_wl), **prof)
         self.extra_names = EXTRA_NAMES.get(scheme, ()) if extras else ()
         rows = n_z - 1 if scheme == "n79" else n_z
         for k in self.extra_names:
-            self.t[k] = torch.empty((self.capacity, rows, n_wl), **f64)
+            self.t[k] = torch.empty((self.capacity, rows, n_wl), **prof)
         if scheme == "bf" and extras:
             self.t["rho_c"] = torch.empty((self.capacity, n_wl), **f64)
         self.band_w = None
@@ -243,10 +254,11 @@ class OutputBuffers:
             co.band_w = self.band_w.data_ptr()
             co.n_bw = self.band_w.shape[0]
             co.absorbed = self.t["absorbed"].data_ptr()
+        co.profile_f32 = 1 if self.profile_f32 else 0
         return co
 
     def bytes_written_per_scenario(self):
-        return sum(t[0].numel() * 8 for k, t in self.t.items())
+        return sum(t[0].numel() * t.element_size() for k, t in self.t.items())
 
 
 def solve_into(dbatch: DeviceBatch, out: OutputBuffers):
@@ -261,11 +273,14 @@ def solve_into(dbatch: DeviceBatch, out: OutputBuffers):
 
 
 def solve(batch, scheme, *, device=None, prologue="device", band_w=None, extras=True, mu_s=0.501,
-          tau_d_method="quad", n_quad=DEFAULT_N_QUAD):
-    """Solve every scenario of `batch`; returns a dict of torch tensors in HBM, profiles (S, n_z, n_wl)."""
+          tau_d_method="quad", n_quad=DEFAULT_N_QUAD, profile_dtype=None):
+    """Solve every scenario of `batch`; returns a dict of torch tensors in HBM, profiles (S, n_z, n_wl).
+    `profile_dtype=torch.float32` stores the profiles as float32 (arithmetic stays float64; closed-form
+    schemes only) and halves the HBM traffic."""
     db = batch if isinstance(batch, DeviceBatch) else DeviceBatch(
         batch, scheme, device=device, prologue=prologue, mu_s=mu_s, tau_d_method=tau_d_method, n_quad=n_quad)
-    ob = OutputBuffers(scheme, db.batch.n_scen, db.batch.n_z, db.batch.n_wl, device=db.device, extras=extras, band_w=band_w)
+    ob = OutputBuffers(scheme, db.batch.n_scen, db.batch.n_z, db.batch.n_wl, device=db.device, extras=extras, band_w=band_w,
+                       profile_dtype=profile_dtype)
     solve_into(db, ob)
     return ob.t
 

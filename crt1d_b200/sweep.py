@@ -83,7 +83,7 @@ class SweepRunner:
     """
 
     def __init__(self, spec, scheme="2s", *, chunk=4096, device=None, n_buffers=2, bands=("PAR", "NIR"),
-                 profiles=True, n_quad=64):
+                 profiles=True, n_quad=32, profile_dtype=None):
         import warnings
 
         from . import engine
@@ -95,6 +95,7 @@ class SweepRunner:
         self.chunk = int(min(chunk, spec.n_scen))
         self.n_buffers = int(n_buffers)
         self.profiles = profiles
+        self.profile_dtype = profile_dtype  # None / torch.float64, or torch.float32 storage (closed-form schemes)
         self.n_quad = n_quad
         self.device = device
         self.band_w = None
@@ -142,7 +143,7 @@ class SweepRunner:
             fields = eng.MAIN_NAMES if self.profiles else ()
             self.ring = [
                 eng.OutputBuffers(self.scheme, self.chunk, self.spec.n_z, self.spec.n_wl, device=dev, fields=fields,
-                                  extras=self.profiles)
+                                  extras=self.profiles, profile_dtype=self.profile_dtype)
                 for _ in range(self.n_buffers if self.profiles else 1)
             ]
             if self.band_w is not None:
@@ -193,6 +194,7 @@ class SweepRunner:
         n_fields = 4 + len(self.engine.EXTRA_NAMES.get(self.scheme, ()))
         if self.scheme == "n79":
             n_fields = 4 + 2 * (nz - 1) / nz
-        w = 8.0 * n_fields if self.profiles else 0.0
+        esz = 4.0 if self.ring and self.ring[0].profile_f32 else 8.0
+        w = esz * n_fields if self.profiles else 0.0
         r = 5 * 8.0 / nz + 8.0 / nw
         return w + r

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CRT1D_ABI_VERSION 1
+#define CRT1D_ABI_VERSION 2
 
 /* exported-symbol marker (the library is built with -fvisibility=hidden) */
 #if defined(__GNUC__)
@@ -130,6 +130,14 @@ typedef struct crt1d_out {
     const double* band_w; /* [n_bw][n_wl] weights, e.g. rows PAR and NIR from spectra._x_frac_in_bounds */
     int32_t n_bw;         /* 0..4 */
     double* absorbed;     /* [S][n_bw], or NULL */
+
+    /* optional float32 STORAGE of the profiles (BASELINE north_star: "optional float32 path at <= 1e-5"):
+     * 0 = float64 (the reference's layout, default); 1 = I_dr, I_df_d, I_df_u, F, x0, x1, x2 point to
+     * float arrays of the same shapes.  All arithmetic stays float64 (fp64 coefficient stage AND level stage,
+     * so the result is the float64 value rounded once: rel. err <= 6e-8); rho_c / absorbed stay float64.
+     * Halves the HBM traffic of the write-bound schemes.  Not available for n79, zq, zq_pa
+     * (CRT1D_ERR_UNSUPPORTED): they park float64 elimination scratch in the profile arrays. */
+    int32_t profile_f32;
 } crt1d_out;
 
 /* ---- library info ---------------------------------------------------------------------------- */

@@ -574,3 +574,35 @@ def test_reduced_diagnostic_mode(scheme):
     full = engine.solve(db, scheme, band_w=bw)
     torch.cuda.synchronize()
     assert torch.equal(ob.t["absorbed"], full["absorbed"])
+
+
+@pytest.mark.parametrize("scheme", ["2s", "4s", "bl", "bf", "g77"])
+@pytest.mark.parametrize("n_scen", [5, 160])
+def test_float32_profile_storage(scheme, n_scen):
+    """Optional float32 path of BASELINE.json (<= 1e-5): float64 arithmetic, float32 storage.  The stored value
+    must be the float64 result rounded once (<= 2^-24 relative), through the tile kernel (5 scenarios) and the
+    row-sweep kernels (160); diagnostics stay float64 and identical.  Tridiagonal schemes refuse."""
+    import torch
+
+    from crt1d_b200 import engine
+    from crt1d_b200 import sweep
+
+    spec = sweep.synthetic_sweep_spec(seed=0)
+    sub = spec.slice(880000, 880000 + n_scen)
+    bw = np.ones((1, spec.n_wl))
+    db = engine.DeviceBatch(sub, scheme)
+    a = engine.solve(db, scheme, band_w=bw)
+    b = engine.solve(db, scheme, band_w=bw, profile_dtype=torch.float32)
+    torch.cuda.synchronize()
+    for k in a:
+        if k in ("absorbed", "rho_c"):
+            assert b[k].dtype == torch.float64 and torch.equal(a[k], b[k]), k
+        else:
+            assert b[k].dtype == torch.float32 and b[k].shape == a[k].shape
+            assert torch.equal(b[k], a[k].to(torch.float32)), f"{scheme}.{k}: not the float64 value rounded once"
+    ref = oracle.run(scheme, sub.scenario_params(n_scen - 1)) if scheme != "4s" else None
+    if ref is not None:
+        for k in ("I_dr", "I_df_d", "I_df_u", "F"):
+            assert_close(b[k][n_scen - 1].cpu().numpy().astype(np.float64), ref[k], 1e-5, f"f32 {scheme}.{k}", atol=1e-30)
+    with pytest.raises(ValueError):
+        engine.solve(sub, "zq", profile_dtype=torch.float32)
