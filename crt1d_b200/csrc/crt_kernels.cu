@@ -250,7 +250,7 @@ size_t solve_shared_bytes(int scheme, int n_z) { return (size_t)n_level_tables(s
 // coefficient phase (fixed thread->column assignment), so it stays deterministic.
 // ---------------------------------------------------------------------------------------------
 template <int VEC, int LV, int MAXT, bool REC>
-__global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batch in, const crt1d_out out, int dbg) {
+__global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batch in, const crt1d_out out) {
     extern __shared__ double sm[];
     __shared__ double red[MAXT / 32][4];
     __shared__ int counter;
@@ -262,8 +262,6 @@ __global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batc
     double* L = sm;
     double* eK = sm + n_z;
     double* cf = sm + 2 * n_z + ((2 * n_z) & 1);  // [8][ld], 16-byte aligned
-    const int cf_off = 2 * n_z + ((2 * n_z) & 1);
-    (void)cf_off;
 
     for (int j = threadIdx.x; j < n_z; j += T) fill_level_tables<CRT1D_SCHEME_2S>(in, s, j, sm);
     if (threadIdx.x == 0) counter = 0;
@@ -283,12 +281,7 @@ __global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batc
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int c = threadIdx.x; c < n_wl; c += T) {
         const BandIn<1> b = load_bands<1>(in, s, c);
-        Coef2s k;
-        if (dbg == 2) {  // timing experiment: skip the coefficient arithmetic
-            k = {b.leaf_r[0], b.leaf_t[0], b.soil_r[0], b.Idr0[0], b.Idf0[0], b.leaf_r[0], b.leaf_t[0], b.Idr0[0]};
-        } else {
-            k = coef_2s(sc, b.leaf_r[0], b.leaf_t[0], b.soil_r[0], b.Idr0[0], b.Idf0[0]);
-        }
+        const Coef2s k = coef_2s(sc, b.leaf_r[0], b.leaf_t[0], b.soil_r[0], b.Idr0[0], b.Idf0[0]);
         cf[0 * ld + c] = k.h;
         cf[1 * ld + c] = k.Au;
         cf[2 * ld + c] = k.Bu;
@@ -322,7 +315,7 @@ __global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batc
     // Reduced-diagnostic mode: with no profile requested there is nothing to sweep -- the absorbed reduction only
     // needs the ground and top levels, which phase B evaluated.
     const bool any_profile = pI || pD || pU || pF;
-    for (; dbg != 1 && any_profile;) {  // dbg == 1: timing experiment, coefficient phase only
+    for (; any_profile;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(&counter, 1);
         item = __shfl_sync(0xffffffffu, item, 0);
@@ -410,8 +403,7 @@ static cudaError_t launch_rows_2s_t(const crt1d_batch& in, const crt1d_out& out,
     auto kern = solve_2s_rows_kernel<VEC, LV, MAXT, REC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const char* dbg = getenv("CRT1D_B200_ROWS_DEBUG");  // 1 = coefficient phase only, 2 = sweep phase only (timing experiments)
-    kern<<<(unsigned)in.n_scen, threads, smem, stream>>>(in, out, dbg ? atoi(dbg) : 0);
+    kern<<<(unsigned)in.n_scen, threads, smem, stream>>>(in, out);
     return cudaGetLastError();
 }
 
