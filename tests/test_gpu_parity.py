@@ -606,3 +606,31 @@ def test_float32_profile_storage(scheme, n_scen):
             assert_close(b[k][n_scen - 1].cpu().numpy().astype(np.float64), ref[k], 1e-5, f"f32 {scheme}.{k}", atol=1e-30)
     with pytest.raises(ValueError):
         engine.solve(sub, "zq", profile_dtype=torch.float32)
+
+
+def test_host_pointer_batch_entry_point(default_p):
+    """`crt1d_solve_host` (host buffers, H2D + kernel + D2H inside one C call) on a multi-scenario batch with
+    the fused reduction, for every scheme: must equal the device-pointer path fed the same host prologue."""
+    import torch
+
+    from crt1d_b200 import engine
+    from crt1d_b200.scenarios import ScenarioBatch
+    from crt1d_b200.solvers._plugin import solve_batch_host
+
+    nz = 15
+    lai_lib = np.stack([np.linspace(1, 0, nz) * 2.5, np.linspace(1, 0, nz) ** 1.3 * 4.0])
+    b = ScenarioBatch(
+        psi=np.radians([15.0, 50.0, 75.0]), lai_lib=lai_lib, leaf_r_lib=default_p["leaf_r"], leaf_t_lib=default_p["leaf_t"],
+        soil_r_lib=default_p["soil_r"], I_dr0_lib=default_p["I_dr0_all"], I_df0_lib=default_p["I_df0_all"],
+        lai_idx=[0, 1, 0], leaf_idx=0, soil_idx=0, sky_idx=0, leaf_angle=default_p["leaf_angle"], mla=57.0,
+        wl=default_p["wl"], dwl=default_p["dwl"],
+    )
+    bw = np.stack([np.ones(b.n_wl), np.arange(b.n_wl) / b.n_wl])
+    for scheme in FAST + ("4s",):
+        pro = engine.host_prologue(b, scheme)
+        host = solve_batch_host(b, scheme, pro, band_w=bw)
+        dev = engine.solve(engine.DeviceBatch(b, scheme, prologue=pro), scheme, band_w=bw)
+        torch.cuda.synchronize()
+        assert set(host) == set(dev)
+        for k in host:
+            assert np.array_equal(host[k], dev[k].cpu().numpy()), f"{scheme}.{k}"
