@@ -288,7 +288,7 @@ def main():
             traffic = None
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-        "kernel": ("crt::solve_2s_rows_kernel<VEC=2, LV=6, 512 threads, REC> (one CTA per scenario, row-major work items)"
+        "kernel": ("crt::solve_2s_rows_kernel<VEC=2, LV=10, 512 threads, REC> (one CTA per scenario, row-major work items)"
                    if args.scheme == "2s" and runner.chunk >= 148 and not os.environ.get("CRT1D_B200_2S_KERNEL")
                    else f"crt::solve_kernel<{args.scheme}, VEC=2> (band-tile kernel)"),
         "kernel_ms": k_ms, "bytes_per_unit": bpu,

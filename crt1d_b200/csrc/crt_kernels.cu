@@ -110,6 +110,25 @@ __device__ __forceinline__ void st_prof(void* base, bool f32, int64_t off, const
         }
     }
 }
+template <int VEC, bool F32>
+__device__ __forceinline__ void st_prof_t(void* base, int64_t off, const double (&x)[VEC]) {
+    if (base == nullptr) return;
+    if constexpr (F32) {
+        float* q = static_cast<float*>(base) + off;
+        if constexpr (VEC == 2) {
+            __stcs(reinterpret_cast<float2*>(q), make_float2((float)x[0], (float)x[1]));
+        } else {
+            __stcs(q, (float)x[0]);
+        }
+    } else {
+        double* q = static_cast<double*>(base) + off;
+        if constexpr (VEC == 2) {
+            __stcs(reinterpret_cast<double2*>(q), make_double2(x[0], x[1]));
+        } else {
+            __stcs(q, x[0]);
+        }
+    }
+}
 __device__ __forceinline__ void* prof_base(double* ptr, bool f32, int64_t elem_off) {
     if (ptr == nullptr) return nullptr;
     return f32 ? static_cast<void*>(reinterpret_cast<float*>(ptr) + elem_off) : static_cast<void*>(ptr + elem_off);
@@ -249,10 +268,31 @@ size_t solve_shared_bytes(int scheme, int n_z) { return (size_t)n_level_tables(s
 // saturates at 5.1 TB/s.  The canopy-absorbed reduction uses the ground/top levels evaluated in the
 // coefficient phase (fixed thread->column assignment), so it stays deterministic.
 // ---------------------------------------------------------------------------------------------
-template <int VEC, int LV, int MAXT, bool REC>
+constexpr int ROWS_MAX_CHUNKS = 256;  // chunks of 32 lanes per band row the row-sweep kernels support
+
+// Warp-level pieces of the row-sweep kernels' work-item protocol.
+// An item is (level group lg, chunk of 32*VEC bands).  The warp that gets a chunk's FIRST item (lg = 0) computes
+// that chunk's per-band coefficients, publishes them in shared memory and raises ready[chunk]; items of later
+// level groups wait for the flag (their producer was handed out earlier, so it is running or done: no deadlock).
+// This removes the separate coefficient phase during which an SM issued no stores (12.6 % of a CTA's life).
+__device__ __forceinline__ void rows_publish(int* ready, int chunk, int lane) {
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) *reinterpret_cast<volatile int*>(ready + chunk) = 1;
+}
+__device__ __forceinline__ void rows_wait(int* ready, int chunk, int lane) {
+    if (lane == 0) {
+        while (*reinterpret_cast<volatile int*>(ready + chunk) == 0) __nanosleep(40);
+    }
+    __syncwarp();
+    __threadfence_block();
+}
+
+template <int VEC, int LV, int MAXT, bool REC, bool F32>
 __global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batch in, const crt1d_out out) {
     extern __shared__ double sm[];
-    __shared__ double red[MAXT / 32][4];
+    __shared__ double partial[ROWS_MAX_CHUNKS][4];  // per-chunk sums of the absorbed reduction (fixed final order)
+    __shared__ int ready[ROWS_MAX_CHUNKS];
     __shared__ int counter;
     __shared__ unsigned char grp_uniform[1024];  // per level group: 1 if its levels are equally spaced (n_z <= 1024*LV)
 
@@ -262,8 +302,12 @@ __global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batc
     double* L = sm;
     double* eK = sm + n_z;
     double* cf = sm + 2 * n_z + ((2 * n_z) & 1);  // [8][ld], 16-byte aligned
+    const int n_grp = n_wl / VEC;
+    const int n_chunks = (n_grp + 31) / 32;
 
+    // ---- phase A: level tables, flags
     for (int j = threadIdx.x; j < n_z; j += T) fill_level_tables<CRT1D_SCHEME_2S>(in, s, j, sm);
+    for (int q = threadIdx.x; q < n_chunks; q += T) ready[q] = 0;
     if (threadIdx.x == 0) counter = 0;
     __syncthreads();
     if (REC) {
@@ -274,71 +318,96 @@ __global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batc
             for (int j = a + 1; j + 1 < b; ++j) u = u && fabs((L[j] - L[j + 1]) - (L[a] - L[a + 1])) <= tol;
             grp_uniform[g] = u ? 1 : 0;
         }
+        __syncthreads();
     }
 
-    // ---- phase B: per-band coefficients -> shared memory; ground/top levels for the absorbed reduction
     const Scen2s sc = scen_2s(in.psi[s], in.K_b[s], in.mu_bar[s], in.mla_deg, L[0]);
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int c = threadIdx.x; c < n_wl; c += T) {
-        const BandIn<1> b = load_bands<1>(in, s, c);
-        const Coef2s k = coef_2s(sc, b.leaf_r[0], b.leaf_t[0], b.soil_r[0], b.Idr0[0], b.Idf0[0]);
-        cf[0 * ld + c] = k.h;
-        cf[1 * ld + c] = k.Au;
-        cf[2 * ld + c] = k.Bu;
-        cf[3 * ld + c] = k.Cu;
-        cf[4 * ld + c] = k.Ad;
-        cf[5 * ld + c] = k.Bd;
-        cf[6 * ld + c] = k.Cd;
-        cf[7 * ld + c] = k.Idr0;
-        if (out.absorbed) {
-            double Ig, dg, ug, Fg, It, dt, ut, Ft;
-            level_2s(k, sc.inv_mu, L[0], eK[0], Ig, dg, ug, Fg);
-            level_2s(k, sc.inv_mu, L[n_z - 1], eK[n_z - 1], It, dt, ut, Ft);
-            const double a = absorbed_from_ends(It, Ig, dt, dg, ut, ug);
-            for (int q = 0; q < out.n_bw; ++q) acc[q] += out.band_w[(int64_t)q * n_wl + c] * a;
-        }
-    }
-    __syncthreads();
-
-    // ---- phase C: row-major work items
     const int64_t prof = (int64_t)n_z * n_wl;
-    const bool f32 = out.profile_f32 != 0;
-    void* pI = prof_base(out.I_dr, f32, s * prof);
-    void* pD = prof_base(out.I_df_d, f32, s * prof);
-    void* pU = prof_base(out.I_df_u, f32, s * prof);
-    void* pF = prof_base(out.F, f32, s * prof);
-    const int n_grp = n_wl / VEC;
-    const int n_chunks = (n_grp + 31) / 32;
-    const int n_lg = (n_z + LV - 1) / LV;
+    void* pI = prof_base(out.I_dr, F32, s * prof);
+    void* pD = prof_base(out.I_df_d, F32, s * prof);
+    void* pU = prof_base(out.I_df_u, F32, s * prof);
+    void* pF = prof_base(out.F, F32, s * prof);
+    // Reduced-diagnostic mode: with no profile requested only the first item of every chunk runs (coefficients +
+    // ground/top levels for the absorbed reduction); there is nothing to sweep.
+    const bool any_profile = pI || pD || pU || pF;
+    const int n_lg = any_profile ? (n_z + LV - 1) / LV : 1;
     const int n_items = n_chunks * n_lg;
     const int lane = threadIdx.x & 31;
-    // Reduced-diagnostic mode: with no profile requested there is nothing to sweep -- the absorbed reduction only
-    // needs the ground and top levels, which phase B evaluated.
-    const bool any_profile = pI || pD || pU || pF;
-    for (; any_profile;) {
+
+    // ---- row-major work items
+    for (;;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(&counter, 1);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
-        const int lg = item / n_chunks, g = (item - lg * n_chunks) * 32 + lane;
-        if (g >= n_grp) continue;
-        const int c0 = g * VEC;
+        const int lg = item / n_chunks, chunk = item - lg * n_chunks;
+        const int g = chunk * 32 + lane;
+        const bool valid = g < n_grp;
+        const int c0 = (valid ? g : 0) * VEC;
         Coef2s k[VEC];
-        if constexpr (VEC == 2) {
-            const double2 a0 = *reinterpret_cast<const double2*>(cf + 0 * ld + c0);
-            const double2 a1 = *reinterpret_cast<const double2*>(cf + 1 * ld + c0);
-            const double2 a2 = *reinterpret_cast<const double2*>(cf + 2 * ld + c0);
-            const double2 a3 = *reinterpret_cast<const double2*>(cf + 3 * ld + c0);
-            const double2 a4 = *reinterpret_cast<const double2*>(cf + 4 * ld + c0);
-            const double2 a5 = *reinterpret_cast<const double2*>(cf + 5 * ld + c0);
-            const double2 a6 = *reinterpret_cast<const double2*>(cf + 6 * ld + c0);
-            const double2 a7 = *reinterpret_cast<const double2*>(cf + 7 * ld + c0);
-            k[0] = {a0.x, a1.x, a2.x, a3.x, a4.x, a5.x, a6.x, a7.x};
-            k[1] = {a0.y, a1.y, a2.y, a3.y, a4.y, a5.y, a6.y, a7.y};
+        if (lg == 0) {  // first touch of this chunk: produce its coefficients (ref _solve_2s.py:65-120)
+            double ab[VEC];
+            if (valid) {
+                const BandIn<VEC> b = load_bands<VEC>(in, s, c0);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    k[v] = coef_2s(sc, b.leaf_r[v], b.leaf_t[v], b.soil_r[v], b.Idr0[v], b.Idf0[v]);
+                    cf[0 * ld + c0 + v] = k[v].h;
+                    cf[1 * ld + c0 + v] = k[v].Au;
+                    cf[2 * ld + c0 + v] = k[v].Bu;
+                    cf[3 * ld + c0 + v] = k[v].Cu;
+                    cf[4 * ld + c0 + v] = k[v].Ad;
+                    cf[5 * ld + c0 + v] = k[v].Bd;
+                    cf[6 * ld + c0 + v] = k[v].Cd;
+                    cf[7 * ld + c0 + v] = k[v].Idr0;
+                }
+            }
+            if (out.absorbed) {  // ground/top levels -> canopy-absorbed sums of this chunk, fixed lane order
+                double a4[4] = {0.0, 0.0, 0.0, 0.0};
+                if (valid) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        double Ig, dg, ug, Fg, It, dt, ut, Ft;
+                        level_2s(k[v], sc.inv_mu, L[0], eK[0], Ig, dg, ug, Fg);
+                        level_2s(k[v], sc.inv_mu, L[n_z - 1], eK[n_z - 1], It, dt, ut, Ft);
+                        ab[v] = absorbed_from_ends(It, Ig, dt, dg, ut, ug);
+                    }
+                    for (int q = 0; q < out.n_bw; ++q) {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) a4[q] += out.band_w[(int64_t)q * n_wl + c0 + v] * ab[v];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    double v = a4[q];
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+                    if (lane == 0) partial[chunk][q] = v;
+                }
+            }
+            rows_publish(ready, chunk, lane);
         } else {
-            k[0] = {cf[0 * ld + c0], cf[1 * ld + c0], cf[2 * ld + c0], cf[3 * ld + c0],
-                    cf[4 * ld + c0], cf[5 * ld + c0], cf[6 * ld + c0], cf[7 * ld + c0]};
+            rows_wait(ready, chunk, lane);
+            if (valid) {
+                if constexpr (VEC == 2) {
+                    const double2 a0 = *reinterpret_cast<const double2*>(cf + 0 * ld + c0);
+                    const double2 a1 = *reinterpret_cast<const double2*>(cf + 1 * ld + c0);
+                    const double2 a2 = *reinterpret_cast<const double2*>(cf + 2 * ld + c0);
+                    const double2 a3 = *reinterpret_cast<const double2*>(cf + 3 * ld + c0);
+                    const double2 a4 = *reinterpret_cast<const double2*>(cf + 4 * ld + c0);
+                    const double2 a5 = *reinterpret_cast<const double2*>(cf + 5 * ld + c0);
+                    const double2 a6 = *reinterpret_cast<const double2*>(cf + 6 * ld + c0);
+                    const double2 a7 = *reinterpret_cast<const double2*>(cf + 7 * ld + c0);
+                    k[0] = {a0.x, a1.x, a2.x, a3.x, a4.x, a5.x, a6.x, a7.x};
+                    k[VEC - 1] = {a0.y, a1.y, a2.y, a3.y, a4.y, a5.y, a6.y, a7.y};
+                } else {
+                    k[0] = {cf[0 * ld + c0], cf[1 * ld + c0], cf[2 * ld + c0], cf[3 * ld + c0],
+                            cf[4 * ld + c0], cf[5 * ld + c0], cf[6 * ld + c0], cf[7 * ld + c0]};
+                }
+            }
         }
+        if (!valid || !any_profile) continue;
+
         const int j0 = lg * LV, j1 = min(n_z, j0 + LV);
         // Equally spaced levels inside the group (every profile the reference's LAI generators make:
         // lai = linspace(1, 0, n) * LAI, ref ../leaf_area.py:82-88): e^{-+h L_j} advance by the constant
@@ -353,7 +422,7 @@ __global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batc
                 exp_pm(k[v].h * dL, qp[v], qm[v]);  // qp = e^{-h dL} multiplies e^{+hL}; qm = e^{+h dL} multiplies e^{-hL}
             }
         }
-        for (int j = j0; j < j1; ++j) {
+        auto one_level = [&](int j) {
             const double Lj = L[j], eKj = eK[j];
             double Idr[VEC], dn[VEC], up[VEC], F[VEC];
 #pragma unroll
@@ -367,26 +436,19 @@ __global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batc
                 }
             }
             const int64_t o = (int64_t)j * n_wl + c0;
-            st_prof<VEC>(pI, f32, o, Idr);
-            st_prof<VEC>(pD, f32, o, dn);
-            st_prof<VEC>(pU, f32, o, up);
-            st_prof<VEC>(pF, f32, o, F);
-        }
+            st_prof_t<VEC, F32>(pI, o, Idr);
+            st_prof_t<VEC, F32>(pD, o, dn);
+            st_prof_t<VEC, F32>(pU, o, up);
+            st_prof_t<VEC, F32>(pF, o, F);
+        };
+        for (int j = j0; j < j1; ++j) one_level(j);  // (a fully unrolled fixed-trip-count variant measured 2-4 % slower)
     }
 
-    if (out.absorbed) {  // fixed-order block reduction (deterministic)
-        const int warp = threadIdx.x >> 5;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            double v = acc[q];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-            if (lane == 0) red[warp][q] = v;
-        }
+    if (out.absorbed) {  // chunk sums added in chunk order: deterministic
         __syncthreads();
         if (threadIdx.x < out.n_bw) {
             double v = 0.0;
-            for (int w = 0; w < (T + 31) / 32; ++w) v += red[w][threadIdx.x];
+            for (int q = 0; q < n_chunks; ++q) v += partial[q][threadIdx.x];
             out.absorbed[s * out.n_bw + threadIdx.x] = v;
         }
     }
@@ -397,33 +459,36 @@ static size_t rows_2s_shared_bytes(int n_z, int n_wl) {
     return (size_t)(2 * n_z + ((2 * n_z) & 1) + 8 * ld) * sizeof(double);
 }
 
-template <int VEC, int LV, int MAXT, bool REC>
+template <int VEC, int LV, int MAXT, bool REC, bool F32 = false>
 static cudaError_t launch_rows_2s_t(const crt1d_batch& in, const crt1d_out& out, int threads, cudaStream_t stream) {
     const size_t smem = rows_2s_shared_bytes(in.n_z, in.n_wl);
-    auto kern = solve_2s_rows_kernel<VEC, LV, MAXT, REC>;
+    auto kern = solve_2s_rows_kernel<VEC, LV, MAXT, REC, F32>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<(unsigned)in.n_scen, threads, smem, stream>>>(in, out);
     return cudaGetLastError();
 }
 
-// rows-kernel configuration: default (LV = 6, 512 threads, recurrence) = best of the measured sweep
-// (profiles/r01_rows_kernel_config_sweep.txt).  "LV,threads,rec" in CRT1D_B200_ROWS_CFG selects one of the few
-// other compiled configurations (tests / tuning): 4,<=512,0|1   10,<=512,1   6,<=512,0   3,<=1024,1.
+// rows-kernel configuration: default (LV = 10, 512 threads, recurrence) = best of the measured sweeps
+// (profiles/r01_rows_kernel_config_sweep.txt and the later fused-coefficient runs: LV 10 > 6 > 4 by 1-3 % each).
+// "LV,threads,rec" in CRT1D_B200_ROWS_CFG selects one of the few other compiled configurations (tests / tuning):
+// 6,<=512,0|1   4,<=512,0|1   3,<=1024,1.
 template <int VEC>
 static cudaError_t launch_rows_2s(const crt1d_batch& in, const crt1d_out& out, cudaStream_t stream) {
-    int lv = 6, th = 512, rec = 1;
+    int lv = 10, th = 512, rec = 1;
     const char* env = getenv("CRT1D_B200_ROWS_CFG");
     if (env) sscanf(env, "%d,%d,%d", &lv, &th, &rec);
     if (th % 32 != 0 || th < 64 || th > 1024) th = 512;
     if (in.n_z > 1024 * 2) rec = 0;
+    if (out.profile_f32) return launch_rows_2s_t<VEC, 10, 512, true, true>(in, out, th > 512 ? 512 : th, stream);
     if (lv == 3 && rec) return launch_rows_2s_t<VEC, 3, 1024, true>(in, out, th, stream);
     if (th > 512) th = 512;
     if (lv == 4) return rec ? launch_rows_2s_t<VEC, 4, 512, true>(in, out, th, stream)
                             : launch_rows_2s_t<VEC, 4, 512, false>(in, out, th, stream);
-    if (lv == 10 && rec) return launch_rows_2s_t<VEC, 10, 512, true>(in, out, th, stream);
-    return rec ? launch_rows_2s_t<VEC, 6, 512, true>(in, out, th, stream)
-               : launch_rows_2s_t<VEC, 6, 512, false>(in, out, th, stream);
+    if (lv == 6) return rec ? launch_rows_2s_t<VEC, 6, 512, true>(in, out, th, stream)
+                            : launch_rows_2s_t<VEC, 6, 512, false>(in, out, th, stream);
+    return rec ? launch_rows_2s_t<VEC, 10, 512, true>(in, out, th, stream)
+               : launch_rows_2s_t<VEC, 10, 512, false>(in, out, th, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -521,12 +586,13 @@ struct RowsTraits<CRT1D_SCHEME_4S> {
     }
 };
 
-template <int SCHEME, int VEC, int LV, int MAXT>
+template <int SCHEME, int VEC, int LV, int MAXT, bool F32, bool FUSED>
 __global__ void __launch_bounds__(MAXT, 1) solve_rows_kernel(const crt1d_batch in, const crt1d_out out) {
     using TR = RowsTraits<SCHEME>;
     constexpr int NC = TR::NC, NF = TR::NF;
     extern __shared__ double sm[];
-    __shared__ double red[MAXT / 32][4];
+    __shared__ double partial[ROWS_MAX_CHUNKS][4];
+    __shared__ int ready[ROWS_MAX_CHUNKS];
     __shared__ int counter;
     __shared__ unsigned char grp_uniform[1024];  // 4s: level group is equally spaced (recurrence allowed)
 
@@ -535,8 +601,12 @@ __global__ void __launch_bounds__(MAXT, 1) solve_rows_kernel(const crt1d_batch i
     const int ld = (n_wl + 1) & ~1;
     const int n_tab = n_level_tables(SCHEME) * n_z;
     double* cf = sm + n_tab + (n_tab & 1);  // [NC][ld], 16-byte aligned
+    const int n_grp = n_wl / VEC;
+    const int n_chunks = (n_grp + 31) / 32;
 
+    // ---- phase A: level tables, flags
     for (int j = threadIdx.x; j < n_z; j += T) fill_level_tables<SCHEME>(in, s, j, sm);
+    for (int q = threadIdx.x; q < n_chunks; q += T) ready[q] = 0;
     if (threadIdx.x == 0) counter = 0;
     __syncthreads();
     if constexpr (SCHEME == CRT1D_SCHEME_4S) {
@@ -547,68 +617,108 @@ __global__ void __launch_bounds__(MAXT, 1) solve_rows_kernel(const crt1d_batch i
             for (int j = a + 1; j + 1 < b; ++j) u = u && fabs((sm[j] - sm[j + 1]) - (sm[a] - sm[a + 1])) <= tol;
             if (g < 1024) grp_uniform[g] = u ? 1 : 0;
         }
+        __syncthreads();
     }
 
-    // ---- phase B: coefficients -> shared memory; ground/top levels for the absorbed reduction
     const typename TR::Scen sc = TR::scen(in, s, sm);
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int c = threadIdx.x; c < n_wl; c += T) {
-        const BandIn<1> b = load_bands<1>(in, s, c);
-        const typename TR::Coef k = TR::coef(sc, b);
-        double a[NC];
-        TR::pack(k, a);
-#pragma unroll
-        for (int i = 0; i < NC; ++i) cf[i * ld + c] = a[i];
-        if (SCHEME == CRT1D_SCHEME_BF && out.rho_c) out.rho_c[s * n_wl + c] = TR::rho_c(k);
-        if (out.absorbed) {
-            double g[NF], t[NF];
-            TR::level(sc, k, sm, n_z, 0, g);
-            TR::level(sc, k, sm, n_z, n_z - 1, t);
-            const double ab = absorbed_from_ends(t[0], g[0], t[1], g[1], t[2], g[2]);
-            for (int q = 0; q < out.n_bw; ++q) acc[q] += out.band_w[(int64_t)q * n_wl + c] * ab;
-        }
-    }
-    __syncthreads();
-
-    // ---- phase C: row-major work items (LV levels x 32*VEC bands)
     const int64_t prof = (int64_t)n_z * n_wl;
-    const bool f32 = out.profile_f32 != 0;
     double* praw[7] = {out.I_dr, out.I_df_d, out.I_df_u, out.F, out.x0, out.x1, out.x2};
     void* pf[7];
+    bool any_profile = false;  // reduced-diagnostic mode: only the first item of every chunk runs
 #pragma unroll
-    for (int q = 0; q < 7; ++q) pf[q] = prof_base(praw[q], f32, s * prof);
+    for (int q = 0; q < 7; ++q) {
+        pf[q] = prof_base(praw[q], F32, s * prof);
+        any_profile = any_profile || (q < NF && pf[q] != nullptr);
+    }
     const double* idr0 = in.I_dr0_lib + (int64_t)in.sky_idx[s] * n_wl;
-    const int n_grp = n_wl / VEC;
-    const int n_chunks = (n_grp + 31) / 32;
-    const int n_items = n_chunks * ((n_z + LV - 1) / LV);
+    const int n_lg = any_profile ? (n_z + LV - 1) / LV : 1;
+    const int n_items = n_chunks * n_lg;
     const int lane = threadIdx.x & 31;
-    bool any_profile = false;  // reduced-diagnostic mode: nothing to sweep if no profile is requested
+
+    // Coefficients of one chunk (32*VEC bands, one lane per VEC adjacent bands) -> shared memory, plus the chunk's
+    // contribution to the canopy-absorbed sums from its ground and top levels (warp-reduced in fixed lane order).
+    auto produce = [&](int chunk, typename TR::Coef (&k)[VEC]) {
+        const int g = chunk * 32 + lane;
+        const bool valid = g < n_grp;
+        const int c0 = (valid ? g : 0) * VEC;
+        double a4[4] = {0.0, 0.0, 0.0, 0.0};
+        if (valid) {
+            const BandIn<VEC> b = load_bands<VEC>(in, s, c0);
 #pragma unroll
-    for (int q = 0; q < NF; ++q) any_profile = any_profile || pf[q] != nullptr;
-    for (; any_profile;) {
-        int item = 0;
-        if (lane == 0) item = atomicAdd(&counter, 1);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= n_items) break;
-        const int lg = item / n_chunks, g = (item - lg * n_chunks) * 32 + lane;
-        if (g >= n_grp) continue;
-        const int c0 = g * VEC;
-        typename TR::Coef k[VEC];
-        {
-            double a[VEC][NC];
+            for (int v = 0; v < VEC; ++v) {
+                BandIn<1> b1;
+                b1.leaf_r[0] = b.leaf_r[v];
+                b1.leaf_t[0] = b.leaf_t[v];
+                b1.soil_r[0] = b.soil_r[v];
+                b1.Idr0[0] = b.Idr0[v];
+                b1.Idf0[0] = b.Idf0[v];
+                k[v] = TR::coef(sc, b1);
+                double a[NC];
+                TR::pack(k[v], a);
 #pragma unroll
-            for (int i = 0; i < NC; ++i) {
-                if constexpr (VEC == 2) {
-                    const double2 t = *reinterpret_cast<const double2*>(cf + i * ld + c0);
-                    a[0][i] = t.x;
-                    a[1][i] = t.y;
-                } else {
-                    a[0][i] = cf[i * ld + c0];
+                for (int i = 0; i < NC; ++i) cf[i * ld + c0 + v] = a[i];
+                if (SCHEME == CRT1D_SCHEME_BF && out.rho_c) out.rho_c[s * n_wl + c0 + v] = TR::rho_c(k[v]);
+                if (out.absorbed) {
+                    double gnd[NF], top[NF];
+                    TR::level(sc, k[v], sm, n_z, 0, gnd);
+                    TR::level(sc, k[v], sm, n_z, n_z - 1, top);
+                    const double ab = absorbed_from_ends(top[0], gnd[0], top[1], gnd[1], top[2], gnd[2]);
+                    for (int q = 0; q < out.n_bw; ++q) a4[q] += out.band_w[(int64_t)q * n_wl + c0 + v] * ab;
                 }
             }
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) k[v] = TR::unpack(a[v], __ldg(idr0 + c0 + v));
         }
+        if (out.absorbed) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                double v = a4[q];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+                if (lane == 0) partial[chunk][q] = v;
+            }
+        }
+    };
+
+    if constexpr (!FUSED) {  // separate coefficient phase: warps take chunks round-robin, then everyone sweeps
+        typename TR::Coef kk[VEC];
+        for (int chunk = threadIdx.x >> 5; chunk < n_chunks; chunk += T >> 5) produce(chunk, kk);
+        __syncthreads();
+    }
+
+    // ---- row-major work items (LV levels x 32*VEC bands); FUSED: a chunk's first item produces its coefficients
+    const int first_item = (FUSED || any_profile) ? 0 : n_items;  // !FUSED + no profiles: nothing left to do
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(&counter, 1) + first_item;
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const int lg = item / n_chunks, chunk = item - lg * n_chunks;
+        const int g = chunk * 32 + lane;
+        const bool valid = g < n_grp;
+        const int c0 = (valid ? g : 0) * VEC;
+        typename TR::Coef k[VEC];
+        if (FUSED && lg == 0) {
+            produce(chunk, k);
+            rows_publish(ready, chunk, lane);
+        } else {
+            if (FUSED) rows_wait(ready, chunk, lane);
+            if (valid) {
+                double a[VEC][NC];
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    if constexpr (VEC == 2) {
+                        const double2 t = *reinterpret_cast<const double2*>(cf + i * ld + c0);
+                        a[0][i] = t.x;
+                        a[VEC - 1][i] = t.y;
+                    } else {
+                        a[0][i] = cf[i * ld + c0];
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) k[v] = TR::unpack(a[v], __ldg(idr0 + c0 + v));
+            }
+        }
+        if (!valid || !any_profile) continue;
+
         const int j0 = lg * LV, j1 = min(n_z, j0 + LV);
         // 4s on an equally spaced group: anchor the four exponentials at the group's first level and advance
         // them by constant factors (same scheme as column_4s); everything else evaluates each level directly.
@@ -654,23 +764,15 @@ __global__ void __launch_bounds__(MAXT, 1) solve_rows_kernel(const crt1d_batch i
             }
             const int64_t off = (int64_t)j * n_wl + c0;
 #pragma unroll
-            for (int q = 0; q < NF; ++q) st_prof<VEC>(pf[q], f32, off, o[q]);
+            for (int q = 0; q < NF; ++q) st_prof_t<VEC, F32>(pf[q], off, o[q]);
         }
     }
 
-    if (out.absorbed) {  // fixed-order block reduction (deterministic)
-        const int warp = threadIdx.x >> 5;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            double v = acc[q];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-            if (lane == 0) red[warp][q] = v;
-        }
+    if (out.absorbed) {  // chunk sums added in chunk order: deterministic
         __syncthreads();
         if (threadIdx.x < out.n_bw) {
             double v = 0.0;
-            for (int w = 0; w < (T + 31) / 32; ++w) v += red[w][threadIdx.x];
+            for (int q = 0; q < n_chunks; ++q) v += partial[q][threadIdx.x];
             out.absorbed[s * out.n_bw + threadIdx.x] = v;
         }
     }
@@ -683,25 +785,29 @@ static size_t rows_shared_bytes(int n_z, int n_wl) {
     return (size_t)(n_tab + (n_tab & 1) + RowsTraits<SCHEME>::NC * ld) * sizeof(double);
 }
 
+template <int SCHEME, int VEC, int LV, int MAXT, bool F32>
+static cudaError_t launch_rows_t(const crt1d_batch& in, const crt1d_out& out, int th, size_t smem, cudaStream_t stream) {
+    // 4s: its coefficient stage (eigen-system + 4x4 solve, 168 registers) is better kept as a separate phase
+    // (0.82 vs 0.77 of HBM peak when fused into the first item); bl/bf/g77 fuse it (no store-free phase).
+    constexpr bool FUSED = SCHEME != CRT1D_SCHEME_4S;
+    auto kern = solve_rows_kernel<SCHEME, VEC, LV, MAXT, F32, FUSED>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)in.n_scen, th, smem, stream>>>(in, out);
+    return cudaGetLastError();
+}
+
 template <int SCHEME, int MAXT, int LV = 6>
 static cudaError_t launch_rows(const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream) {
     const size_t smem = rows_shared_bytes<SCHEME>(in.n_z, in.n_wl);
     int th = MAXT;
     const char* env = getenv("CRT1D_B200_ROWS_THREADS");
     if (env && atoi(env) >= 64 && atoi(env) <= MAXT && atoi(env) % 32 == 0) th = atoi(env);
-    cudaError_t e;
-    if (vec2) {
-        auto kern = solve_rows_kernel<SCHEME, 2, LV, MAXT>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        kern<<<(unsigned)in.n_scen, th, smem, stream>>>(in, out);
-    } else {
-        auto kern = solve_rows_kernel<SCHEME, 1, LV, MAXT>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        kern<<<(unsigned)in.n_scen, th, smem, stream>>>(in, out);
-    }
-    return cudaGetLastError();
+    if (out.profile_f32)
+        return vec2 ? launch_rows_t<SCHEME, 2, LV, MAXT, true>(in, out, th, smem, stream)
+                    : launch_rows_t<SCHEME, 1, LV, MAXT, true>(in, out, th, smem, stream);
+    return vec2 ? launch_rows_t<SCHEME, 2, LV, MAXT, false>(in, out, th, smem, stream)
+                : launch_rows_t<SCHEME, 1, LV, MAXT, false>(in, out, th, smem, stream);
 }
 
 // Batches with at least this many scenarios go to the row-sweep kernels (one CTA per SM needs >= n_SM
@@ -715,12 +821,14 @@ cudaError_t launch_solve(int scheme, const crt1d_batch& in, const crt1d_out& out
     if (getenv("CRT1D_B200_FORCE_VEC1") != nullptr) vec2 = false;  // tuning experiments
     if (scheme == CRT1D_SCHEME_2S && in.n_scen >= scen_kernel_min_batch()) {
         const char* mode = getenv("CRT1D_B200_2S_KERNEL");  // "rows" (default) | "tile" (tuning / tests)
-        const bool rows_fit = rows_2s_shared_bytes(in.n_z, in.n_wl) <= 227u * 1024u - 4096u;
+        const int n_chunks = (in.n_wl / (vec2 ? 2 : 1) + 31) / 32;
+        const bool rows_fit = rows_2s_shared_bytes(in.n_z, in.n_wl) <= 227u * 1024u - 12288u && n_chunks <= ROWS_MAX_CHUNKS;
         if ((mode == nullptr || mode[0] == 'r') && rows_fit)
             return vec2 ? launch_rows_2s<2>(in, out, stream) : launch_rows_2s<1>(in, out, stream);
     }
     if (in.n_scen >= scen_kernel_min_batch() && getenv("CRT1D_B200_NO_ROWS") == nullptr) {
-        const size_t cap = 227u * 1024u - 2048u;  // dynamic + static shared memory of one CTA
+        const size_t cap = 227u * 1024u - 12288u;  // dynamic + ~10 KB static shared memory of one CTA
+        if ((in.n_wl / (vec2 ? 2 : 1) + 31) / 32 > ROWS_MAX_CHUNKS) goto tile;
         switch (scheme) {
             case CRT1D_SCHEME_BL:
                 if (rows_shared_bytes<CRT1D_SCHEME_BL>(in.n_z, in.n_wl) <= cap) return launch_rows<CRT1D_SCHEME_BL, 512>(in, out, vec2, stream);
@@ -738,6 +846,7 @@ cudaError_t launch_solve(int scheme, const crt1d_batch& in, const crt1d_out& out
             default: break;
         }
     }
+tile:
     switch (scheme) {
         case CRT1D_SCHEME_2S: return launch_vec<CRT1D_SCHEME_2S>(in, out, vec2, stream);
         case CRT1D_SCHEME_4S: return launch_vec<CRT1D_SCHEME_4S>(in, out, vec2, stream);

@@ -60,6 +60,36 @@ __global__ void rowmajor_kernel(double* f0, double* f1, double* f2, double* f3, 
     }
 }
 
+// the row-sweep kernel's actual store order: one CTA per scenario, warps pull (LV levels x 64 bands) items
+// from a shared counter in row-major order
+template <int POLICY>
+__global__ void items_kernel(double* f0, double* f1, double* f2, double* f3, int n_z, int n_wl, int LV) {
+    __shared__ int counter;
+    if (threadIdx.x == 0) counter = 0;
+    __syncthreads();
+    const size_t s = blockIdx.x;
+    const int n_grp = n_wl / 2, n_chunks = (n_grp + 31) / 32, n_items = n_chunks * ((n_z + LV - 1) / LV);
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(&counter, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const int lg = item / n_chunks, g = (item - lg * n_chunks) * 32 + lane;
+        if (g >= n_grp) continue;
+        const int c0 = 2 * g;
+        double v = (double)c0;
+        for (int j = lg * LV; j < min(n_z, lg * LV + LV); ++j) {
+            const size_t o = (s * n_z + j) * (size_t)n_wl + c0;
+            st16<POLICY>(f0 + o, v, v + 1);
+            st16<POLICY>(f1 + o, v + 2, v + 3);
+            st16<POLICY>(f2 + o, v + 4, v + 5);
+            st16<POLICY>(f3 + o, v + 6, v + 7);
+            v += 0.5;
+        }
+    }
+}
+
 template <class F>
 float time_ms(F f, int reps) {
     cudaEvent_t a, b;
@@ -109,5 +139,10 @@ int main() {
     ROWS(0, 1024, 60, 120 * 1024) ROWS(0, 1024, 60, 60 * 1024) ROWS(0, 512, 60, 120 * 1024) ROWS(0, 512, 60, 60 * 1024)
     ROWS(0, 544, 60, 120 * 1024) ROWS(0, 544, 60, 60*1024) ROWS(0, 352, 60, 120 * 1024) ROWS(0, 1024, 30, 120 * 1024) ROWS(0, 1024, 20, 120 * 1024)
     ROWS(0, 1024, 10, 120 * 1024) ROWS(0, 1024, 6, 120 * 1024)
+#define ITEMS(P, BLK, LVV, SMEM) { CK(cudaFuncSetAttribute(items_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+                 float ms = time_ms([&] { items_kernel<P><<<S, BLK, SMEM>>>(f[0], f[1], f[2], f[3], n_z, n_wl, LVV); }, 5); \
+                 printf("items    %-3s block=%-4d LV=%-3d smem=%-6d %8.3f ms  %8.1f GB/s\n", pol[P], BLK, LVV, SMEM, ms, gb / ms * 1e3); }
+    ITEMS(0, 512, 6, 134 * 1024) ITEMS(0, 512, 1, 134 * 1024) ITEMS(0, 512, 2, 134 * 1024) ITEMS(0, 512, 10, 134 * 1024)
+    ITEMS(0, 384, 6, 134 * 1024) ITEMS(0, 1024, 6, 134 * 1024) ITEMS(0, 512, 60, 134 * 1024) ITEMS(0, 256, 6, 134 * 1024)
     return 0;
 }
