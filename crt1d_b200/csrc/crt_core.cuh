@@ -50,6 +50,24 @@ CRT_CONST double kExpPm[12] = {
     1.0 / 479001600.0, 1.0 / 3628800.0, 1.0 / 40320.0, 1.0 / 720.0, 1.0 / 24.0, 0.5,
     1.0 / 6227020800.0, 1.0 / 39916800.0, 1.0 / 362880.0, 1.0 / 5040.0, 1.0 / 120.0, 1.0 / 6.0};
 
+// rcp_nr: 1/x for the per-level reciprocals of the Thomas sweeps.  The compiler's IEEE division costs ~20
+// issue slots on sm_100a (MUFU.RCP64H, 5 DFMA, exponent checks and a convergent slow-path branch); the
+// pivots here are O(1) and never zero, subnormal or infinite, so the seed (rcp.approx.ftz.f64: the top
+// ~20 bits) and two Newton steps suffice: 5 instructions, result within 1 ulp of the rounded quotient.
+// The host build (tests/_hostcheck) uses the plain division.
+CRT_HD double rcp_nr(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / x;
+#endif
+}
+
 CRT_HD double scale_pow2(double v, int n) {  // v * 2^n for results that stay normal
 #if defined(__CUDA_ARCH__)
     return __hiloint2double(__double2hiint(v) + (n << 20), __double2loint(v));
@@ -430,8 +448,8 @@ CRT_HD void column_g77(const ScenBf& s, const double* L, const double* eb, int n
 // ref :167-200) is reproduced row for row; the forward-sweep coefficients e, f of the two rows of
 // level j are parked in the four OUTPUT arrays at level j (I_dr <- e_up, F <- e_dn, I_df_u <- f_up,
 // I_df_d <- f_dn) and overwritten with the final values during back-substitution, so the solve needs
-// no scratch memory beyond the arrays it has to write anyway.  (Only the downward row's pair is parked;
-// the upward row's is recomputed from it in the back sweep: half the scratch traffic.)
+// no scratch memory beyond the arrays it has to write anyway.  (Only the downward row's pair of every
+// CK-th level is parked -- checkpoints; everything between is recomputed in the back sweep.)
 // Level tables: tbcum[j] = exp(-K_b L[j]) (n_z), tb[j] = exp(-K_b dlai[j]), td[j] = tau_d(dlai[j]),
 // fsun[j] = exp(-K_b laim[j]), dlai[j]  (all n_z - 1)   (ref :41-59).
 // =================================================================================================
@@ -445,130 +463,168 @@ struct ScenN79 {
 CRT_HD void n79_layer(double td, double rho, double tau, double& fiv, double& eiv) {
     const double refld = (1.0 - td) * rho;
     const double trand = (1.0 - td) * tau + td;
-    const double ir = 1.0 / refld;
+    const double ir = rcp_nr(refld);
     eiv = trand * ir;
     fiv = refld - trand * eiv;
-}
-
-CRT_HD void n79_up_row(double td, double tbcum, double tb, double rho, double tau, double Idr0, double& a, double& c,
-                       double& d) {  // ref :101-108 / :122-129
-    double fiv, eiv;
-    n79_layer(td, rho, tau, fiv, eiv);
-    a = -eiv;
-    c = -fiv;
-    d = Idr0 * tbcum * (1.0 - tb) * (rho - tau * eiv);
-}
-
-CRT_HD void n79_dn_row(double td, double tbcum, double tb, double rho, double tau, double Idr0, double& a, double& c,
-                       double& d) {  // ref :85-92 / :111-118
-    double aiv, biv;
-    n79_layer(td, rho, tau, aiv, biv);
-    a = -aiv;
-    c = -biv;
-    d = Idr0 * tbcum * (1.0 - tb) * (tau - rho * biv);
-}
-
-// Forward-sweep coefficients of the UPWARD row of level j from those of the downward row of level j-1
-// (e_prev, f_prev); level 0 is the soil row (ref :79-82).  Used identically in both sweeps, so the
-// back-substitution recomputes bit-identical values instead of loading them.
-CRT_HD void n79_up_ef(int j, const double* tbcum, const double* tb, const double* td, double rho, double tau,
-                      double soil_r, double Idr0, double e_prev, double f_prev, double& eu, double& fu) {
-    if (j == 0) {
-        eu = -soil_r;
-        fu = Idr0 * tbcum[0] * soil_r;
-    } else {
-        double a, c, d;
-        n79_up_row(td[j - 1], tbcum[j], tb[j - 1], rho, tau, Idr0, a, c, d);
-        const double r = 1.0 / (1.0 - a * e_prev);  // one reciprocal for both quotients of tdma (ref :186, :191)
-        eu = c * r;
-        fu = (d - a * f_prev) * r;
-    }
 }
 
 template <int VEC, class Out>
 CRT_HD void column_n79(const ScenN79& s, const double* tbcum, const double* tb, const double* td, const double* fsun,
                        const double* dlai, int n_z, const BandIn<VEC>& in, Out& out, double (&absorbed)[VEC]) {
-    // ---- forward sweep (ref tdma :183-192); unit diagonal.  Only the DOWNWARD row's (e, f) of each level
-    // is parked (F <- e_dn, I_df_d <- f_dn): 16 B per layer.band instead of 32.
+    const int CK = out.seg_levels();
+    // Layer coefficients are a pure function of (td, rho, tau): the upward row of level j and the downward
+    // row of level j-1 share layer j-1, and on equally spaced levels every layer has the same td, so the
+    // last evaluation is kept and reused while td repeats (td is a per-scenario table: the test is
+    // uniform over the CTA).
+    double c_td = -1.0, c_f[VEC], c_e[VEC];
+    auto layer = [&](double tdv) {
+        if (tdv != c_td) {
+            c_td = tdv;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) n79_layer(tdv, in.leaf_r[v], in.leaf_t[v], c_f[v], c_e[v]);
+        }
+    };
+    // Forward-sweep coefficients of the UPWARD row of level j from those of the downward row of level j-1
+    // (e_in, f_in); level 0 is the soil row (ref :79-82; rows :101-108 / :122-129).  Used identically in both
+    // sweeps, so the back-substitution recomputes the forward values instead of loading them.
+    auto up_rows = [&](int j, const double (&e_in)[VEC], const double (&f_in)[VEC], double (&eu)[VEC], double (&fu)[VEC]) {
+        if (j == 0) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                eu[v] = -in.soil_r[v];
+                fu[v] = in.Idr0[v] * tbcum[0] * in.soil_r[v];
+            }
+            return;
+        }
+        layer(td[j - 1]);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const double a = -c_e[v], c = -c_f[v];
+            const double d = in.Idr0[v] * tbcum[j] * (1.0 - tb[j - 1]) * (in.leaf_r[v] - in.leaf_t[v] * c_e[v]);
+            const double r = rcp_nr(1.0 - a * e_in[v]);  // one reciprocal for both quotients of tdma (ref :186, :191)
+            eu[v] = c * r;
+            fu[v] = (d - a * f_in[v]) * r;
+        }
+    };
+    // ... and of the DOWNWARD row of level j from the upward row of the same level (rows :85-92 / :111-118;
+    // top boundary :132-135).  May write its outputs over its inputs.
+    auto dn_rows = [&](int j, const double (&eu)[VEC], const double (&fu)[VEC], double (&ed)[VEC], double (&fd)[VEC]) {
+        if (j == n_z - 1) {  // top boundary: dn = sky diffuse; a = c = 0
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                ed[v] = 0.0;
+                fd[v] = in.Idf0[v];
+            }
+            return;
+        }
+        const int q = (j == 0) ? 1 : j;  // the soil row uses index 1 as shipped (ref :85-92)
+        layer(td[q]);
+        const double tbc = tbcum[q + 1 - (j == 0 ? 1 : 0)];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const double a = -c_f[v], c = -c_e[v];
+            const double d = in.Idr0[v] * tbc * (1.0 - tb[q]) * (in.leaf_t[v] - in.leaf_r[v] * c_e[v]);
+            const double r = rcp_nr(1.0 - a * eu[v]);
+            const double e_new = c * r;
+            fd[v] = (d - a * fu[v]) * r;
+            ed[v] = e_new;
+        }
+    };
+    // ---- forward sweep (ref tdma :183-192); unit diagonal.  Checkpointed: the DOWNWARD row's (e, f) of every
+    // CK-th level is parked (F <- e_dn, I_df_d <- f_dn), 16/CK B per layer.band; the back sweep re-runs the
+    // recurrence from a checkpoint through the CK levels above it into the Out object's segment store.
     double e_prev[VEC], f_prev[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) e_prev[v] = f_prev[v] = 0.0;
-    for (int j = 0; j < n_z; ++j) {
-        double ed[VEC], fd[VEC];
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            const double rho = in.leaf_r[v], tau = in.leaf_t[v], Idr0 = in.Idr0[v];
-            double eu, fu;
-            n79_up_ef(j, tbcum, tb, td, rho, tau, in.soil_r[v], Idr0, e_prev[v], f_prev[v], eu, fu);
-            if (j == n_z - 1) {  // top boundary: dn = sky diffuse   (ref :132-135); a = c = 0
-                ed[v] = 0.0;
-                fd[v] = in.Idf0[v];
-            } else {
-                const int q = (j == 0) ? 1 : j;  // the soil row uses index 1 as shipped (ref :85-92)
-                double a, c, d;
-                n79_dn_row(td[q], tbcum[q + 1 - (j == 0 ? 1 : 0)], tb[q], rho, tau, Idr0, a, c, d);
-                const double r = 1.0 / (1.0 - a * eu);
-                ed[v] = c * r;
-                fd[v] = (d - a * fu) * r;
-            }
-            e_prev[v] = ed[v];
-            f_prev[v] = fd[v];
+    const int g_last = (n_z - 1) / CK;  // segment g covers levels g CK .. min((g+1) CK, n_z) - 1
+    for (int j = 0; j < g_last * CK; ++j) {  // the top segment is left to the back sweep's recomputation
+        double eu[VEC], fu[VEC];
+        up_rows(j, e_prev, f_prev, eu, fu);
+        dn_rows(j, eu, fu, e_prev, f_prev);
+        if ((j + 1) % CK == 0) {
+            out.st_tmp(F_F, j, e_prev);
+            out.st_tmp(F_DN, j, f_prev);
         }
-        out.st_tmp(F_F, j, ed);
-        out.st_tmp(F_DN, j, fd);
     }
     // ---- back substitution (ref tdma :195-198) fused with the output stage (ref :141-161)
-    double up_above[VEC], dn_above[VEC], top[VEC][3], ed[VEC], fd[VEC];
+    double up_above[VEC], dn_above[VEC], top[VEC][3];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) up_above[v] = dn_above[v] = 0.0;
-    out.ld_tmp(F_F, n_z - 1, ed);
-    out.ld_tmp(F_DN, n_z - 1, fd);
-    for (int j = n_z - 1; j >= 0; --j) {
-        double edl[VEC], fdl[VEC], Idr[VEC], dn[VEC], up[VEC], F[VEC];  // (e, f) of the level below
-        if (j > 0) {
-            out.ld_tmp(F_F, j - 1, edl);
-            out.ld_tmp(F_DN, j - 1, fdl);
+    for (int g = g_last; g >= 0; --g) {
+        const int base = g * CK;
+        const int len = (n_z - base < CK) ? n_z - base : CK;
+        double e0[VEC], f0[VEC];  // downward row's pair of level base-1 (zeros below the soil row)
+        if (g == g_last) {        // still in registers from the forward sweep
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { e0[v] = e_prev[v]; f0[v] = f_prev[v]; }
+        } else if (g > 0) {
+            out.ld_tmp(F_F, base - 1, e0);
+            out.ld_tmp(F_DN, base - 1, f0);
         } else {
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) edl[v] = fdl[v] = 0.0;
+            for (int v = 0; v < VEC; ++v) e0[v] = f0[v] = 0.0;
         }
+        {
+            double e[VEC], f[VEC];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            double eu, fu;
-            n79_up_ef(j, tbcum, tb, td, in.leaf_r[v], in.leaf_t[v], in.soil_r[v], in.Idr0[v], edl[v], fdl[v], eu, fu);
-            dn[v] = (j == n_z - 1) ? fd[v] : fd[v] - ed[v] * up_above[v];
-            up[v] = fu - eu * dn[v];
-            Idr[v] = in.Idr0[v] * tbcum[j];                                  // ref :151
-            F[v] = Idr[v] * s.inv_mu + 2.0 * dn[v] + 2.0 * up[v];            // ref :161
+            for (int v = 0; v < VEC; ++v) { e[v] = e0[v]; f[v] = f0[v]; }
+            for (int i = 0; i < len; ++i) {
+                double eu[VEC], fu[VEC];
+                up_rows(base + i, e, f, eu, fu);
+                dn_rows(base + i, eu, fu, e, f);
+                out.seg_st(i, 0, e);
+                out.seg_st(i, 1, f);
+            }
         }
-        if (j < n_z - 1) {  // layer j (between levels j and j+1): absorbed per unit sunlit/shaded leaf area
-            double sl[VEC], sh[VEC];
+        for (int i = len - 1; i >= 0; --i) {
+            const int j = base + i;
+            double ed[VEC], fd[VEC], edl[VEC], fdl[VEC], eu[VEC], fu[VEC];  // (e, f) of this level and the level below
+            double Idr[VEC], dn[VEC], up[VEC], F[VEC];
+            out.seg_ld(i, 0, ed);
+            out.seg_ld(i, 1, fd);
+            if (i > 0) {
+                out.seg_ld(i - 1, 0, edl);
+                out.seg_ld(i - 1, 1, fdl);
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { edl[v] = e0[v]; fdl[v] = f0[v]; }
+            }
+            up_rows(j, edl, fdl, eu, fu);
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                const double one_m_om = 1.0 - (in.leaf_r[v] + in.leaf_t[v]);
-                const double direct = in.Idr0[v] * tbcum[j + 1] * (1.0 - tb[j]) * one_m_om;    // ref :145
-                const double diffuse = (dn_above[v] + up[v]) * (1.0 - td[j]) * one_m_om;       // ref :146
-                const double sun = diffuse * fsun[j] + direct;                                 // ref :147
-                const double shade = diffuse * (1.0 - fsun[j]);                                // ref :148
-                sl[v] = sun / (fsun[j] * dlai[j]);                                             // ref :154
-                sh[v] = shade / ((1.0 - fsun[j]) * dlai[j]);                                   // ref :155
+                dn[v] = (j == n_z - 1) ? fd[v] : fd[v] - ed[v] * up_above[v];
+                up[v] = fu[v] - eu[v] * dn[v];
+                Idr[v] = in.Idr0[v] * tbcum[j];                                  // ref :151
+                F[v] = Idr[v] * s.inv_mu + 2.0 * dn[v] + 2.0 * up[v];            // ref :161
             }
-            out.st(F_X0, j, sl);
-            out.st(F_X1, j, sh);
-        }
+            if (j < n_z - 1) {  // layer j (between levels j and j+1): absorbed per unit sunlit/shaded leaf area
+                double sl[VEC], sh[VEC];
+                const double inv_sl = rcp_nr(fsun[j] * dlai[j]), inv_sh = rcp_nr((1.0 - fsun[j]) * dlai[j]);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            if (j == n_z - 1) { top[v][0] = Idr[v]; top[v][1] = dn[v]; top[v][2] = up[v]; }
-            if (j == 0) absorbed[v] = absorbed_from_ends(top[v][0], Idr[v], top[v][1], dn[v], top[v][2], up[v]);
-            up_above[v] = up[v];
-            dn_above[v] = dn[v];
-            ed[v] = edl[v];
-            fd[v] = fdl[v];
+                for (int v = 0; v < VEC; ++v) {
+                    const double one_m_om = 1.0 - (in.leaf_r[v] + in.leaf_t[v]);
+                    const double direct = in.Idr0[v] * tbcum[j + 1] * (1.0 - tb[j]) * one_m_om;    // ref :145
+                    const double diffuse = (dn_above[v] + up[v]) * (1.0 - td[j]) * one_m_om;       // ref :146
+                    const double sun = diffuse * fsun[j] + direct;                                 // ref :147
+                    const double shade = diffuse * (1.0 - fsun[j]);                                // ref :148
+                    sl[v] = sun * inv_sl;                                                          // ref :154
+                    sh[v] = shade * inv_sh;                                                        // ref :155
+                }
+                out.st(F_X0, j, sl);
+                out.st(F_X1, j, sh);
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                if (j == n_z - 1) { top[v][0] = Idr[v]; top[v][1] = dn[v]; top[v][2] = up[v]; }
+                if (j == 0) absorbed[v] = absorbed_from_ends(top[v][0], Idr[v], top[v][1], dn[v], top[v][2], up[v]);
+                up_above[v] = up[v];
+                dn_above[v] = dn[v];
+            }
+            out.st(F_IDR, j, Idr);
+            out.st(F_DN, j, dn);
+            out.st(F_UP, j, up);
+            out.st(F_F, j, F);
         }
-        out.st(F_IDR, j, Idr);
-        out.st(F_DN, j, dn);
-        out.st(F_UP, j, up);
-        out.st(F_F, j, F);
     }
 }
 
@@ -579,8 +635,8 @@ CRT_HD void column_n79(const ScenN79& s, const double* tbcum, const double* tb, 
 // row 2m+1 (x = I_df0) are trivial; rows 2li-1, 2li (li = 1..m) are a tridiagonal whose coefficients
 // are identical in every real layer except next to the ghost soil (li = 1) and ghost top (li = m)
 // layers (ref :99-122).  Thomas elimination without pivoting (SuperLU in the reference; agreement
-// ~1e-14); forward coefficients of rows (2li-1, 2li) are parked at level li-1 of
-// the four main output arrays, as in column_n79.
+// ~1e-14); the forward coefficients of row 2li of every CK-th level are parked at
+// level li-1 of two of the main output arrays (checkpoints), the rest is recomputed in the back sweep.
 // =================================================================================================
 struct ScenZq {
     double inv_mu, cos_psi, tau_i, t_psi;
@@ -609,13 +665,23 @@ CRT_HD ZqRowSet zq_rows(double r_lo, double a_lo, double t_lo, double r_me, doub
     return q;
 }
 
+// Per-column constants of the zq rows.  The middle layer of every row pair is a real layer, so the twelve
+// coefficients of zq_rows() reduce to: pen and s = s_me (always), s_lo in {s, s_bot} (soil ghost below
+// li = 1), s_hi in {s, 0} (top ghost above li = m), m_lo in {m_mid, m_bot}, m_hi in {m_mid, 1}.
+// Same expressions as zq_rows(), evaluated once per column instead of once per row class.
+struct ZqCol {
+    double pen, s, s_bot, m_mid, m_bot, im_mid, im_bot;
+    double mainAB, kA, kB;  // interior rows: -s pen (both diagonals), m_mid cA, m_mid cB
+    double cA, cB;
+};
+
 // eK[j] = exp(-K L[j]) level table.
 template <int VEC, class Out>
 CRT_HD void column_zq(const ScenZq& s, const double* eK, int n_z, const BandIn<VEC>& in, Out& out,
                       double (&absorbed)[VEC]) {
     const int m = n_z;
-    ZqRowSet q_bot[VEC], q_mid[VEC], q_top[VEC], q_one[VEC];
-    double cA[VEC], cB[VEC], x0[VEC];
+    ZqCol col[VEC];
+    double x0[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
         const double bL = in.leaf_r[v], tL = in.leaf_t[v], rho = in.soil_r[v];
@@ -623,38 +689,71 @@ CRT_HD void column_zq(const ScenZq& s, const double* eK, int n_z, const BandIn<V
         const double a = 1.0 - (bL + tL);                                           // ref :88
         const double t = s.tau_i;
         const double a0 = 1.0 - rho;                                                // ghost soil layer: r=1, t=0, a=1-rho
-        q_mid[v] = zq_rows(r, a, t, r, a, t, r, a, t);
-        q_bot[v] = zq_rows(1.0, a0, 0.0, r, a, t, r, a, t);                         // li = 1
-        q_top[v] = zq_rows(r, a, t, r, a, t, 0.0, 0.0, 1.0);                        // li = m (ghost top: r=0, t=1, a=0)
-        q_one[v] = zq_rows(1.0, a0, 0.0, r, a, t, 0.0, 0.0, 1.0);                   // m == 1: both ghosts adjacent
+        ZqCol& c = col[v];
+        c.pen = t + (1.0 - t) * (1.0 - a) * (1.0 - r);
+        c.s = r * (1.0 - a) * (1.0 - t);
+        c.s_bot = 1.0 * (1.0 - a0) * (1.0 - 0.0);
+        c.m_mid = 1.0 - c.s * c.s;
+        c.m_bot = 1.0 - c.s_bot * c.s;
+        c.im_mid = 1.0 / c.m_mid;
+        c.im_bot = 1.0 / c.m_bot;
         const double r_psi = 0.5 + 0.3334 * ((bL - tL) / (bL + tL)) * s.cos_psi;    // eq. 22 (ref :35-38)
-        cA[v] = r_psi * (1.0 - s.t_psi) * (1.0 - a);                                // C[2li-1] / (m_lo S)  (ref :136-139)
-        cB[v] = (1.0 - s.t_psi) * (1.0 - a) * (1.0 - r_psi);                        // C[2li]   / (m_hi S)  (ref :140-143)
+        c.cA = r_psi * (1.0 - s.t_psi) * (1.0 - a);                                 // C[2li-1] / (m_lo S)  (ref :136-139)
+        c.cB = (1.0 - s.t_psi) * (1.0 - a) * (1.0 - r_psi);                         // C[2li]   / (m_hi S)  (ref :140-143)
+        c.mainAB = -c.s * c.pen;
+        c.kA = c.m_mid * c.cA;
+        c.kB = c.m_mid * c.cB;
         x0[v] = rho * (in.Idr0[v] * eK[0]);                                         // row 0: x0 = rho S[0]  (ref :134)
     }
-    // ---- forward sweep over li = 1..m; previous row is row 0 (e = 0, f = x0) at the start
+    // Rows 2li-1 ("A") and 2li ("B") of level li (ref :113-118):
+    //   A: sub = -pen, main = -s_lo pen, sup = m_lo, rhs = m_lo cA S;   B: sub = m_hi, main = -s_hi pen, sup = -pen, rhs = m_hi cB S
+    // Row A's forward pair from the pair of the row before it (one reciprocal per row).
+    auto rowA = [&](int li, int v, double e_in, double f_in, double& eA, double& fA) {
+        const ZqCol& c = col[v];
+        const double S = in.Idr0[v] * eK[li - 1];
+        if (li > 1) {
+            const double rA = rcp_nr(c.mainAB + c.pen * e_in);
+            eA = c.m_mid * rA;
+            fA = (c.kA * S + c.pen * f_in) * rA;
+        } else {
+            const double rA = rcp_nr(-c.s_bot * c.pen + c.pen * e_in);
+            eA = c.m_bot * rA;
+            fA = (c.m_bot * c.cA * S + c.pen * f_in) * rA;
+        }
+    };
+    // ---- forward sweep over li = 1..m; previous row is row 0 (e = 0, f = x0) at the start.
+    // Checkpointed Thomas: only every CK-th level's row-B pair (e, f) is parked in the output arrays
+    // (st_tmp: 16/CK B per layer.band of scratch traffic instead of 16 out + 16 back); the back sweep
+    // re-runs the forward recurrence from a checkpoint through the CK levels above it into the Out
+    // object's segment store (shared memory on the device) and back-substitutes through them.
+    // The recomputation uses the same inlined expressions, so it reproduces the forward values.
+    const int CK = out.seg_levels();
+    auto fwd = [&](int li, int v, double e_in, double f_in, double& eB_o, double& fB_o) {
+        const ZqCol& c = col[v];
+        double eA, fA;
+        rowA(li, v, e_in, f_in, eA, fA);
+        const double S = in.Idr0[v] * eK[li - 1];
+        if (li < m) {
+            const double rB = rcp_nr(c.mainAB - c.m_mid * eA);
+            eB_o = -c.pen * rB;
+            fB_o = (c.kB * S - c.m_mid * fA) * rB;
+        } else {  // top ghost: s_hi = 0, m_hi = 1
+            const double rB = rcp_nr(-0.0 * c.pen - eA);
+            eB_o = -c.pen * rB;
+            fB_o = (c.cB * S - fA) * rB;
+        }
+    };
     double e_prev[VEC], f_prev[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) { e_prev[v] = 0.0; f_prev[v] = x0[v]; }
-    for (int li = 1; li <= m; ++li) {
-        double eA[VEC], fA[VEC], eB[VEC], fB[VEC];
+    const int g_last = (m - 1) / CK;  // segment g covers li = g CK + 1 .. min((g+1) CK, m)
+    for (int li = 1; li <= g_last * CK; ++li) {  // the top segment is left to the back sweep's recomputation
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            const ZqRowSet& q = (m == 1) ? q_one[v] : (li == 1 ? q_bot[v] : (li == m ? q_top[v] : q_mid[v]));
-            const double S = in.Idr0[v] * eK[li - 1];
-            const double dA = q.m_lo * cA[v] * S;
-            const double dB = q.m_hi * cB[v] * S;
-            const double rA = 1.0 / (q.mainA - q.subA * e_prev[v]);  // one reciprocal per row
-            eA[v] = q.supA * rA;
-            fA[v] = (dA - q.subA * f_prev[v]) * rA;
-            const double rB = 1.0 / (q.mainB - q.subB * eA[v]);
-            eB[v] = q.supB * rB;
-            fB[v] = (dB - q.subB * fA[v]) * rB;
-            e_prev[v] = eB[v];
-            f_prev[v] = fB[v];
+        for (int v = 0; v < VEC; ++v) fwd(li, v, e_prev[v], f_prev[v], e_prev[v], f_prev[v]);
+        if (li % CK == 0) {
+            out.st_tmp(F_F, li - 1, e_prev);   // row B's pair of level li, parked at output level li-1
+            out.st_tmp(F_DN, li - 1, f_prev);
         }
-        out.st_tmp(F_F, li - 1, eB);   // only row B's pair is parked (16 B per layer.band); row A's is
-        out.st_tmp(F_DN, li - 1, fB);  // recomputed from the level below during back-substitution
     }
     // ---- back substitution + multiple-scattering correction (eq. 24, 25; ref :173-187) + outputs.
     // x[2k] = SWu0[k], x[2k+1] = SWd0[k]; x[2m+1] = I_df0 (last row: sub-diagonal is 0).  Step li knows
@@ -667,62 +766,83 @@ CRT_HD void column_zq(const ScenZq& s, const double* eK, int n_z, const BandIn<V
     double pend_SWd0[VEC];  // SWd0[li+1] = x[2li+3] for the output level j = li finished at step li
 #pragma unroll
     for (int v = 0; v < VEC; ++v) pend_SWd0[v] = 0.0;
-    double eB[VEC], fB[VEC];
-    out.ld_tmp(F_F, m - 1, eB);
-    out.ld_tmp(F_DN, m - 1, fB);
-    for (int li = m; li >= 1; --li) {
-        double eBl[VEC], fBl[VEC];  // row B of the level below = the row preceding this level's row A
-        if (li >= 2) {
-            out.ld_tmp(F_F, li - 2, eBl);
-            out.ld_tmp(F_DN, li - 2, fBl);
+    for (int g = g_last; g >= 0; --g) {
+        const int base = g * CK;
+        const int len = (m - base < CK) ? m - base : CK;
+        double e0[VEC], f0[VEC];  // row B's pair of level `base` (row 0 for the lowest segment)
+        if (g == g_last) {        // still in registers from the forward sweep
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { e0[v] = e_prev[v]; f0[v] = f_prev[v]; }
+        } else if (g > 0) {
+            out.ld_tmp(F_F, base - 1, e0);
+            out.ld_tmp(F_DN, base - 1, f0);
         } else {
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) { eBl[v] = 0.0; fBl[v] = x0[v]; }
+            for (int v = 0; v < VEC; ++v) { e0[v] = 0.0; f0[v] = x0[v]; }
         }
-        double xB[VEC], xA[VEC];
+        {
+            double e[VEC], f[VEC];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            const ZqRowSet& q = (m == 1) ? q_one[v] : (li == 1 ? q_bot[v] : (li == m ? q_top[v] : q_mid[v]));
-            const double dA = q.m_lo * cA[v] * (in.Idr0[v] * eK[li - 1]);  // same expressions as the forward sweep
-            const double rA = 1.0 / (q.mainA - q.subA * eBl[v]);
-            const double eA = q.supA * rA;
-            const double fA = (dA - q.subA * fBl[v]) * rA;
-            xB[v] = fB[v] - eB[v] * x_next[v];   // x[2li]   = SWu0[li]
-            xA[v] = fA - eA * xB[v];             // x[2li-1] = SWd0[li-1]
-            eB[v] = eBl[v];
-            fB[v] = fBl[v];
+            for (int v = 0; v < VEC; ++v) { e[v] = e0[v]; f[v] = f0[v]; }
+            for (int i = 1; i <= len; ++i) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) fwd(base + i, v, e[v], f[v], e[v], f[v]);
+                out.seg_st(i - 1, 0, e);
+                out.seg_st(i - 1, 1, f);
+            }
         }
-        // Now SWu0[li] (xB) is known: finish output level j = li (needs SWu0[li], SWd0[li+1]) -- but
-        // level index j runs 0..m-1 with I_df_u[j] = SWu[j], I_df_d[j] = SWd[j+1]; level j=li exists
-        // only for li <= m-1 and its SWd0[j+1] = x[2li+3] was x_next of the previous step (pend_SWd0).
-        if (li <= m - 1) {
-            const int j = li;
-            double Idr[VEC], dn[VEC], up[VEC], F[VEC], dn_ss[VEC], up_ss[VEC], F_ss[VEC];
+        for (int i = len; i >= 1; --i) {
+            const int li = base + i;
+            double eB[VEC], fB[VEC], eBl[VEC], fBl[VEC];  // row B of this level and of the level below
+            out.seg_ld(i - 1, 0, eB);
+            out.seg_ld(i - 1, 1, fB);
+            if (i >= 2) {
+                out.seg_ld(i - 2, 0, eBl);
+                out.seg_ld(i - 2, 1, fBl);
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { eBl[v] = e0[v]; fBl[v] = f0[v]; }
+            }
+            double xB[VEC], xA[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                const ZqRowSet& q = (j + 1 == m) ? q_top[v] : q_mid[v];  // class of li' = j+1 (>= 2 here)
-                const double SWu0 = xB[v], SWd0 = pend_SWd0[v];
-                dn[v] = (SWd0 + q.s_me * SWu0) * q.inv_m_lo;             // eq. 24 with li' = j+1  (ref :178-180)
-                up[v] = (SWu0 + q.s_lo * SWd0) * q.inv_m_lo;             // eq. 25                 (ref :183-185)
-                dn_ss[v] = SWd0;
-                up_ss[v] = SWu0;
-                Idr[v] = in.Idr0[v] * eK[j];
-                F_ss[v] = Idr[v] * s.inv_mu + 2.0 * SWu0 + 2.0 * SWd0;   // ref :206
-                F[v] = Idr[v] * s.inv_mu + 2.0 * up[v] + 2.0 * dn[v];    // ref :207
-                if (j == m - 1) { top[v][0] = Idr[v]; top[v][1] = dn[v]; top[v][2] = up[v]; }
+                double eA, fA;
+                rowA(li, v, eBl[v], fBl[v], eA, fA);  // same expressions as the forward sweep
+                xB[v] = fB[v] - eB[v] * x_next[v];   // x[2li]   = SWu0[li]
+                xA[v] = fA - eA * xB[v];             // x[2li-1] = SWd0[li-1]
             }
-            out.st(F_IDR, j, Idr);
-            out.st(F_DN, j, dn);
-            out.st(F_UP, j, up);
-            out.st(F_F, j, F);
-            out.st(F_X0, j, dn_ss);
-            out.st(F_X1, j, up_ss);
-            out.st(F_X2, j, F_ss);
-        }
+            // Now SWu0[li] (xB) is known: finish output level j = li (needs SWu0[li], SWd0[li+1]) -- but
+            // level index j runs 0..m-1 with I_df_u[j] = SWu[j], I_df_d[j] = SWd[j+1]; level j=li exists
+            // only for li <= m-1 and its SWd0[j+1] = x[2li+3] was x_next of the previous step (pend_SWd0).
+            if (li <= m - 1) {
+                const int j = li;
+                double Idr[VEC], dn[VEC], up[VEC], F[VEC], dn_ss[VEC], up_ss[VEC], F_ss[VEC];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            pend_SWd0[v] = x_next[v];  // SWd0[li] = x[2li+1], needed by output level j = li-1
-            x_next[v] = xA[v];         // x[2(li-1)+1]
+                for (int v = 0; v < VEC; ++v) {
+                    const ZqCol& c = col[v];                                 // li' = j+1 >= 2: s_lo = s_me = s, m_lo = m_mid
+                    const double SWu0 = xB[v], SWd0 = pend_SWd0[v];
+                    dn[v] = (SWd0 + c.s * SWu0) * c.im_mid;                  // eq. 24 with li' = j+1  (ref :178-180)
+                    up[v] = (SWu0 + c.s * SWd0) * c.im_mid;                  // eq. 25                 (ref :183-185)
+                    dn_ss[v] = SWd0;
+                    up_ss[v] = SWu0;
+                    Idr[v] = in.Idr0[v] * eK[j];
+                    F_ss[v] = Idr[v] * s.inv_mu + 2.0 * SWu0 + 2.0 * SWd0;   // ref :206
+                    F[v] = Idr[v] * s.inv_mu + 2.0 * up[v] + 2.0 * dn[v];    // ref :207
+                    if (j == m - 1) { top[v][0] = Idr[v]; top[v][1] = dn[v]; top[v][2] = up[v]; }
+                }
+                out.st(F_IDR, j, Idr);
+                out.st(F_DN, j, dn);
+                out.st(F_UP, j, up);
+                out.st(F_F, j, F);
+                out.st(F_X0, j, dn_ss);
+                out.st(F_X1, j, up_ss);
+                out.st(F_X2, j, F_ss);
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                pend_SWd0[v] = x_next[v];  // SWd0[li] = x[2li+1], needed by output level j = li-1
+                x_next[v] = xA[v];         // x[2(li-1)+1]
+            }
         }
     }
     // output level j = 0: SWu0[0] = x[0] = x0 - e0 x[1] with e0 = 0; SWd0[1] = pend_SWd0
@@ -730,10 +850,10 @@ CRT_HD void column_zq(const ScenZq& s, const double* eK, int n_z, const BandIn<V
         double Idr[VEC], dn[VEC], up[VEC], F[VEC], dn_ss[VEC], up_ss[VEC], F_ss[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            const ZqRowSet& q = (m == 1) ? q_one[v] : q_bot[v];  // li' = 1
+            const ZqCol& c = col[v];  // li' = 1: s_lo = s_bot, m_lo = m_bot
             const double SWu0 = x0[v], SWd0 = pend_SWd0[v];
-            dn[v] = (SWd0 + q.s_me * SWu0) * q.inv_m_lo;
-            up[v] = (SWu0 + q.s_lo * SWd0) * q.inv_m_lo;
+            dn[v] = (SWd0 + c.s * SWu0) * c.im_bot;
+            up[v] = (SWu0 + c.s_bot * SWd0) * c.im_bot;
             dn_ss[v] = SWd0;
             up_ss[v] = SWu0;
             Idr[v] = in.Idr0[v] * eK[0];
@@ -819,10 +939,10 @@ CRT_HD void column_zq_pa(const ScenZqPa& s, const double* lai, const double* eK,
             const ZqRowSet& q = (M == 1) ? q_one : (k == 1 ? q_bot : (k == M ? q_top : q_mid));
             const double Ib = eC[M + 1 - k] * IbSky;                                // f_sl[k] IbSky  (ref :165-169)
             const double dA = q.m_lo * cA * Ib, dB = q.m_hi * cB * Ib;
-            const double rA = 1.0 / (q.mainA - q.subA * eB[k - 1]);
+            const double rA = rcp_nr(q.mainA - q.subA * eB[k - 1]);
             const double eA = q.supA * rA;
             const double fA = (dA - q.subA * fB[k - 1]) * rA;
-            const double rB = 1.0 / (q.mainB - q.subB * eA);
+            const double rB = rcp_nr(q.mainB - q.subB * eA);
             eB[k] = q.supB * rB;
             fB[k] = (dB - q.subB * fA) * rB;
         }
@@ -832,7 +952,7 @@ CRT_HD void column_zq_pa(const ScenZqPa& s, const double* lai, const double* eK,
             const ZqRowSet& q = (M == 1) ? q_one : (k == 1 ? q_bot : (k == M ? q_top : q_mid));
             const double Ib = eC[M + 1 - k] * IbSky;
             const double dA = q.m_lo * cA * Ib;
-            const double rA = 1.0 / (q.mainA - q.subA * eB[k - 1]);   // row 2k-1 again, same expressions
+            const double rA = rcp_nr(q.mainA - q.subA * eB[k - 1]);   // row 2k-1 again, same expressions
             const double eA = q.supA * rA;
             const double fA = (dA - q.subA * fB[k - 1]) * rA;
             const double SWu0_k = fB[k] - eB[k] * SWd0_hi;   // x[2k]

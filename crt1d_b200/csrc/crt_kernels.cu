@@ -22,6 +22,15 @@ namespace crt {
 
 constexpr int BLOCK = 128;  // threads per CTA of the elementwise kernels (absorption)
 
+// Checkpoint spacing of the zq / n79 Thomas sweeps (levels recomputed per segment in the back sweep).
+#ifndef CRT_SEG_CK
+#define CRT_SEG_CK 10
+#endif
+constexpr int SEG_CK = CRT_SEG_CK;
+__host__ __device__ constexpr bool uses_segments(int scheme) { return scheme == CRT1D_SCHEME_ZQ || scheme == CRT1D_SCHEME_N79; }
+// doubles of level tables, rounded up so that the segment store behind them is 16-byte aligned
+__host__ __device__ inline size_t tab_doubles(int scheme, int n_z) { return ((size_t)n_level_tables(scheme) * n_z + 1) & ~(size_t)1; }
+
 // ---------------------------------------------------------------------------------------------
 // global-memory column accessor
 // ---------------------------------------------------------------------------------------------
@@ -66,6 +75,29 @@ struct GlobalOut {
         } else {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) q[v] = x[v];
+        }
+    }
+    // segment store of the checkpointed Thomas sweeps (zq, n79): SEG_CK levels x 2 values x VEC columns per
+    // thread in shared memory, laid out [slot][k][thread] so that a warp's accesses are contiguous
+    double* seg;      // this thread's first element
+    int seg_stride;   // threads per CTA
+    __device__ __forceinline__ int seg_levels() const { return SEG_CK; }
+    __device__ __forceinline__ void seg_st(int slot, int k, const double (&x)[VEC]) const {
+        double* q = seg + (int64_t)(slot * 2 + k) * seg_stride * VEC;
+        if constexpr (VEC == 2) {
+            *reinterpret_cast<double2*>(q) = make_double2(x[0], x[1]);
+        } else {
+            q[0] = x[0];
+        }
+    }
+    __device__ __forceinline__ void seg_ld(int slot, int k, double (&x)[VEC]) const {
+        const double* q = seg + (int64_t)(slot * 2 + k) * seg_stride * VEC;
+        if constexpr (VEC == 2) {
+            const double2 t = *reinterpret_cast<const double2*>(q);
+            x[0] = t.x;
+            x[1] = t.y;
+        } else {
+            x[0] = q[0];
         }
     }
     __device__ __forceinline__ void ld_tmp(int f, int j, double (&x)[VEC]) const {
@@ -193,6 +225,8 @@ __global__ void __launch_bounds__(BLK, MINB) solve_kernel(const crt1d_batch in, 
         GlobalOut<VEC> o;
         o.stride = n_wl;
         o.f32 = out.profile_f32 != 0;
+        o.seg = tab + tab_doubles(SCHEME, n_z) + threadIdx.x * VEC;
+        o.seg_stride = BLK;
         o.p[F_IDR] = static_cast<double*>(prof_base(out.I_dr, o.f32, s * prof + b0));
         o.p[F_DN] = static_cast<double*>(prof_base(out.I_df_d, o.f32, s * prof + b0));
         o.p[F_UP] = static_cast<double*>(prof_base(out.I_df_u, o.f32, s * prof + b0));
@@ -243,7 +277,8 @@ static cudaError_t launch_one(const crt1d_batch& in, const crt1d_out& out, cudaS
     const int ctas_per_scen = (tiles_per_scen + tiles_per_cta - 1) / tiles_per_cta;
     const int64_t grid = in.n_scen * ctas_per_scen;
     if (grid <= 0 || grid > 2147483647LL) return cudaErrorInvalidConfiguration;
-    const size_t smem = (size_t)n_level_tables(SCHEME) * in.n_z * sizeof(double);
+    size_t smem = (size_t)n_level_tables(SCHEME) * in.n_z * sizeof(double);
+    if (uses_segments(SCHEME)) smem = (tab_doubles(SCHEME, in.n_z) + (size_t)SEG_CK * 2 * VEC * BLK) * sizeof(double);
     auto kern = solve_kernel<SCHEME, VEC, BLK, MINB>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -264,8 +299,12 @@ template <> struct TileCfg<CRT1D_SCHEME_2S> { static constexpr int BLK = 256, MI
 template <> struct TileCfg<CRT1D_SCHEME_BL> { static constexpr int BLK = 256, MINB = 2; };   // 0.80 -> 0.87
 template <> struct TileCfg<CRT1D_SCHEME_BF> { static constexpr int BLK = 256, MINB = 2; };   // +3.5 %
 template <> struct TileCfg<CRT1D_SCHEME_G77> { static constexpr int BLK = 256, MINB = 2; };  // +3.4 %
-template <> struct TileCfg<CRT1D_SCHEME_ZQ> { static constexpr int BLK = 128, MINB = 4; };   // 4 CTAs/SM hide the Thomas latency: +14 %
-template <> struct TileCfg<CRT1D_SCHEME_N79> { static constexpr int BLK = 128, MINB = 4; };  // +22 %
+#ifndef CRT_TRI_BLK  // tuning hooks for the tridiagonal schemes (build.py `defines`)
+#define CRT_TRI_BLK 128
+#define CRT_TRI_MINB 4
+#endif
+template <> struct TileCfg<CRT1D_SCHEME_ZQ> { static constexpr int BLK = CRT_TRI_BLK, MINB = CRT_TRI_MINB; };   // 4 CTAs/SM hide the Thomas latency: +14 %
+template <> struct TileCfg<CRT1D_SCHEME_N79> { static constexpr int BLK = CRT_TRI_BLK, MINB = CRT_TRI_MINB; };  // +22 %
 
 template <int SCHEME>
 static cudaError_t launch_vec(const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream) {
@@ -273,7 +312,11 @@ static cudaError_t launch_vec(const crt1d_batch& in, const crt1d_out& out, bool 
     return vec2 ? launch_one<SCHEME, 2, B, M>(in, out, stream) : launch_one<SCHEME, 1, B, M>(in, out, stream);
 }
 
-size_t solve_shared_bytes(int scheme, int n_z) { return (size_t)n_level_tables(scheme) * n_z * sizeof(double); }
+size_t solve_shared_bytes(int scheme, int n_z) {
+    if (!uses_segments(scheme)) return (size_t)n_level_tables(scheme) * n_z * sizeof(double);
+    const int blk = scheme == CRT1D_SCHEME_ZQ ? TileCfg<CRT1D_SCHEME_ZQ>::BLK : TileCfg<CRT1D_SCHEME_N79>::BLK;
+    return (tab_doubles(scheme, n_z) + (size_t)SEG_CK * 2 * 2 * blk) * sizeof(double);
+}
 
 // ---------------------------------------------------------------------------------------------
 // 2s row-sweep kernel: ONE CTA = one whole scenario, per-band coefficients in SHARED MEMORY.

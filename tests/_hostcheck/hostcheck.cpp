@@ -25,6 +25,16 @@ struct HostOut {
         if (p[f]) p[f][(int64_t)j * stride + v] = x;
     }
     void st_tmp(int f, int j, const double (&x)[VEC]) const { st(f, j, x); }
+    // segment store of the checkpointed Thomas sweeps (shared memory on the device)
+    static constexpr int CK = 8;
+    mutable double seg_buf[CK][2][VEC];
+    int seg_levels() const { return CK; }
+    void seg_st(int slot, int k, const double (&x)[VEC]) const {
+        for (int v = 0; v < VEC; ++v) seg_buf[slot][k][v] = x[v];
+    }
+    void seg_ld(int slot, int k, double (&x)[VEC]) const {
+        for (int v = 0; v < VEC; ++v) x[v] = seg_buf[slot][k][v];
+    }
     void ld_tmp(int f, int j, double (&x)[VEC]) const {
         for (int v = 0; v < VEC; ++v) x[v] = p[f][(int64_t)j * stride + v];
     }
