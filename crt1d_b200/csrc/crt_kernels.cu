@@ -34,42 +34,58 @@ __host__ __device__ inline size_t tab_doubles(int scheme, int n_z) { return ((si
 // ---------------------------------------------------------------------------------------------
 // global-memory column accessor
 // ---------------------------------------------------------------------------------------------
+// streaming store of VEC doubles to a typed cursor (float cursors round once)
 template <int VEC>
+__device__ __forceinline__ void st_raw(double* q, const double (&x)[VEC]) {
+    if constexpr (VEC == 2) {
+        __stcs(reinterpret_cast<double2*>(q), make_double2(x[0], x[1]));
+    } else {
+        __stcs(q, x[0]);
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void st_raw(float* q, const double (&x)[VEC]) {
+    if constexpr (VEC == 2) {
+        __stcs(reinterpret_cast<float2*>(q), make_float2((float)x[0], (float)x[1]));
+    } else {
+        __stcs(q, (float)x[0]);
+    }
+}
+
+// Fields are addressed as  base[f] + off + j * stride : `base` are the caller's field pointers (uniform:
+// kernel parameters, they cost no per-thread registers), `off` the thread's element offset of
+// (scenario, level 0, first band) -- `xoff` for the extra-output slots, whose row count can differ.
+// FAST = every field of the scheme requested and float64 storage: no null checks, no dtype switch
+// (15 -> 3 issue slots per store); the general path keeps both.  BLK = threads per CTA.
+template <int VEC, bool FAST, int BLK>
 struct GlobalOut {
-    double* p[N_FIELDS];  // pre-offset to (scenario, level 0, first band of this thread); nullptr = skip
-    int64_t stride;       // elements between consecutive levels (= n_wl)
-    bool f32;             // float32 storage: p[] really are float* (pre-offset in floats)
+    double* base[N_FIELDS];
+    int64_t off, xoff, stride;
+    bool f32;  // float32 storage (general path only): base[] really are float*
+
+    __device__ __forceinline__ int64_t at(int f, int j) const { return (f >= F_X0 ? xoff : off) + (int64_t)j * stride; }
 
     // final results: written once, never re-read by this kernel -> streaming (evict-first) stores
     __device__ __forceinline__ void st(int f, int j, const double (&x)[VEC]) const {
-        double* q = p[f];
-        if (q == nullptr) return;
-        if (f32) {
-            float* qf = reinterpret_cast<float*>(q) + (int64_t)j * stride;
-            if constexpr (VEC == 2) {
-                __stcs(reinterpret_cast<float2*>(qf), make_float2((float)x[0], (float)x[1]));
-            } else {
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) __stcs(qf + v, (float)x[v]);
-            }
-            return;
-        }
-        q += (int64_t)j * stride;
-        if constexpr (VEC == 2) {
-            __stcs(reinterpret_cast<double2*>(q), make_double2(x[0], x[1]));
+        if constexpr (FAST) {
+            st_raw<VEC>(base[f] + at(f, j), x);
         } else {
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) __stcs(q + v, x[v]);
+            if (base[f] == nullptr) return;
+            if (f32) {
+                st_raw<VEC>(reinterpret_cast<float*>(base[f]) + at(f, j), x);
+            } else {
+                st_raw<VEC>(base[f] + at(f, j), x);
+            }
         }
     }
-    // one column at a time (zq_pa finishes each column before starting the next)
+    // one column at a time (zq_pa finishes each column before starting the next); float64 only
     __device__ __forceinline__ void st1(int f, int j, int v, double x) const {
-        if (p[f] != nullptr) __stcs(p[f] + (int64_t)j * stride + v, x);  // zq_pa: float64 only
+        if (FAST || base[f] != nullptr) __stcs(base[f] + at(f, j) + v, x);
     }
     // elimination scratch parked in the output arrays: re-read by the same thread during
     // back-substitution -> default (write-back, L2-resident) stores
     __device__ __forceinline__ void st_tmp(int f, int j, const double (&x)[VEC]) const {
-        double* q = p[f] + (int64_t)j * stride;
+        double* q = base[f] + at(f, j);
         if constexpr (VEC == 2) {
             *reinterpret_cast<double2*>(q) = make_double2(x[0], x[1]);
         } else {
@@ -77,31 +93,8 @@ struct GlobalOut {
             for (int v = 0; v < VEC; ++v) q[v] = x[v];
         }
     }
-    // segment store of the checkpointed Thomas sweeps (zq, n79): SEG_CK levels x 2 values x VEC columns per
-    // thread in shared memory, laid out [slot][k][thread] so that a warp's accesses are contiguous
-    double* seg;      // this thread's first element
-    int seg_stride;   // threads per CTA
-    __device__ __forceinline__ int seg_levels() const { return SEG_CK; }
-    __device__ __forceinline__ void seg_st(int slot, int k, const double (&x)[VEC]) const {
-        double* q = seg + (int64_t)(slot * 2 + k) * seg_stride * VEC;
-        if constexpr (VEC == 2) {
-            *reinterpret_cast<double2*>(q) = make_double2(x[0], x[1]);
-        } else {
-            q[0] = x[0];
-        }
-    }
-    __device__ __forceinline__ void seg_ld(int slot, int k, double (&x)[VEC]) const {
-        const double* q = seg + (int64_t)(slot * 2 + k) * seg_stride * VEC;
-        if constexpr (VEC == 2) {
-            const double2 t = *reinterpret_cast<const double2*>(q);
-            x[0] = t.x;
-            x[1] = t.y;
-        } else {
-            x[0] = q[0];
-        }
-    }
     __device__ __forceinline__ void ld_tmp(int f, int j, double (&x)[VEC]) const {
-        const double* q = p[f] + (int64_t)j * stride;
+        const double* q = base[f] + at(f, j);
         if constexpr (VEC == 2) {
             const double2 t = __ldcs(reinterpret_cast<const double2*>(q));  // last use: evict-first
             x[0] = t.x;
@@ -109,6 +102,28 @@ struct GlobalOut {
         } else {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) x[v] = __ldcs(q + v);
+        }
+    }
+    // segment store of the checkpointed Thomas sweeps (zq, n79): SEG_CK levels x 2 values x VEC columns per
+    // thread in shared memory, laid out [slot][k][thread] so that a warp's accesses are contiguous
+    double* seg;  // this thread's first element
+    __device__ __forceinline__ int seg_levels() const { return SEG_CK; }
+    __device__ __forceinline__ void seg_st(int slot, int k, const double (&x)[VEC]) const {
+        double* q = seg + (slot * 2 + k) * (BLK * VEC);
+        if constexpr (VEC == 2) {
+            *reinterpret_cast<double2*>(q) = make_double2(x[0], x[1]);
+        } else {
+            q[0] = x[0];
+        }
+    }
+    __device__ __forceinline__ void seg_ld(int slot, int k, double (&x)[VEC]) const {
+        const double* q = seg + (slot * 2 + k) * (BLK * VEC);
+        if constexpr (VEC == 2) {
+            const double2 t = *reinterpret_cast<const double2*>(q);
+            x[0] = t.x;
+            x[1] = t.y;
+        } else {
+            x[0] = q[0];
         }
     }
 };
@@ -144,24 +159,6 @@ __device__ __forceinline__ void st_prof(void* base, bool f32, int64_t off, const
         }
     }
 }
-// streaming store of VEC doubles to a typed cursor (float cursors round once)
-template <int VEC>
-__device__ __forceinline__ void st_raw(double* q, const double (&x)[VEC]) {
-    if constexpr (VEC == 2) {
-        __stcs(reinterpret_cast<double2*>(q), make_double2(x[0], x[1]));
-    } else {
-        __stcs(q, x[0]);
-    }
-}
-template <int VEC>
-__device__ __forceinline__ void st_raw(float* q, const double (&x)[VEC]) {
-    if constexpr (VEC == 2) {
-        __stcs(reinterpret_cast<float2*>(q), make_float2((float)x[0], (float)x[1]));
-    } else {
-        __stcs(q, (float)x[0]);
-    }
-}
-
 template <int VEC, bool F32>
 __device__ __forceinline__ void st_prof_t(void* base, int64_t off, const double (&x)[VEC]) {
     if (base == nullptr) return;
@@ -199,7 +196,7 @@ __device__ __forceinline__ void st_vec(double* base, int64_t off, const double (
 // ---------------------------------------------------------------------------------------------
 // the solver kernel
 // ---------------------------------------------------------------------------------------------
-template <int SCHEME, int VEC, int BLK, int MINB>
+template <int SCHEME, int VEC, int BLK, int MINB, bool FAST>
 __global__ void __launch_bounds__(BLK, MINB) solve_kernel(const crt1d_batch in, const crt1d_out out, int tiles_per_scen,
                                                           int tiles_per_cta) {
     extern __shared__ double tab[];
@@ -222,18 +219,19 @@ __global__ void __launch_bounds__(BLK, MINB) solve_kernel(const crt1d_batch in, 
         const int b0 = (t * BLK + threadIdx.x) * VEC;
         if (b0 >= n_wl) continue;
         const BandIn<VEC> b = load_bands<VEC>(in, s, b0);
-        GlobalOut<VEC> o;
+        GlobalOut<VEC, FAST, BLK> o;
         o.stride = n_wl;
         o.f32 = out.profile_f32 != 0;
         o.seg = tab + tab_doubles(SCHEME, n_z) + threadIdx.x * VEC;
-        o.seg_stride = BLK;
-        o.p[F_IDR] = static_cast<double*>(prof_base(out.I_dr, o.f32, s * prof + b0));
-        o.p[F_DN] = static_cast<double*>(prof_base(out.I_df_d, o.f32, s * prof + b0));
-        o.p[F_UP] = static_cast<double*>(prof_base(out.I_df_u, o.f32, s * prof + b0));
-        o.p[F_F] = static_cast<double*>(prof_base(out.F, o.f32, s * prof + b0));
-        o.p[F_X0] = static_cast<double*>(prof_base(out.x0, o.f32, s * xprof + b0));
-        o.p[F_X1] = static_cast<double*>(prof_base(out.x1, o.f32, s * xprof + b0));
-        o.p[F_X2] = static_cast<double*>(prof_base(out.x2, o.f32, s * xprof + b0));
+        o.off = s * prof + b0;
+        o.xoff = s * xprof + b0;
+        o.base[F_IDR] = out.I_dr;
+        o.base[F_DN] = out.I_df_d;
+        o.base[F_UP] = out.I_df_u;
+        o.base[F_F] = out.F;
+        o.base[F_X0] = out.x0;
+        o.base[F_X1] = out.x1;
+        o.base[F_X2] = out.x2;
         double rho_c[VEC], ab[VEC];
         solve_column_group<SCHEME, VEC>(in, s, tab, b, o, rho_c, ab);
         if constexpr (SCHEME == CRT1D_SCHEME_BF) {
@@ -269,6 +267,15 @@ __global__ void __launch_bounds__(BLK, MINB) solve_kernel(const crt1d_batch in, 
     }
 }
 
+// Number of output fields a scheme writes (4 profiles + its extra slots).
+__host__ __device__ constexpr int n_out_fields(int scheme) {
+    return scheme == CRT1D_SCHEME_ZQ ? 7 : scheme == CRT1D_SCHEME_N79 ? 6 : (scheme == CRT1D_SCHEME_BF || scheme == CRT1D_SCHEME_G77) ? 7 : 4;
+}
+// The compile-time fast store path exists for the schemes whose only kernel this is.
+__host__ __device__ constexpr bool has_fast_tile(int scheme) {
+    return scheme == CRT1D_SCHEME_ZQ || scheme == CRT1D_SCHEME_N79 || scheme == CRT1D_SCHEME_ZQ_PA;
+}
+
 template <int SCHEME, int VEC, int BLK, int MINB>
 static cudaError_t launch_one(const crt1d_batch& in, const crt1d_out& out, cudaStream_t stream) {
     const int cols = BLK * VEC;
@@ -279,7 +286,13 @@ static cudaError_t launch_one(const crt1d_batch& in, const crt1d_out& out, cudaS
     if (grid <= 0 || grid > 2147483647LL) return cudaErrorInvalidConfiguration;
     size_t smem = (size_t)n_level_tables(SCHEME) * in.n_z * sizeof(double);
     if (uses_segments(SCHEME)) smem = (tab_doubles(SCHEME, in.n_z) + (size_t)SEG_CK * 2 * VEC * BLK) * sizeof(double);
-    auto kern = solve_kernel<SCHEME, VEC, BLK, MINB>;
+    auto kern = solve_kernel<SCHEME, VEC, BLK, MINB, false>;
+    if constexpr (has_fast_tile(SCHEME)) {
+        double* const f[7] = {out.I_dr, out.I_df_d, out.I_df_u, out.F, out.x0, out.x1, out.x2};
+        bool all = out.profile_f32 == 0;
+        for (int q = 0; q < n_out_fields(SCHEME); ++q) all = all && f[q] != nullptr;
+        if (all) kern = solve_kernel<SCHEME, VEC, BLK, MINB, true>;
+    }
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
