@@ -889,30 +889,47 @@ struct ScenZqPa {
     int M;
 };
 
-// np.interp(x, xp, fp) for ascending xp[0..n-1] (numpy's rules at and beyond the ends, ref :359-361)
-CRT_HD double interp_np(double x, const double* xp, const double* fp_rev, int n, double dl) {
-    // fp_rev is indexed so that the value at xp[i] is fp_rev[n - 1 - i]
-    if (x < xp[0]) return fp_rev[n - 1];
-    if (x > xp[n - 1]) return fp_rev[0];
+// np.interp(x, xp, .) for ascending xp[0..n-1] (numpy's rules at and beyond the ends, ref :359-361), reduced
+// to what does not depend on the interpolated array: with values stored in reverse (value at xp[i] is
+// SW[n-1-i], ref :354-358) the result is   t < 0 ? SW[k-1] : ((SW[k-1] - SW[k]) * w) * t + SW[k].
+// k in 1..n-1 identifies the grid interval (k, k-1); t = x - xp[i] (or 0 for an exact hit / x < xp[0],
+// or -1 for x at or beyond the last grid point, where numpy returns the end value itself); w = 1/(xp[i+1]-xp[i]).
+CRT_HD void interp_np_prepare(double x, const double* xp, int n, double dl, int& k, double& t, double& w) {
+    w = 0.0;
+    if (x < xp[0]) { k = n - 1; t = 0.0; return; }
+    if (x > xp[n - 1]) { k = 1; t = -1.0; return; }
     int j = (int)(x / dl);
     if (j > n - 1) j = n - 1;
     if (j < 0) j = 0;
     while (j > 0 && xp[j] > x) --j;
     while (j < n - 1 && xp[j + 1] <= x) ++j;
-    if (j == n - 1 || xp[j] == x) return fp_rev[n - 1 - j];
-    const double y0 = fp_rev[n - 1 - j], y1 = fp_rev[n - 2 - j];
-    const double slope = (y1 - y0) / (xp[j + 1] - xp[j]);
-    return slope * (x - xp[j]) + y0;
+    if (j == n - 1) { k = 1; t = -1.0; return; }
+    k = n - 1 - j;
+    if (xp[j] == x) { t = 0.0; return; }
+    t = x - xp[j];
+    w = 1.0 / (xp[j + 1] - xp[j]);
 }
 
-// lai[j]: the caller's cumulative-LAI levels; eK[j] = exp(-Kb lai[j]); cum[i] (i = 0..M): running sum of
-// LAI/M as np.cumsum produces it (ref :161); eC[i] = exp(-Kb cum[i]).
+// eK[j] = exp(-Kb lai[j]) on the caller's levels; eC[i] = exp(-Kb cum[i]) on the M-grid (cum = running sum
+// of LAI/M as np.cumsum produces it, ref :161); kk/tt/ww: interp_np_prepare() of every caller level;
+// ord: the caller's levels sorted by descending kk (the order in which the back sweep can finish them).
+//
+// The M-grid solve is the checkpointed Thomas sweep of column_zq (checkpoints in the Out object's segment
+// store: slots CK.. hold the checkpoints, slots 0..CK-1 the segment being back-substituted).  The back sweep
+// runs from the top of the canopy down and the corrected fluxes (eq. 24/25, ref :286-345) of grid pair k are
+// final at step k, so the interpolation to the caller's levels (ref :350-361) is streamed: as soon as both
+// ends of a grid interval are final, every caller level inside it is interpolated and written.  Nothing of
+// the M-grid is stored per thread beyond a three-value window (the first version kept four 101-element
+// work arrays per thread in local memory and ran at a third of this speed).
 template <int VEC, class Out>
-CRT_HD void column_zq_pa(const ScenZqPa& s, const double* lai, const double* eK, const double* cum, const double* eC,
-                         int n_z, const BandIn<VEC>& in, Out& out, double (&absorbed)[VEC]) {
+CRT_HD void column_zq_pa(const ScenZqPa& s, const double* eK, const double* eC, const double* kk, const double* tt,
+                         const double* ww, const double* ord, int n_z, const BandIn<VEC>& in, Out& out,
+                         double (&absorbed)[VEC]) {
     const int M = s.M;
     const double dl = s.LAI / M;
     const double taub = exp(-s.Kb * dl);                                            // ref :173
+    ZqCol col[VEC];
+    double x0[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
         const double bL = in.leaf_r[v], tLf = in.leaf_t[v], rho = in.soil_r[v];
@@ -922,72 +939,178 @@ CRT_HD void column_zq_pa(const ScenZqPa& s, const double* lai, const double* eK,
         const double rb = 0.5 + 0.3334 * (rL - tL) / (rL + tL) * s.cos_psi;         // ref :185
         const double rd = 2.0 / 3.0 * rL / (rL + tL) + 1.0 / 3.0 * tL / (rL + tL);  // ref :186
         const double t = s.tau_d, a0 = 1.0 - rho;
-        const ZqRowSet q_mid = zq_rows(rd, aL, t, rd, aL, t, rd, aL, t);
-        const ZqRowSet q_bot = zq_rows(1.0, a0, 0.0, rd, aL, t, rd, aL, t);         // k = 1 (soil below)
-        const ZqRowSet q_top = zq_rows(rd, aL, t, rd, aL, t, 0.0, 0.0, t);          // k = M (rd[M+1] = 0)
-        const ZqRowSet q_one = zq_rows(1.0, a0, 0.0, rd, aL, t, 0.0, 0.0, t);
-        const double cA = rb * (1.0 - taub) * (1.0 - aL);                           // ref :243-256
-        const double cB = (1.0 - taub) * (1.0 - aL) * (1.0 - rb);                   // ref :257-271
-        const double IbSky = in.Idr0[v], IdSky = in.Idf0[v];
-        const double x0 = rho * (eC[M] * IbSky);                                    // C[0] = SoilAlbedo Ib[0]  (ref :241)
-
-        double eB[ZQPA_MAX_M + 1], fB[ZQPA_MAX_M + 1];  // forward coefficients of rows 2k (row 2k-1's are recomputed)
-        double SWd[ZQPA_MAX_M + 1], SWu[ZQPA_MAX_M + 1];
-        eB[0] = 0.0;   // row 0: x[0] = x0
-        fB[0] = x0;
-        for (int k = 1; k <= M; ++k) {  // forward elimination, rows 2k-1 and 2k
-            const ZqRowSet& q = (M == 1) ? q_one : (k == 1 ? q_bot : (k == M ? q_top : q_mid));
-            const double Ib = eC[M + 1 - k] * IbSky;                                // f_sl[k] IbSky  (ref :165-169)
-            const double dA = q.m_lo * cA * Ib, dB = q.m_hi * cB * Ib;
-            const double rA = rcp_nr(q.mainA - q.subA * eB[k - 1]);
-            const double eA = q.supA * rA;
-            const double fA = (dA - q.subA * fB[k - 1]) * rA;
-            const double rB = rcp_nr(q.mainB - q.subB * eA);
-            eB[k] = q.supB * rB;
-            fB[k] = (dB - q.subB * fA) * rB;
+        ZqCol& c = col[v];
+        c.pen = t + (1.0 - t) * (1.0 - aL) * (1.0 - rd);
+        c.s = rd * (1.0 - aL) * (1.0 - t);
+        c.s_bot = 1.0 * (1.0 - a0) * (1.0 - 0.0);                                   // k = 1: soil below
+        c.m_mid = 1.0 - c.s * c.s;
+        c.m_bot = 1.0 - c.s_bot * c.s;
+        c.im_mid = 1.0 / c.m_mid;
+        c.im_bot = 1.0 / c.m_bot;
+        c.cA = rb * (1.0 - taub) * (1.0 - aL);                                      // ref :243-256
+        c.cB = (1.0 - taub) * (1.0 - aL) * (1.0 - rb);                              // ref :257-271
+        c.mainAB = -c.s * c.pen;
+        c.kA = c.m_mid * c.cA;
+        c.kB = c.m_mid * c.cB;
+        x0[v] = rho * (eC[M] * in.Idr0[v]);                                         // C[0] = SoilAlbedo Ib[0]  (ref :241)
+    }
+    // rows 2k-1 ("A") and 2k ("B") of grid layer k, as in column_zq (ref :195-236); Ib[k] = f_sl[k] IbSky (ref :165-169)
+    auto rowA = [&](int k, int v, double e_in, double f_in, double& eA, double& fA) {
+        const ZqCol& c = col[v];
+        const double Ib = eC[M + 1 - k] * in.Idr0[v];
+        if (k > 1) {
+            const double rA = rcp_nr(c.mainAB + c.pen * e_in);
+            eA = c.m_mid * rA;
+            fA = (c.kA * Ib + c.pen * f_in) * rA;
+        } else {
+            const double rA = rcp_nr(-c.s_bot * c.pen + c.pen * e_in);
+            eA = c.m_bot * rA;
+            fA = (c.m_bot * c.cA * Ib + c.pen * f_in) * rA;
         }
-        // back substitution: SWu0[k] = x[2k], SWd0[k] = x[2k+1]; multiple scattering eq. 24/25 (ref :286-345)
-        double SWd0_hi = IdSky;  // x[2M+1]
-        for (int k = M; k >= 1; --k) {
-            const ZqRowSet& q = (M == 1) ? q_one : (k == 1 ? q_bot : (k == M ? q_top : q_mid));
-            const double Ib = eC[M + 1 - k] * IbSky;
-            const double dA = q.m_lo * cA * Ib;
-            const double rA = rcp_nr(q.mainA - q.subA * eB[k - 1]);   // row 2k-1 again, same expressions
-            const double eA = q.supA * rA;
-            const double fA = (dA - q.subA * fB[k - 1]) * rA;
-            const double SWu0_k = fB[k] - eB[k] * SWd0_hi;   // x[2k]
-            const double SWd0_lo = fA - eA * SWu0_k;         // x[2k-1] = SWd0[k-1]
-            SWd[k] = SWd0_hi;    // temporarily SWd0[k]
-            SWu[k] = SWu0_k;     // temporarily SWu0[k]
-            SWd0_hi = SWd0_lo;
+    };
+    auto fwd = [&](int k, int v, double e_in, double f_in, double& eB_o, double& fB_o) {
+        const ZqCol& c = col[v];
+        double eA, fA;
+        rowA(k, v, e_in, f_in, eA, fA);
+        const double Ib = eC[M + 1 - k] * in.Idr0[v];
+        if (k < M) {
+            const double rB = rcp_nr(c.mainAB - c.m_mid * eA);
+            eB_o = -c.pen * rB;
+            fB_o = (c.kB * Ib - c.m_mid * fA) * rB;
+        } else {  // k = M: nothing reflects down from above the canopy (rd[M+1] = 0)
+            const double rB = rcp_nr(-0.0 * c.pen - eA);
+            eB_o = -c.pen * rB;
+            fB_o = (c.cB * Ib - fA) * rB;
         }
-        SWu[0] = x0;             // SWu0[0] = x[0]
-        SWd[0] = SWd0_hi;        // SWd0[0] (unused by the correction)
-        for (int k = 0; k < M; ++k) {  // D_k couples layers k and k+1: row class of li = k+1
-            const ZqRowSet& q = (M == 1) ? q_one : (k + 1 == 1 ? q_bot : (k + 1 == M ? q_top : q_mid));
-            const double SWd0_k1 = SWd[k + 1], SWu0_k = SWu[k];
-            const double newd = (SWd0_k1 + SWu0_k * q.s_me) * q.inv_m_lo;           // eq. 24 (ref :288-312)
-            const double newu = (SWu0_k + SWd0_k1 * q.s_lo) * q.inv_m_lo;           // eq. 25 (ref :318-342)
-            SWd[k + 1] = newd;   // SWd0[k+1] is not needed again (pair k+1 uses SWd0[k+2], SWu0[k+1])
-            SWu[k] = newu;       // SWu0[k] is not needed again
-        }
-        SWd[0] = SWd[1];         // ref :313
-        SWu[M] = SWu[M - 1];     // ref :343
-        // back to the caller's levels (ref :350-361) and outputs (ref :403-407)
-        double gnd[3] = {0, 0, 0};
-        for (int j = 0; j < n_z; ++j) {
-            const double dn = interp_np(lai[j], cum, SWd, M + 1, dl);
-            const double up = interp_np(lai[j], cum, SWu, M + 1, dl);
-            const double Idr = IbSky * eK[j];
-            const double F = Idr * s.inv_mu + 2.0 * up + 2.0 * dn;
-            if (j == 0) { gnd[0] = Idr; gnd[1] = dn; gnd[2] = up; }
-            if (j == n_z - 1) absorbed[v] = absorbed_from_ends(Idr, gnd[0], dn, gnd[1], up, gnd[2]);
-            out.st1(F_IDR, j, v, Idr);
-            out.st1(F_DN, j, v, dn);
-            out.st1(F_UP, j, v, up);
-            out.st1(F_F, j, v, F);
+    };
+    const int CK = out.seg_levels();
+    double e_prev[VEC], f_prev[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { e_prev[v] = 0.0; f_prev[v] = x0[v]; }
+    const int g_last = (M - 1) / CK;  // segment g covers k = g CK + 1 .. min((g+1) CK, M)
+    for (int k = 1; k <= g_last * CK; ++k) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) fwd(k, v, e_prev[v], f_prev[v], e_prev[v], f_prev[v]);
+        if (k % CK == 0) {
+            out.seg_st(CK + k / CK, 0, e_prev);
+            out.seg_st(CK + k / CK, 1, f_prev);
         }
     }
+    // ---- streamed interpolation + outputs (ref :350-361, :403-407).  D[k] = SWd[k], U[k] = SWu[k] after the
+    // correction; interval (k, k-1) needs D[k], D[k-1], U[k], U[k-1].
+    int jc = 0;  // next entry of `ord`
+    double gnd[VEC][3] = {}, top[VEC][3] = {};
+    auto emit = [&](int k, const double (&Dk)[VEC], const double (&Dk1)[VEC], const double (&Uk)[VEC], const double (&Uk1)[VEC]) {
+        while (jc < n_z) {
+            const int j = (int)ord[jc];
+            if ((int)kk[j] != k) break;
+            ++jc;
+            const double t = tt[j], w = ww[j];
+            double Idr[VEC], dn[VEC], up[VEC], F[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                dn[v] = (t < 0.0) ? Dk1[v] : ((Dk1[v] - Dk[v]) * w) * t + Dk[v];
+                up[v] = (t < 0.0) ? Uk1[v] : ((Uk1[v] - Uk[v]) * w) * t + Uk[v];
+                Idr[v] = in.Idr0[v] * eK[j];
+                F[v] = Idr[v] * s.inv_mu + 2.0 * up[v] + 2.0 * dn[v];
+                if (j == 0) { gnd[v][0] = Idr[v]; gnd[v][1] = dn[v]; gnd[v][2] = up[v]; }
+                if (j == n_z - 1) { top[v][0] = Idr[v]; top[v][1] = dn[v]; top[v][2] = up[v]; }
+            }
+            out.st(F_IDR, j, Idr);
+            out.st(F_DN, j, dn);
+            out.st(F_UP, j, up);
+            out.st(F_F, j, F);
+        }
+    };
+    double D_prev[VEC], U_prev[VEC], U_prev2[VEC];  // D[t+2], U[t+1], U[t+2] when pair t arrives
+    auto pair_done = [&](int t, const double (&Dn)[VEC], const double (&Un)[VEC]) {  // Dn = D[t+1], Un = U[t]
+        if (t == M - 1) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { D_prev[v] = Dn[v]; U_prev[v] = Un[v]; U_prev2[v] = Un[v]; }  // U[M] = U[M-1]  (ref :343)
+        } else {
+            emit(t + 2, D_prev, Dn, U_prev2, U_prev);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { D_prev[v] = Dn[v]; U_prev2[v] = U_prev[v]; U_prev[v] = Un[v]; }
+        }
+    };
+    // ---- back substitution: SWu0[k] = x[2k], SWd0[k] = x[2k+1]; multiple scattering eq. 24/25 (ref :286-345)
+    double SWd0_hi[VEC], pend[VEC];  // x[2k+1] = SWd0[k];  SWd0[k+1]
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { SWd0_hi[v] = in.Idf0[v]; pend[v] = 0.0; }
+    for (int g = g_last; g >= 0; --g) {
+        const int base = g * CK;
+        const int len = (M - base < CK) ? M - base : CK;
+        double e0[VEC], f0[VEC];
+        if (g == g_last) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { e0[v] = e_prev[v]; f0[v] = f_prev[v]; }
+        } else if (g > 0) {
+            out.seg_ld(CK + g, 0, e0);
+            out.seg_ld(CK + g, 1, f0);
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { e0[v] = 0.0; f0[v] = x0[v]; }
+        }
+        {
+            double e[VEC], f[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { e[v] = e0[v]; f[v] = f0[v]; }
+            for (int i = 1; i <= len; ++i) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) fwd(base + i, v, e[v], f[v], e[v], f[v]);
+                out.seg_st(i - 1, 0, e);
+                out.seg_st(i - 1, 1, f);
+            }
+        }
+        for (int i = len; i >= 1; --i) {
+            const int k = base + i;
+            double eB[VEC], fB[VEC], eBl[VEC], fBl[VEC];
+            out.seg_ld(i - 1, 0, eB);
+            out.seg_ld(i - 1, 1, fB);
+            if (i >= 2) {
+                out.seg_ld(i - 2, 0, eBl);
+                out.seg_ld(i - 2, 1, fBl);
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { eBl[v] = e0[v]; fBl[v] = f0[v]; }
+            }
+            double SWu0_k[VEC], SWd0_k[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                double eA, fA;
+                rowA(k, v, eBl[v], fBl[v], eA, fA);              // row 2k-1 again, same expressions
+                SWd0_k[v] = SWd0_hi[v];
+                SWu0_k[v] = fB[v] - eB[v] * SWd0_hi[v];          // x[2k]
+                SWd0_hi[v] = fA - eA * SWu0_k[v];                // x[2k-1] = SWd0[k-1]
+            }
+            if (k <= M - 1) {  // pair k couples layers k and k+1: row class of li = k+1 >= 2
+                double Dn[VEC], Un[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    const ZqCol& c = col[v];
+                    Dn[v] = (pend[v] + SWu0_k[v] * c.s) * c.im_mid;  // eq. 24 (ref :288-312)
+                    Un[v] = (SWu0_k[v] + pend[v] * c.s) * c.im_mid;  // eq. 25 (ref :318-342)
+                }
+                pair_done(k, Dn, Un);
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) pend[v] = SWd0_k[v];   // needed by pair k-1
+        }
+    }
+    {   // pair 0: SWu0[0] = x[0] = x0, SWd0[1] = pend; row class li = 1 (soil below)
+        double Dn[VEC], Un[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const ZqCol& c = col[v];
+            Dn[v] = (pend[v] + x0[v] * c.s) * c.im_bot;
+            Un[v] = (x0[v] + pend[v] * c.s_bot) * c.im_bot;
+        }
+        pair_done(0, Dn, Un);
+    }
+    emit(1, D_prev, D_prev, U_prev2, U_prev);  // D[0] = D[1]  (ref :313)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+        absorbed[v] = absorbed_from_ends(top[v][0], gnd[v][0], top[v][1], gnd[v][1], top[v][2], gnd[v][2]);
 }
 
 // =================================================================================================

@@ -27,7 +27,15 @@ constexpr int BLOCK = 128;  // threads per CTA of the elementwise kernels (absor
 #define CRT_SEG_CK 10
 #endif
 constexpr int SEG_CK = CRT_SEG_CK;
-__host__ __device__ constexpr bool uses_segments(int scheme) { return scheme == CRT1D_SCHEME_ZQ || scheme == CRT1D_SCHEME_N79; }
+__host__ __device__ constexpr bool uses_segments(int scheme) {
+    return scheme == CRT1D_SCHEME_ZQ || scheme == CRT1D_SCHEME_N79 || scheme == CRT1D_SCHEME_ZQ_PA;
+}
+// slots (levels) of the segment store: the segment itself, plus zq_pa's checkpoints (its M-grid is not the output grid)
+__host__ __device__ inline int seg_slots(int scheme, int n_z) {
+    if (scheme != CRT1D_SCHEME_ZQ_PA) return SEG_CK;
+    const int M = n_z < ZQPA_MAX_M ? n_z : ZQPA_MAX_M;
+    return SEG_CK + (M - 1) / SEG_CK + 1;
+}
 // doubles of level tables, rounded up so that the segment store behind them is 16-byte aligned
 __host__ __device__ inline size_t tab_doubles(int scheme, int n_z) { return ((size_t)n_level_tables(scheme) * n_z + 1) & ~(size_t)1; }
 
@@ -210,6 +218,12 @@ __global__ void __launch_bounds__(BLK, MINB) solve_kernel(const crt1d_batch in, 
 
     for (int j = threadIdx.x; j < n_z; j += BLK) fill_level_tables<SCHEME>(in, s, j, tab);
     __syncthreads();
+    if constexpr (SCHEME == CRT1D_SCHEME_ZQ_PA) {
+        for (int j = threadIdx.x; j < n_z; j += BLK) fill_level_tables_2<SCHEME>(in, s, j, tab);
+        __syncthreads();
+        for (int j = threadIdx.x; j < n_z; j += BLK) fill_level_tables_3<SCHEME>(in, s, j, tab);
+        __syncthreads();
+    }
 
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     const int64_t prof = (int64_t)n_z * n_wl;                       // doubles per scenario in a profile
@@ -285,7 +299,7 @@ static cudaError_t launch_one(const crt1d_batch& in, const crt1d_out& out, cudaS
     const int64_t grid = in.n_scen * ctas_per_scen;
     if (grid <= 0 || grid > 2147483647LL) return cudaErrorInvalidConfiguration;
     size_t smem = (size_t)n_level_tables(SCHEME) * in.n_z * sizeof(double);
-    if (uses_segments(SCHEME)) smem = (tab_doubles(SCHEME, in.n_z) + (size_t)SEG_CK * 2 * VEC * BLK) * sizeof(double);
+    if (uses_segments(SCHEME)) smem = (tab_doubles(SCHEME, in.n_z) + (size_t)seg_slots(SCHEME, in.n_z) * 2 * VEC * BLK) * sizeof(double);
     auto kern = solve_kernel<SCHEME, VEC, BLK, MINB, false>;
     if constexpr (has_fast_tile(SCHEME)) {
         double* const f[7] = {out.I_dr, out.I_df_d, out.I_df_u, out.F, out.x0, out.x1, out.x2};
@@ -306,7 +320,7 @@ static cudaError_t launch_one(const crt1d_batch& in, const crt1d_out& out, cudaS
 // (128,1 | 128,4 | 256,2 tried for every scheme).  Only the chosen one is compiled.
 template <int SCHEME>
 struct TileCfg {
-    static constexpr int BLK = 128, MINB = 1;  // zq_pa (local-memory bound, insensitive); 4s (wants its 212 registers)
+    static constexpr int BLK = 128, MINB = 1;  // 4s (wants its 212 registers)
 };
 template <> struct TileCfg<CRT1D_SCHEME_2S> { static constexpr int BLK = 256, MINB = 2; };   // 4 KB row fragments: 0.79 -> 0.85
 template <> struct TileCfg<CRT1D_SCHEME_BL> { static constexpr int BLK = 256, MINB = 2; };   // 0.80 -> 0.87
@@ -316,6 +330,12 @@ template <> struct TileCfg<CRT1D_SCHEME_G77> { static constexpr int BLK = 256, M
 #define CRT_TRI_BLK 128
 #define CRT_TRI_MINB 4
 #endif
+#ifndef CRT_PA_BLK  // measured: (128,4) one column per thread 0.476; (128,3) two columns 0.461; (128,4) two columns 0.350; (128,2) 0.383
+#define CRT_PA_BLK 128
+#define CRT_PA_MINB 4
+#define CRT_PA_VEC 1
+#endif
+template <> struct TileCfg<CRT1D_SCHEME_ZQ_PA> { static constexpr int BLK = CRT_PA_BLK, MINB = CRT_PA_MINB; };  // 32 KB of segment store per CTA at n_z = 60
 template <> struct TileCfg<CRT1D_SCHEME_ZQ> { static constexpr int BLK = CRT_TRI_BLK, MINB = CRT_TRI_MINB; };   // 4 CTAs/SM hide the Thomas latency: +14 %
 template <> struct TileCfg<CRT1D_SCHEME_N79> { static constexpr int BLK = CRT_TRI_BLK, MINB = CRT_TRI_MINB; };  // +22 %
 
@@ -327,8 +347,9 @@ static cudaError_t launch_vec(const crt1d_batch& in, const crt1d_out& out, bool 
 
 size_t solve_shared_bytes(int scheme, int n_z) {
     if (!uses_segments(scheme)) return (size_t)n_level_tables(scheme) * n_z * sizeof(double);
-    const int blk = scheme == CRT1D_SCHEME_ZQ ? TileCfg<CRT1D_SCHEME_ZQ>::BLK : TileCfg<CRT1D_SCHEME_N79>::BLK;
-    return (tab_doubles(scheme, n_z) + (size_t)SEG_CK * 2 * 2 * blk) * sizeof(double);
+    const int blk = scheme == CRT1D_SCHEME_ZQ ? TileCfg<CRT1D_SCHEME_ZQ>::BLK
+                  : scheme == CRT1D_SCHEME_N79 ? TileCfg<CRT1D_SCHEME_N79>::BLK : TileCfg<CRT1D_SCHEME_ZQ_PA>::BLK;
+    return (tab_doubles(scheme, n_z) + (size_t)seg_slots(scheme, n_z) * 2 * 2 * blk) * sizeof(double);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -967,7 +988,7 @@ tile:
         case CRT1D_SCHEME_G77: return launch_vec<CRT1D_SCHEME_G77>(in, out, vec2, stream);
         case CRT1D_SCHEME_N79: return launch_vec<CRT1D_SCHEME_N79>(in, out, vec2, stream);
         case CRT1D_SCHEME_ZQ: return launch_vec<CRT1D_SCHEME_ZQ>(in, out, vec2, stream);
-        case CRT1D_SCHEME_ZQ_PA: return launch_vec<CRT1D_SCHEME_ZQ_PA>(in, out, false, stream);  // columns are solved one at a time: 8-byte stores coalesce only with VEC = 1
+        case CRT1D_SCHEME_ZQ_PA: return launch_vec<CRT1D_SCHEME_ZQ_PA>(in, out, vec2 && CRT_PA_VEC == 2, stream);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -18,7 +18,7 @@ CRT_HD int n_level_tables(int scheme) {
         case CRT1D_SCHEME_G77: return 2;  // L, exp(-k_b L)
         case CRT1D_SCHEME_N79: return 5;  // tbcum, tb, td, fsun, dlai
         case CRT1D_SCHEME_ZQ: return 1;   // exp(-K L)
-        case CRT1D_SCHEME_ZQ_PA: return 5;  // lai, exp(-Kb lai), cum[0..M], exp(-Kb cum[0..M]) (M <= n_z)
+        case CRT1D_SCHEME_ZQ_PA: return 9;  // lai, exp(-Kb lai), cum[0..M], exp(-Kb cum[0..M]) (M <= n_z; 3 slots), kk, tt, ww, ord
         default: return 0;
     }
 }
@@ -72,6 +72,35 @@ CRT_HD void fill_level_tables(const crt1d_batch& in, int64_t s, int j, double* t
     }
 }
 
+// Second and third passes over the levels, each after a barrier (zq_pa only): the interpolation tables of
+// the caller's levels on the M-grid (needs cum[] from the first pass) and their processing order.
+template <int SCHEME>
+CRT_HD void fill_level_tables_2(const crt1d_batch& in, int64_t s, int j, double* tab) {
+    if constexpr (SCHEME == CRT1D_SCHEME_ZQ_PA) {
+        const int n_z = in.n_z;
+        const int M = n_z < ZQPA_MAX_M ? n_z : ZQPA_MAX_M;
+        const double* cum = tab + 2 * n_z;
+        int k;
+        double t, w;
+        interp_np_prepare(tab[j], cum, M + 1, tab[0] / M, k, t, w);
+        tab[5 * n_z + j] = (double)k;
+        tab[6 * n_z + j] = t;
+        tab[7 * n_z + j] = w;
+    }
+}
+template <int SCHEME>
+CRT_HD void fill_level_tables_3(const crt1d_batch& in, int64_t s, int j, double* tab) {
+    if constexpr (SCHEME == CRT1D_SCHEME_ZQ_PA) {
+        const int n_z = in.n_z;
+        const double* kk = tab + 5 * n_z;
+        int rank = 0;  // levels finished before level j: larger kk first, ties from the top level down
+        for (int i = 0; i < n_z; ++i) rank += (kk[i] > kk[j]) || (kk[i] == kk[j] && i > j);
+        tab[8 * n_z + rank] = (double)j;
+    }
+}
+// number of table passes a scheme needs
+CRT_HD int n_table_passes(int scheme) { return scheme == CRT1D_SCHEME_ZQ_PA ? 3 : 1; }
+
 // Solve VEC adjacent columns of scenario s.  `tab` = the level tables above.
 template <int SCHEME, int VEC, class Out>
 CRT_HD void solve_column_group(const crt1d_batch& in, int64_t s, const double* tab, const BandIn<VEC>& b, Out& out,
@@ -111,7 +140,8 @@ CRT_HD void solve_column_group(const crt1d_batch& in, int64_t s, const double* t
         sc.tau_d = in.tau_i[s];
         sc.LAI = L_T;
         sc.M = n_z < ZQPA_MAX_M ? n_z : ZQPA_MAX_M;
-        column_zq_pa<VEC>(sc, tab, tab + n_z, tab + 2 * n_z, tab + 2 * n_z + sc.M + 1, n_z, b, out, absorbed);
+        column_zq_pa<VEC>(sc, tab + n_z, tab + 2 * n_z + sc.M + 1, tab + 5 * n_z, tab + 6 * n_z, tab + 7 * n_z,
+                          tab + 8 * n_z, n_z, b, out, absorbed);
     } else if constexpr (SCHEME == CRT1D_SCHEME_ZQ) {
         ScenZq sc;
         sc.cos_psi = cos(psi);

@@ -27,7 +27,7 @@ struct HostOut {
     void st_tmp(int f, int j, const double (&x)[VEC]) const { st(f, j, x); }
     // segment store of the checkpointed Thomas sweeps (shared memory on the device)
     static constexpr int CK = 8;
-    mutable double seg_buf[CK][2][VEC];
+    mutable double seg_buf[CK + 100 / CK + 2][2][VEC];  // + zq_pa's checkpoint slots
     int seg_levels() const { return CK; }
     void seg_st(int slot, int k, const double (&x)[VEC]) const {
         for (int v = 0; v < VEC; ++v) seg_buf[slot][k][v] = x[v];
@@ -47,6 +47,8 @@ void run(const crt1d_batch& in, const crt1d_out& out) {
     const int64_t prof = (int64_t)n_z * n_wl, xprof = (int64_t)crt::extra_rows(SCHEME, n_z) * n_wl;
     for (int64_t s = 0; s < in.n_scen; ++s) {
         for (int j = 0; j < n_z; ++j) crt::fill_level_tables<SCHEME>(in, s, j, tab.data());
+        for (int j = 0; j < n_z; ++j) crt::fill_level_tables_2<SCHEME>(in, s, j, tab.data());
+        for (int j = 0; j < n_z; ++j) crt::fill_level_tables_3<SCHEME>(in, s, j, tab.data());
         double acc[4] = {0, 0, 0, 0};
         for (int b0 = 0; b0 < n_wl; b0 += VEC) {
             const crt::BandIn<VEC> b = crt::load_bands<VEC>(in, s, b0);
