@@ -330,14 +330,14 @@ template <> struct TileCfg<CRT1D_SCHEME_G77> { static constexpr int BLK = 256, M
 #define CRT_TRI_BLK 128
 #define CRT_TRI_MINB 4
 #endif
-#ifndef CRT_PA_BLK  // measured: (128,4) one column per thread 0.476; (128,3) two columns 0.461; (128,4) two columns 0.350; (128,2) 0.383
-#define CRT_PA_BLK 128
-#define CRT_PA_MINB 4
-#define CRT_PA_VEC 1
-#endif
-template <> struct TileCfg<CRT1D_SCHEME_ZQ_PA> { static constexpr int BLK = CRT_PA_BLK, MINB = CRT_PA_MINB; };  // 32 KB of segment store per CTA at n_z = 60
-template <> struct TileCfg<CRT1D_SCHEME_ZQ> { static constexpr int BLK = CRT_TRI_BLK, MINB = CRT_TRI_MINB; };   // 4 CTAs/SM hide the Thomas latency: +14 %
-template <> struct TileCfg<CRT1D_SCHEME_N79> { static constexpr int BLK = CRT_TRI_BLK, MINB = CRT_TRI_MINB; };  // +22 %
+// Tridiagonal schemes (checkpointed sweeps; measured on 66 304-scenario runs, fraction of HBM peak):
+//   zq    (128,4) 0.706 | (128,3) 0.729 | (256,2) 0.748 | (128,5) 0.627 | one column per thread 0.645
+//   n79   (128,4) 0.632 | (128,3) 0.609 | (256,2) 0.625 | (128,5) 0.555 | one column per thread 0.498
+//   zq_pa (128,4) one column per thread 0.476 | (128,3) two columns 0.461 | (128,4) two columns 0.350 | (128,2) 0.383
+constexpr int ZQPA_VEC = 1;
+template <> struct TileCfg<CRT1D_SCHEME_ZQ_PA> { static constexpr int BLK = 128, MINB = 4; };
+template <> struct TileCfg<CRT1D_SCHEME_ZQ> { static constexpr int BLK = 256, MINB = 2; };
+template <> struct TileCfg<CRT1D_SCHEME_N79> { static constexpr int BLK = 128, MINB = 4; };
 
 template <int SCHEME>
 static cudaError_t launch_vec(const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream) {
@@ -988,7 +988,7 @@ tile:
         case CRT1D_SCHEME_G77: return launch_vec<CRT1D_SCHEME_G77>(in, out, vec2, stream);
         case CRT1D_SCHEME_N79: return launch_vec<CRT1D_SCHEME_N79>(in, out, vec2, stream);
         case CRT1D_SCHEME_ZQ: return launch_vec<CRT1D_SCHEME_ZQ>(in, out, vec2, stream);
-        case CRT1D_SCHEME_ZQ_PA: return launch_vec<CRT1D_SCHEME_ZQ_PA>(in, out, vec2 && CRT_PA_VEC == 2, stream);
+        case CRT1D_SCHEME_ZQ_PA: return launch_vec<CRT1D_SCHEME_ZQ_PA>(in, out, vec2 && ZQPA_VEC == 2, stream);
         default: return cudaErrorInvalidValue;
     }
 }

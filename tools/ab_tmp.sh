@@ -1,6 +1,6 @@
-timeout 600 python -m pytest tests -m gpu -q -x -k "zq_pa or deep or variant or indexing" 2>&1 | tail -3
-for sch in zq_pa; do for lib in cur pa2 pa4v1 pa4 pa4ck6; do
-if [ $lib = cur ]; then unset CRT1D_B200_LIB; else export CRT1D_B200_LIB=/root/repo/crt1d_b200/libcrt1d_b200_$lib.so; fi
+for sch in zq n79; do for lib in cur curv1 tri3 tri256 tri5 tri5v1; do
+unset CRT1D_B200_LIB CRT1D_B200_FORCE_VEC1
+case $lib in cur) ;; curv1) export CRT1D_B200_FORCE_VEC1=1;; tri5v1) export CRT1D_B200_FORCE_VEC1=1 CRT1D_B200_LIB=/root/repo/crt1d_b200/libcrt1d_b200_tri5.so;; *) export CRT1D_B200_LIB=/root/repo/crt1d_b200/libcrt1d_b200_$lib.so;; esac
 timeout 300 python bench.py --scheme $sch --scenarios 66304 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | python -c "
 import json,sys
 L=[l for l in sys.stdin if l.startswith('{')]
