@@ -910,9 +910,10 @@ CRT_HD void interp_np_prepare(double x, const double* xp, int n, double dl, int&
     w = 1.0 / (xp[j + 1] - xp[j]);
 }
 
-// eK[j] = exp(-Kb lai[j]) on the caller's levels; eC[i] = exp(-Kb cum[i]) on the M-grid (cum = running sum
-// of LAI/M as np.cumsum produces it, ref :161); kk/tt/ww: interp_np_prepare() of every caller level;
-// ord: the caller's levels sorted by descending kk (the order in which the back sweep can finish them).
+// eC[i] = exp(-Kb cum[i]) on the M-grid (cum = running sum of LAI/M as np.cumsum produces it, ref :161).
+// The caller's levels come sorted by descending grid interval (the order in which the back sweep can finish
+// them): lk[c] = (level j, interval k) as two int32, and tt/ww (interp_np_prepare()) and eK = exp(-Kb lai[j])
+// of that level.
 //
 // The M-grid solve is the checkpointed Thomas sweep of column_zq (checkpoints in the Out object's segment
 // store: slots CK.. hold the checkpoints, slots 0..CK-1 the segment being back-substituted).  The back sweep
@@ -922,9 +923,8 @@ CRT_HD void interp_np_prepare(double x, const double* xp, int n, double dl, int&
 // the M-grid is stored per thread beyond a three-value window (the first version kept four 101-element
 // work arrays per thread in local memory and ran at a third of this speed).
 template <int VEC, class Out>
-CRT_HD void column_zq_pa(const ScenZqPa& s, const double* eK, const double* eC, const double* kk, const double* tt,
-                         const double* ww, const double* ord, int n_z, const BandIn<VEC>& in, Out& out,
-                         double (&absorbed)[VEC]) {
+CRT_HD void column_zq_pa(const ScenZqPa& s, const double* eC, const double* lk, const double* tt, const double* ww,
+                         const double* eK, int n_z, const BandIn<VEC>& in, Out& out, double (&absorbed)[VEC]) {
     const int M = s.M;
     const double dl = s.LAI / M;
     const double taub = exp(-s.Kb * dl);                                            // ref :173
@@ -1002,16 +1002,17 @@ CRT_HD void column_zq_pa(const ScenZqPa& s, const double* eK, const double* eC, 
     double gnd[VEC][3] = {}, top[VEC][3] = {};
     auto emit = [&](int k, const double (&Dk)[VEC], const double (&Dk1)[VEC], const double (&Uk)[VEC], const double (&Uk1)[VEC]) {
         while (jc < n_z) {
-            const int j = (int)ord[jc];
-            if ((int)kk[j] != k) break;
+            const int* e = reinterpret_cast<const int*>(lk + jc);
+            if (e[1] != k) break;
+            const int j = e[0];
+            const double t = tt[jc], w = ww[jc], eKj = eK[jc];
             ++jc;
-            const double t = tt[j], w = ww[j];
             double Idr[VEC], dn[VEC], up[VEC], F[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 dn[v] = (t < 0.0) ? Dk1[v] : ((Dk1[v] - Dk[v]) * w) * t + Dk[v];
                 up[v] = (t < 0.0) ? Uk1[v] : ((Uk1[v] - Uk[v]) * w) * t + Uk[v];
-                Idr[v] = in.Idr0[v] * eK[j];
+                Idr[v] = in.Idr0[v] * eKj;
                 F[v] = Idr[v] * s.inv_mu + 2.0 * up[v] + 2.0 * dn[v];
                 if (j == 0) { gnd[v][0] = Idr[v]; gnd[v][1] = dn[v]; gnd[v][2] = up[v]; }
                 if (j == n_z - 1) { top[v][0] = Idr[v]; top[v][1] = dn[v]; top[v][2] = up[v]; }

@@ -18,7 +18,7 @@ CRT_HD int n_level_tables(int scheme) {
         case CRT1D_SCHEME_G77: return 2;  // L, exp(-k_b L)
         case CRT1D_SCHEME_N79: return 5;  // tbcum, tb, td, fsun, dlai
         case CRT1D_SCHEME_ZQ: return 1;   // exp(-K L)
-        case CRT1D_SCHEME_ZQ_PA: return 9;  // lai, exp(-Kb lai), cum[0..M], exp(-Kb cum[0..M]) (M <= n_z; 3 slots), kk, tt, ww, ord
+        case CRT1D_SCHEME_ZQ_PA: return 12;  // lai, exp(-Kb lai), cum[0..M], exp(-Kb cum[0..M]) (M <= n_z; 3 slots), kk, tt, ww; in emission order: (level, kk), tt, ww, exp(-Kb lai)
         default: return 0;
     }
 }
@@ -95,7 +95,14 @@ CRT_HD void fill_level_tables_3(const crt1d_batch& in, int64_t s, int j, double*
         const double* kk = tab + 5 * n_z;
         int rank = 0;  // levels finished before level j: larger kk first, ties from the top level down
         for (int i = 0; i < n_z; ++i) rank += (kk[i] > kk[j]) || (kk[i] == kk[j] && i > j);
-        tab[8 * n_z + rank] = (double)j;
+        // emission-ordered copies, so the back sweep walks all four tables with one cursor:
+        // (level, kk) packed as two int32 in one slot; t, w and exp(-Kb lai) of that level
+        int* lk = reinterpret_cast<int*>(tab + 8 * n_z + rank);
+        lk[0] = j;
+        lk[1] = (int)kk[j];
+        tab[9 * n_z + rank] = tab[6 * n_z + j];
+        tab[10 * n_z + rank] = tab[7 * n_z + j];
+        tab[11 * n_z + rank] = tab[n_z + j];
     }
 }
 // number of table passes a scheme needs
@@ -140,8 +147,8 @@ CRT_HD void solve_column_group(const crt1d_batch& in, int64_t s, const double* t
         sc.tau_d = in.tau_i[s];
         sc.LAI = L_T;
         sc.M = n_z < ZQPA_MAX_M ? n_z : ZQPA_MAX_M;
-        column_zq_pa<VEC>(sc, tab + n_z, tab + 2 * n_z + sc.M + 1, tab + 5 * n_z, tab + 6 * n_z, tab + 7 * n_z,
-                          tab + 8 * n_z, n_z, b, out, absorbed);
+        column_zq_pa<VEC>(sc, tab + 2 * n_z + sc.M + 1, tab + 8 * n_z, tab + 9 * n_z, tab + 10 * n_z, tab + 11 * n_z, n_z,
+                          b, out, absorbed);
     } else if constexpr (SCHEME == CRT1D_SCHEME_ZQ) {
         ScenZq sc;
         sc.cos_psi = cos(psi);

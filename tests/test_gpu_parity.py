@@ -436,6 +436,23 @@ def test_deep_canopy_nz1000():
         assert_close_4s(sol[k], ref[k], f"deep 4s.{k}")
 
 
+@pytest.mark.parametrize("kind", ["cluster", "quad"])
+def test_checkpointed_sweeps_ragged_levels(kind):
+    """zq / n79 / zq_pa at every level count around the checkpoint spacing (10) and zq_pa's 100-layer cap, on
+    non-uniform level axes (zq_pa: several caller levels per M-grid interval and empty intervals)."""
+    import crt1d_b200 as crt
+    from util import RAGGED_NZ, ragged_case
+
+    for nz in RAGGED_NZ:
+        q = ragged_case(nz, kind)
+        for scheme in ("zq", "zq_pa", "n79"):
+            kw = {"tau_d_method": "9sky"} if scheme == "n79" else {}
+            ref = oracle.run(scheme, q, **kw)
+            sol = crt.solvers.AVAILABLE_SCHEMES[scheme]["solver"](**_args(scheme, q), **kw)
+            for k in ref:
+                assert_close(sol[k], ref[k], RTOL, f"ragged {kind} nz={nz} {scheme}.{k}")
+
+
 @pytest.mark.parametrize("scheme", ["bl", "bf", "g77", "4s"])
 def test_rows_kernel_other_schemes(scheme, monkeypatch):
     """bl, bf, g77, 4s on batches >= 148 scenarios use the generic row-sweep kernel; it must agree with the

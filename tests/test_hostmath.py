@@ -75,6 +75,23 @@ def test_kernel_math_variants(nz, sza):
                 assert_close(sol[k], g[full], RTOL, f"{tag} {scheme}.{k}")
 
 
+@pytest.mark.parametrize("kind", ["cluster", "quad"])
+def test_kernel_math_checkpointed_sweeps_ragged_levels(kind):
+    """Every level count around the checkpoint spacing (8 here, 10 on the device) and around zq_pa's
+    100-layer cap, on non-uniform level axes."""
+    from util import RAGGED_NZ, ragged_case
+
+    for nz in RAGGED_NZ:
+        q = ragged_case(nz, kind)
+        for scheme in ("zq", "zq_pa", "n79"):
+            kw = {"tau_d_method": "9sky"} if scheme == "n79" else {}
+            ref = oracle.run(scheme, q, **kw)
+            for vec in (1, 2):
+                sol = _solve(q, scheme, vec=vec, **kw)
+                for k in ref:
+                    assert_close(sol[k], ref[k], RTOL, f"ragged {kind} nz={nz} {scheme}.{k} vec{vec}")
+
+
 def test_kernel_math_multi_scenario_indexing(default_p):
     """Library/index plumbing: scenarios pick different rows; each must equal its own single solve."""
     rng = np.random.default_rng(3)

@@ -117,3 +117,23 @@ def deep_case(n_bands=6):
     for k in ("leaf_t", "leaf_r", "soil_r", "I_dr0_all", "I_df0_all", "wl", "dwl", "wl_leafsoil"):
         q[k] = q[k][::step][:n_bands].copy()
     return with_callables(q)
+
+
+def ragged_case(nz, kind="cluster", n_bands=8):
+    """Default case on `nz` levels with a NON-uniform cumulative-LAI axis, for the checkpointed tridiagonal
+    sweeps (segment boundaries at every multiple of the checkpoint spacing) and zq_pa's streamed
+    interpolation: `cluster` packs the levels near the canopy top (several caller levels inside one M-grid
+    interval, empty intervals lower down), `quad` is the reference's own beta-like shape."""
+    from crt1d_b200 import cases
+
+    q = dict(cases.load_default_case(nz))
+    x = np.linspace(1, 0, nz)
+    q["lai"] = (x ** 4 if kind == "cluster" else x ** 2) * 4.0
+    q["psi"] = np.deg2rad(35.0)
+    step = max(1, 107 // n_bands)
+    for k in ("leaf_t", "leaf_r", "soil_r", "I_dr0_all", "I_df0_all", "wl", "dwl", "wl_leafsoil"):
+        q[k] = q[k][::step][:n_bands].copy()
+    return with_callables(q)
+
+
+RAGGED_NZ = (7, 8, 9, 10, 11, 16, 17, 20, 21, 30, 31, 99, 100, 101, 110)
