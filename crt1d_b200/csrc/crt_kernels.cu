@@ -39,6 +39,12 @@ __host__ __device__ inline int seg_slots(int scheme, int n_z) {
 // doubles of level tables, rounded up so that the segment store behind them is 16-byte aligned
 __host__ __device__ inline size_t tab_doubles(int scheme, int n_z) { return ((size_t)n_level_tables(scheme) * n_z + 1) & ~(size_t)1; }
 
+// doubles of segment store per thread (thread-major, one pad element: see GlobalOut)
+template <int VEC>
+__host__ __device__ inline int seg_thread_doubles(int scheme, int n_z) {
+    return uses_segments(scheme) ? (seg_slots(scheme, n_z) * 2 + 1) * VEC : 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // global-memory column accessor
 // ---------------------------------------------------------------------------------------------
@@ -64,8 +70,8 @@ __device__ __forceinline__ void st_raw(float* q, const double (&x)[VEC]) {
 // kernel parameters, they cost no per-thread registers), `off` the thread's element offset of
 // (scenario, level 0, first band) -- `xoff` for the extra-output slots, whose row count can differ.
 // FAST = every field of the scheme requested and float64 storage: no null checks, no dtype switch
-// (15 -> 3 issue slots per store); the general path keeps both.  BLK = threads per CTA.
-template <int VEC, bool FAST, int BLK>
+// (15 -> 3 issue slots per store); the general path keeps both.
+template <int VEC, bool FAST>
 struct GlobalOut {
     double* base[N_FIELDS];
     int64_t off, xoff, stride;
@@ -112,12 +118,13 @@ struct GlobalOut {
             for (int v = 0; v < VEC; ++v) x[v] = __ldcs(q + v);
         }
     }
-    // segment store of the checkpointed Thomas sweeps (zq, n79): SEG_CK levels x 2 values x VEC columns per
-    // thread in shared memory, laid out [slot][k][thread] so that a warp's accesses are contiguous
+    // segment store of the checkpointed Thomas sweeps: `slots` levels x 2 values x VEC columns per thread in
+    // shared memory, thread-major with one pad element: thread stride (2 slots + 1) * VEC doubles is an odd
+    // multiple of the access width, so a warp's 8/16-byte accesses are bank-conflict free for any CTA size
     double* seg;  // this thread's first element
     __device__ __forceinline__ int seg_levels() const { return SEG_CK; }
     __device__ __forceinline__ void seg_st(int slot, int k, const double (&x)[VEC]) const {
-        double* q = seg + (slot * 2 + k) * (BLK * VEC);
+        double* q = seg + (slot * 2 + k) * VEC;
         if constexpr (VEC == 2) {
             *reinterpret_cast<double2*>(q) = make_double2(x[0], x[1]);
         } else {
@@ -125,7 +132,7 @@ struct GlobalOut {
         }
     }
     __device__ __forceinline__ void seg_ld(int slot, int k, double (&x)[VEC]) const {
-        const double* q = seg + (slot * 2 + k) * (BLK * VEC);
+        const double* q = seg + (slot * 2 + k) * VEC;
         if constexpr (VEC == 2) {
             const double2 t = *reinterpret_cast<const double2*>(q);
             x[0] = t.x;
@@ -210,18 +217,19 @@ __global__ void __launch_bounds__(BLK, MINB) solve_kernel(const crt1d_batch in, 
     extern __shared__ double tab[];
     __shared__ double red[BLK / 32][4];
 
+    const int nthr = blockDim.x;  // <= BLK: the launcher picks the CTA size that leaves the fewest idle lanes in the last tile
     const int ctas_per_scen = (tiles_per_scen + tiles_per_cta - 1) / tiles_per_cta;
     const int64_t s = blockIdx.x / ctas_per_scen;
     const int t0 = (blockIdx.x % ctas_per_scen) * tiles_per_cta;
     const int t1 = min(t0 + tiles_per_cta, tiles_per_scen);
     const int n_z = in.n_z, n_wl = in.n_wl;
 
-    for (int j = threadIdx.x; j < n_z; j += BLK) fill_level_tables<SCHEME>(in, s, j, tab);
+    for (int j = threadIdx.x; j < n_z; j += nthr) fill_level_tables<SCHEME>(in, s, j, tab);
     __syncthreads();
     if constexpr (SCHEME == CRT1D_SCHEME_ZQ_PA) {
-        for (int j = threadIdx.x; j < n_z; j += BLK) fill_level_tables_2<SCHEME>(in, s, j, tab);
+        for (int j = threadIdx.x; j < n_z; j += nthr) fill_level_tables_2<SCHEME>(in, s, j, tab);
         __syncthreads();
-        for (int j = threadIdx.x; j < n_z; j += BLK) fill_level_tables_3<SCHEME>(in, s, j, tab);
+        for (int j = threadIdx.x; j < n_z; j += nthr) fill_level_tables_3<SCHEME>(in, s, j, tab);
         __syncthreads();
     }
 
@@ -230,13 +238,13 @@ __global__ void __launch_bounds__(BLK, MINB) solve_kernel(const crt1d_batch in, 
     const int64_t xprof = (int64_t)extra_rows(SCHEME, n_z) * n_wl;  // ... in an extra-output slot
 
     for (int t = t0; t < t1; ++t) {
-        const int b0 = (t * BLK + threadIdx.x) * VEC;
+        const int b0 = (t * nthr + threadIdx.x) * VEC;
         if (b0 >= n_wl) continue;
         const BandIn<VEC> b = load_bands<VEC>(in, s, b0);
-        GlobalOut<VEC, FAST, BLK> o;
+        GlobalOut<VEC, FAST> o;
         o.stride = n_wl;
         o.f32 = out.profile_f32 != 0;
-        o.seg = tab + tab_doubles(SCHEME, n_z) + threadIdx.x * VEC;
+        o.seg = tab + tab_doubles(SCHEME, n_z) + (size_t)threadIdx.x * seg_thread_doubles<VEC>(SCHEME, n_z);
         o.off = s * prof + b0;
         o.xoff = s * xprof + b0;
         o.base[F_IDR] = out.I_dr;
@@ -275,7 +283,7 @@ __global__ void __launch_bounds__(BLK, MINB) solve_kernel(const crt1d_batch in, 
         if (threadIdx.x < out.n_bw) {
             double v = 0.0;
 #pragma unroll
-            for (int w = 0; w < BLK / 32; ++w) v += red[w][threadIdx.x];
+            for (int w = 0; w < nthr / 32; ++w) v += red[w][threadIdx.x];
             out.absorbed[s * out.n_bw + threadIdx.x] = v;
         }
     }
@@ -290,16 +298,33 @@ __host__ __device__ constexpr bool has_fast_tile(int scheme) {
     return scheme == CRT1D_SCHEME_ZQ || scheme == CRT1D_SCHEME_N79 || scheme == CRT1D_SCHEME_ZQ_PA;
 }
 
+constexpr int ZQPA_VEC = 1, ZQPA_THREADS = 128;  // zq_pa: one column per thread, 128-thread CTAs (measured below)
+
+// Threads per CTA of a tile-kernel launch: the configured size, or CRT1D_B200_TILE_THREADS (<= the compiled
+// bound; tuning).  One CTA walks a scenario's bands in passes of nthr * VEC columns and the last pass is partly
+// empty (2100 bands, 256 threads x 2: 18 % of the thread-passes idle) -- but picking the size with the fullest
+// last pass does NOT pay: measured zq 96 thr 0.68 | 128 0.70 | 192 0.74 | 256 0.74; n79 0.60-0.62 for all;
+// zq_pa 96 0.47 | 128 0.50 | 192 0.45 | 256 0.50 (early-exiting warps free their issue slots; longer row
+// fragments help the stores).
+static int tile_threads(int cfg, int blk) {
+    if (const char* e = getenv("CRT1D_B200_TILE_THREADS")) {
+        const int t = atoi(e);
+        if (t >= 32 && t <= blk && t % 32 == 0) return t;
+    }
+    return cfg;
+}
+
 template <int SCHEME, int VEC, int BLK, int MINB>
 static cudaError_t launch_one(const crt1d_batch& in, const crt1d_out& out, cudaStream_t stream) {
-    const int cols = BLK * VEC;
+    const int nthr = tile_threads(SCHEME == CRT1D_SCHEME_ZQ_PA ? ZQPA_THREADS : BLK, BLK);
+    const int cols = nthr * VEC;
     const int tiles_per_scen = (in.n_wl + cols - 1) / cols;
     const int tiles_per_cta = out.absorbed ? tiles_per_scen : 1;
     const int ctas_per_scen = (tiles_per_scen + tiles_per_cta - 1) / tiles_per_cta;
     const int64_t grid = in.n_scen * ctas_per_scen;
     if (grid <= 0 || grid > 2147483647LL) return cudaErrorInvalidConfiguration;
     size_t smem = (size_t)n_level_tables(SCHEME) * in.n_z * sizeof(double);
-    if (uses_segments(SCHEME)) smem = (tab_doubles(SCHEME, in.n_z) + (size_t)seg_slots(SCHEME, in.n_z) * 2 * VEC * BLK) * sizeof(double);
+    if (uses_segments(SCHEME)) smem = (tab_doubles(SCHEME, in.n_z) + (size_t)nthr * seg_thread_doubles<VEC>(SCHEME, in.n_z)) * sizeof(double);
     auto kern = solve_kernel<SCHEME, VEC, BLK, MINB, false>;
     if constexpr (has_fast_tile(SCHEME)) {
         double* const f[7] = {out.I_dr, out.I_df_d, out.I_df_u, out.F, out.x0, out.x1, out.x2};
@@ -311,7 +336,7 @@ static cudaError_t launch_one(const crt1d_batch& in, const crt1d_out& out, cudaS
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    kern<<<(unsigned)grid, BLK, smem, stream>>>(in, out, tiles_per_scen, tiles_per_cta);
+    kern<<<(unsigned)grid, nthr, smem, stream>>>(in, out, tiles_per_scen, tiles_per_cta);
     return cudaGetLastError();
 }
 
@@ -334,10 +359,9 @@ template <> struct TileCfg<CRT1D_SCHEME_G77> { static constexpr int BLK = 256, M
 //   zq    (128,4) 0.706 | (128,3) 0.729 | (256,2) 0.748 | (128,5) 0.627 | one column per thread 0.645
 //   n79   (128,4) 0.632 | (128,3) 0.609 | (256,2) 0.625 | (128,5) 0.555 | one column per thread 0.498
 //   zq_pa (128,4) one column per thread 0.476 | (128,3) two columns 0.461 | (128,4) two columns 0.350 | (128,2) 0.383
-constexpr int ZQPA_VEC = 1;
-template <> struct TileCfg<CRT1D_SCHEME_ZQ_PA> { static constexpr int BLK = 128, MINB = 4; };
+template <> struct TileCfg<CRT1D_SCHEME_ZQ_PA> { static constexpr int BLK = 256, MINB = 2; };
 template <> struct TileCfg<CRT1D_SCHEME_ZQ> { static constexpr int BLK = 256, MINB = 2; };
-template <> struct TileCfg<CRT1D_SCHEME_N79> { static constexpr int BLK = 128, MINB = 4; };
+template <> struct TileCfg<CRT1D_SCHEME_N79> { static constexpr int BLK = 256, MINB = 2; };
 
 template <int SCHEME>
 static cudaError_t launch_vec(const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream) {
@@ -347,9 +371,10 @@ static cudaError_t launch_vec(const crt1d_batch& in, const crt1d_out& out, bool 
 
 size_t solve_shared_bytes(int scheme, int n_z) {
     if (!uses_segments(scheme)) return (size_t)n_level_tables(scheme) * n_z * sizeof(double);
-    const int blk = scheme == CRT1D_SCHEME_ZQ ? TileCfg<CRT1D_SCHEME_ZQ>::BLK
-                  : scheme == CRT1D_SCHEME_N79 ? TileCfg<CRT1D_SCHEME_N79>::BLK : TileCfg<CRT1D_SCHEME_ZQ_PA>::BLK;
-    return (tab_doubles(scheme, n_z) + (size_t)seg_slots(scheme, n_z) * 2 * 2 * blk) * sizeof(double);
+    if (scheme == CRT1D_SCHEME_ZQ_PA)
+        return (tab_doubles(scheme, n_z) + (size_t)ZQPA_THREADS * seg_thread_doubles<ZQPA_VEC>(scheme, n_z)) * sizeof(double);
+    const int blk = scheme == CRT1D_SCHEME_ZQ ? TileCfg<CRT1D_SCHEME_ZQ>::BLK : TileCfg<CRT1D_SCHEME_N79>::BLK;
+    return (tab_doubles(scheme, n_z) + (size_t)blk * seg_thread_doubles<2>(scheme, n_z)) * sizeof(double);
 }
 
 // ---------------------------------------------------------------------------------------------
