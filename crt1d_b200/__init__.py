@@ -15,4 +15,6 @@ from . import spectra  # noqa: F401
 from .leaf_angle import LeafAngle  # noqa: F401
 from .model import Model  # noqa: F401
 from .model import run_sensitivity  # noqa: F401
+from .model import sensitivity_dataset  # noqa: F401
+from .model import sensitivity_to_xr  # noqa: F401
 from .scenarios import ScenarioBatch  # noqa: F401

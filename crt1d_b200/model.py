@@ -337,3 +337,55 @@ def run_sensitivity(m0, p_sets, *, bands=("PAR", "NIR"), profiles=True):
     res = {k: v.reshape(tuple(sizes) + v.shape[1:]) for k, v in flat.items()}
     res["dims"] = keys
     return res
+
+
+def sensitivity_dataset(res, m0, p_sets, *, bands=("PAR", "NIR")):
+    """Describe a `run_sensitivity` result as a dataset: `{"coords": ..., "data_vars": ..., "attrs": ...}` with
+    every entry a `(dims, data, attrs)` tuple, i.e. exactly the arguments of `xarray.Dataset` -- "a new
+    dimension for each key in `p_sets`" (ref model.py:650-664) in front of the reference's `z`/`zm`/`wl`
+    dims (ref model.py:338-447, variables.yml:4-9).  Scalar parameters (psi) become coordinate values;
+    array-valued ones (lai, spectra) get an integer case coordinate `<name>_case`.  No xarray needed."""
+    p = m0._p
+    keys = list(res["dims"])
+    nlev = len(p["lai"])
+
+    def tup(name, data, dims):
+        m = VMD[name] if name in VMD else None
+        return (tuple(dims), data, {"units": m.units, "long_name": m.long_name} if m else {})
+
+    coords = {"z": tup("z", p["z"], ["z"]), "zm": tup("zm", p["zm"], ["zm"]), "wl": tup("wl", p["wl"], ["wl"])}
+    sw_dims = []
+    for k in keys:
+        vals = [np.asarray(v, dtype=np.float64) for v in p_sets[k]]
+        if all(v.ndim == 0 for v in vals):
+            sw_dims.append(k)
+            coords[k] = tup(k, np.array([float(v) for v in vals]), [k])
+        else:
+            d = f"{k}_case"
+            sw_dims.append(d)
+            coords[d] = ((d,), np.arange(len(vals)), {"long_name": f"index into the swept values of {k}"})
+    dv = {}
+    for k, v in res.items():
+        if k == "dims":
+            continue
+        if k == "absorbed":
+            coords["band"] = (("band",), np.array(list(bands)), {"long_name": "spectral band of the absorbed-irradiance diagnostic"})
+            dv[k] = (tuple(sw_dims) + ("band",), v, {"units": "W m-2", "long_name": "canopy-absorbed irradiance in band"})
+            continue
+        if v.ndim != len(sw_dims) + 2:
+            dv[k] = (tuple(sw_dims) + tuple(f"{k}_dim{i}" for i in range(v.ndim - len(sw_dims))), v, {})
+            continue
+        lev = "z" if v.shape[-2] == nlev else "zm"
+        dv[k] = tup(k, v, sw_dims + [lev, "wl"])
+    attrs = {"scheme_name": m0.scheme["name"], "scheme_long_name": m0.scheme["long_name"],
+             "scheme_short_name": m0.scheme["short_name"], "swept": ", ".join(keys)}
+    return {"coords": coords, "data_vars": dv, "attrs": attrs}
+
+
+def sensitivity_to_xr(res, m0, p_sets, *, bands=("PAR", "NIR")):
+    """`run_sensitivity` result as the `xr.Dataset` the reference's docstring promises (xarray imported lazily)."""
+    try:
+        import xarray as xr
+    except ImportError as e:
+        raise ImportError("sensitivity_to_xr needs xarray, which is not installed") from e
+    return xr.Dataset(**sensitivity_dataset(res, m0, p_sets, bands=bands))

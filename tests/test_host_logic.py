@@ -123,6 +123,39 @@ def test_sensitivity_requires_parametric_leaf_angle():
         m.scenario_batch()
 
 
+def test_sensitivity_dataset_layout():
+    """One leading dim per swept parameter in front of the reference's z / zm / wl dims (ref model.py:650-664);
+    the description is exactly the argument set of xarray.Dataset (checked here with a recording stand-in)."""
+    import sys
+    import types
+
+    from crt1d_b200.model import sensitivity_dataset, sensitivity_to_xr
+
+    m = crt.Model("n79", nlayers=12)
+    nz, nw = 12, m.nwl
+    p_sets = {"psi": [0.2, 0.9, 1.2], "lai": [m._p["lai"], m._p["lai"] * 0.5]}
+    res = {"dims": ["psi", "lai"], "F": np.zeros((3, 2, nz, nw)), "aI_lsl": np.zeros((3, 2, nz - 1, nw)),
+           "absorbed": np.zeros((3, 2, 2))}
+    d = sensitivity_dataset(res, m, p_sets)
+    assert d["data_vars"]["F"][0] == ("psi", "lai_case", "z", "wl")
+    assert d["data_vars"]["aI_lsl"][0] == ("psi", "lai_case", "zm", "wl")
+    assert d["data_vars"]["absorbed"][0] == ("psi", "lai_case", "band")
+    assert np.allclose(d["coords"]["psi"][1], [0.2, 0.9, 1.2]) and list(d["coords"]["lai_case"][1]) == [0, 1]
+    assert list(d["coords"]["band"][1]) == ["PAR", "NIR"] and d["coords"]["zm"][1].shape == (nz - 1,)
+    assert d["data_vars"]["F"][2]["units"] == "W m-2" and d["attrs"]["scheme_name"] == "n79"
+    for dims, data, _ in list(d["data_vars"].values()) + list(d["coords"].values()):
+        assert len(dims) == np.ndim(data)
+    with pytest.raises(ImportError):
+        sensitivity_to_xr(res, m, p_sets)  # xarray is not in this image
+    fake = types.ModuleType("xarray")
+    fake.Dataset = lambda **kw: kw
+    sys.modules["xarray"] = fake
+    try:
+        assert set(sensitivity_to_xr(res, m, p_sets)) == {"coords", "data_vars", "attrs"}
+    finally:
+        del sys.modules["xarray"]
+
+
 def test_host_prologue_uses_reference_quadratures(default_p):
     """The plugin path evaluates the Python callables with the same scipy calls as the reference."""
     import crt_oracle as oracle
