@@ -450,114 +450,133 @@ CRT_HD void column_g77(const ScenBf& s, const double* L, const double* eb, int n
 // I_df_d <- f_dn) and overwritten with the final values during back-substitution, so the solve needs
 // no scratch memory beyond the arrays it has to write anyway.  (Only the downward row's pair of every
 // CK-th level is parked -- checkpoints; everything between is recomputed in the back sweep.)
-// Level tables: tbcum[j] = exp(-K_b L[j]) (n_z), tb[j] = exp(-K_b dlai[j]), td[j] = tau_d(dlai[j]),
-// fsun[j] = exp(-K_b laim[j]), dlai[j]  (all n_z - 1)   (ref :41-59).
+// Level tables: everything of a row that does not depend on the band (fill_level_tables<N79>; ref :41-59).
 // =================================================================================================
 struct ScenN79 {
     double inv_mu;
 };
 
 // Layer coefficients shared by the upward row above a layer and the downward row below it:
-// aiv = fiv = refld - trand^2/refld,  biv = eiv = trand/refld   (ref :85-88, :98-101, :111-114).
+// aiv = fiv = refld - trand^2/refld,  biv = eiv = trand/refld   (ref :85-88, :98-101, :111-114), plus the
+// band-dependent factors of the two beam sources, rho - tau eiv (:108/:129) and tau - rho biv (:92/:118).
 // One reciprocal instead of the reference's two divisions (same algebra; <= 1 ulp apart).
-CRT_HD void n79_layer(double td, double rho, double tau, double& fiv, double& eiv) {
-    const double refld = (1.0 - td) * rho;
-    const double trand = (1.0 - td) * tau + td;
-    const double ir = rcp_nr(refld);
-    eiv = trand * ir;
-    fiv = refld - trand * eiv;
-}
+template <int VEC>
+struct N79Layer {
+    double f[VEC], e[VEC], wu[VEC], wd[VEC];
+};
 
+// tab = the eight level tables of fill_level_tables<N79>: tbcum, g, td, 1 - td, fsun, 1 - fsun, 1/(fsun dlai),
+// 1/((1 - fsun) dlai).
 template <int VEC, class Out>
-CRT_HD void column_n79(const ScenN79& s, const double* tbcum, const double* tb, const double* td, const double* fsun,
-                       const double* dlai, int n_z, const BandIn<VEC>& in, Out& out, double (&absorbed)[VEC]) {
+CRT_HD void column_n79(const ScenN79& s, const double* tab, int n_z, const BandIn<VEC>& in, Out& out,
+                       double (&absorbed)[VEC]) {
+    const double *tbcum = tab, *g = tab + n_z, *td = tab + 2 * n_z, *omtd = tab + 3 * n_z, *fsun = tab + 4 * n_z,
+                 *omfs = tab + 5 * n_z, *isl = tab + 6 * n_z, *ish = tab + 7 * n_z;
     const int CK = out.seg_levels();
-    // Layer coefficients are a pure function of (td, rho, tau): the upward row of level j and the downward
-    // row of level j-1 share layer j-1, and on equally spaced levels every layer has the same td, so the
-    // last evaluation is kept and reused while td repeats (td is a per-scenario table: the test is
-    // uniform over the CTA).
-    double c_td = -1.0, c_f[VEC], c_e[VEC];
-    auto layer = [&](double tdv) {
-        if (tdv != c_td) {
-            c_td = tdv;
+    using Lay = N79Layer<VEC>;
+    auto layer = [&](int i, Lay& L) {
+        const double t = td[i], o = omtd[i];
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) n79_layer(tdv, in.leaf_r[v], in.leaf_t[v], c_f[v], c_e[v]);
+        for (int v = 0; v < VEC; ++v) {
+            const double rho = in.leaf_r[v], tau = in.leaf_t[v];
+            const double refld = o * rho;
+            const double trand = o * tau + t;
+            const double ir = rcp_nr(refld);
+            L.e[v] = trand * ir;
+            L.f[v] = refld - trand * L.e[v];
+            L.wu[v] = rho - tau * L.e[v];
+            L.wd[v] = tau - rho * L.e[v];
         }
     };
-    // Forward-sweep coefficients of the UPWARD row of level j from those of the downward row of level j-1
-    // (e_in, f_in); level 0 is the soil row (ref :79-82; rows :101-108 / :122-129).  Used identically in both
-    // sweeps, so the back-substitution recomputes the forward values instead of loading them.
-    auto up_rows = [&](int j, const double (&e_in)[VEC], const double (&f_in)[VEC], double (&eu)[VEC], double (&fu)[VEC]) {
+    // Forward-sweep coefficients of the UPWARD row of level j >= 1 (a = -eiv, c = -fiv of the layer below, L) from
+    // those of the downward row of level j-1 (e_in, f_in); unit diagonal (ref :101-108 / :122-129, tdma :186, :191).
+    // Used identically in both sweeps, so the back-substitution recomputes the forward values.
+    auto up_row = [&](int j, const Lay& L, const double (&e_in)[VEC], const double (&f_in)[VEC], double (&eu)[VEC],
+                      double (&fu)[VEC]) {
+        const double gj = g[j];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const double d = in.Idr0[v] * gj * L.wu[v];
+            const double r = rcp_nr(1.0 + L.e[v] * e_in[v]);  // one reciprocal for both quotients of tdma
+            eu[v] = -L.f[v] * r;
+            fu[v] = (d + L.e[v] * f_in[v]) * r;
+        }
+    };
+    auto soil_row = [&](double (&eu)[VEC], double (&fu)[VEC]) {  // level 0 (ref :79-82)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            eu[v] = -in.soil_r[v];
+            fu[v] = in.Idr0[v] * tbcum[0] * in.soil_r[v];
+        }
+    };
+    // One level of the forward recurrence: (e, f) holds the downward row's pair of level j-1 on entry and of level j
+    // on exit; La holds layer j-1 on entry (j >= 1) and layer j on exit (the layer the next upward row needs).
+    auto step = [&](int j, Lay& La, double (&e)[VEC], double (&f)[VEC]) {
+        double eu[VEC], fu[VEC];
         if (j == 0) {
+            soil_row(eu, fu);
+        } else {
+            up_row(j, La, e, f, eu, fu);
+        }
+        if (j == n_z - 1) {  // top boundary: dn = sky diffuse (ref :132-135); a = c = 0
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                eu[v] = -in.soil_r[v];
-                fu[v] = in.Idr0[v] * tbcum[0] * in.soil_r[v];
+                e[v] = 0.0;
+                f[v] = in.Idf0[v];
             }
             return;
         }
-        layer(td[j - 1]);
+        // downward row (a = -aiv, c = -biv; ref :85-92 / :111-118): the soil row uses layer 1 as shipped
+        Lay L1;
+        if (j == 0) {
+            layer(1, L1);
+            layer(0, La);
+        } else {
+            layer(j, La);
+        }
+        const Lay& Ld = (j == 0) ? L1 : La;
+        const double gj = (j == 0) ? g[0] : g[j + 1];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            const double a = -c_e[v], c = -c_f[v];
-            const double d = in.Idr0[v] * tbcum[j] * (1.0 - tb[j - 1]) * (in.leaf_r[v] - in.leaf_t[v] * c_e[v]);
-            const double r = rcp_nr(1.0 - a * e_in[v]);  // one reciprocal for both quotients of tdma (ref :186, :191)
-            eu[v] = c * r;
-            fu[v] = (d - a * f_in[v]) * r;
+            const double d = in.Idr0[v] * gj * Ld.wd[v];
+            const double r = rcp_nr(1.0 + Ld.f[v] * eu[v]);
+            e[v] = -Ld.e[v] * r;
+            f[v] = (d + Ld.f[v] * fu[v]) * r;
         }
     };
-    // ... and of the DOWNWARD row of level j from the upward row of the same level (rows :85-92 / :111-118;
-    // top boundary :132-135).  May write its outputs over its inputs.
-    auto dn_rows = [&](int j, const double (&eu)[VEC], const double (&fu)[VEC], double (&ed)[VEC], double (&fd)[VEC]) {
-        if (j == n_z - 1) {  // top boundary: dn = sky diffuse; a = c = 0
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                ed[v] = 0.0;
-                fd[v] = in.Idf0[v];
-            }
-            return;
-        }
-        const int q = (j == 0) ? 1 : j;  // the soil row uses index 1 as shipped (ref :85-92)
-        layer(td[q]);
-        const double tbc = tbcum[q + 1 - (j == 0 ? 1 : 0)];
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            const double a = -c_f[v], c = -c_e[v];
-            const double d = in.Idr0[v] * tbc * (1.0 - tb[q]) * (in.leaf_t[v] - in.leaf_r[v] * c_e[v]);
-            const double r = rcp_nr(1.0 - a * eu[v]);
-            const double e_new = c * r;
-            fd[v] = (d - a * fu[v]) * r;
-            ed[v] = e_new;
-        }
-    };
-    // ---- forward sweep (ref tdma :183-192); unit diagonal.  Checkpointed: the DOWNWARD row's (e, f) of every
-    // CK-th level is parked (F <- e_dn, I_df_d <- f_dn), 16/CK B per layer.band; the back sweep re-runs the
-    // recurrence from a checkpoint through the CK levels above it into the Out object's segment store.
+    // ---- forward sweep (ref tdma :183-192).  Checkpointed: the DOWNWARD row's (e, f) of every CK-th level is
+    // parked (F <- e_dn, I_df_d <- f_dn), 16/CK B per layer.band; the back sweep re-runs the recurrence from a
+    // checkpoint through the CK levels above it into the Out object's segment store.
     double e_prev[VEC], f_prev[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) e_prev[v] = f_prev[v] = 0.0;
     const int g_last = (n_z - 1) / CK;  // segment g covers levels g CK .. min((g+1) CK, n_z) - 1
-    for (int j = 0; j < g_last * CK; ++j) {  // the top segment is left to the back sweep's recomputation
-        double eu[VEC], fu[VEC];
-        up_rows(j, e_prev, f_prev, eu, fu);
-        dn_rows(j, eu, fu, e_prev, f_prev);
-        if ((j + 1) % CK == 0) {
-            out.st_tmp(F_F, j, e_prev);
-            out.st_tmp(F_DN, j, f_prev);
+    {
+        Lay La;
+        for (int j = 0; j < g_last * CK; ++j) {  // the top segment is left to the back sweep's recomputation
+            step(j, La, e_prev, f_prev);
+            if ((j + 1) % CK == 0) {
+                out.st_tmp(F_F, j, e_prev);
+                out.st_tmp(F_DN, j, f_prev);
+            }
         }
     }
     // ---- back substitution (ref tdma :195-198) fused with the output stage (ref :141-161)
-    double up_above[VEC], dn_above[VEC], top[VEC][3];
+    double up_above[VEC], dn_above[VEC], top[VEC][3], Io[VEC], omo[VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) up_above[v] = dn_above[v] = 0.0;
-    for (int g = g_last; g >= 0; --g) {
-        const int base = g * CK;
+    for (int v = 0; v < VEC; ++v) {
+        up_above[v] = dn_above[v] = 0.0;
+        omo[v] = 1.0 - (in.leaf_r[v] + in.leaf_t[v]);
+        Io[v] = in.Idr0[v] * omo[v];
+    }
+    for (int sg = g_last; sg >= 0; --sg) {
+        const int base = sg * CK;
         const int len = (n_z - base < CK) ? n_z - base : CK;
         double e0[VEC], f0[VEC];  // downward row's pair of level base-1 (zeros below the soil row)
-        if (g == g_last) {        // still in registers from the forward sweep
+        if (sg == g_last) {       // still in registers from the forward sweep
 #pragma unroll
             for (int v = 0; v < VEC; ++v) { e0[v] = e_prev[v]; f0[v] = f_prev[v]; }
-        } else if (g > 0) {
+        } else if (sg > 0) {
             out.ld_tmp(F_F, base - 1, e0);
             out.ld_tmp(F_DN, base - 1, f0);
         } else {
@@ -566,12 +585,12 @@ CRT_HD void column_n79(const ScenN79& s, const double* tbcum, const double* tb, 
         }
         {
             double e[VEC], f[VEC];
+            Lay La;
+            if (base > 0) layer(base - 1, La);
 #pragma unroll
             for (int v = 0; v < VEC; ++v) { e[v] = e0[v]; f[v] = f0[v]; }
             for (int i = 0; i < len; ++i) {
-                double eu[VEC], fu[VEC];
-                up_rows(base + i, e, f, eu, fu);
-                dn_rows(base + i, eu, fu, e, f);
+                step(base + i, La, e, f);
                 out.seg_st(i, 0, e);
                 out.seg_st(i, 1, f);
             }
@@ -589,26 +608,30 @@ CRT_HD void column_n79(const ScenN79& s, const double* tbcum, const double* tb, 
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) { edl[v] = e0[v]; fdl[v] = f0[v]; }
             }
-            up_rows(j, edl, fdl, eu, fu);
+            if (j == 0) {
+                soil_row(eu, fu);
+            } else {
+                Lay Lb;
+                layer(j - 1, Lb);
+                up_row(j, Lb, edl, fdl, eu, fu);
+            }
+            const double tbc = tbcum[j];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 dn[v] = (j == n_z - 1) ? fd[v] : fd[v] - ed[v] * up_above[v];
                 up[v] = fu[v] - eu[v] * dn[v];
-                Idr[v] = in.Idr0[v] * tbcum[j];                                  // ref :151
+                Idr[v] = in.Idr0[v] * tbc;                                       // ref :151
                 F[v] = Idr[v] * s.inv_mu + 2.0 * dn[v] + 2.0 * up[v];            // ref :161
             }
             if (j < n_z - 1) {  // layer j (between levels j and j+1): absorbed per unit sunlit/shaded leaf area
                 double sl[VEC], sh[VEC];
-                const double inv_sl = rcp_nr(fsun[j] * dlai[j]), inv_sh = rcp_nr((1.0 - fsun[j]) * dlai[j]);
+                const double gd = g[j + 1], o = omtd[j], fs = fsun[j], ofs = omfs[j], wsl = isl[j], wsh = ish[j];
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
-                    const double one_m_om = 1.0 - (in.leaf_r[v] + in.leaf_t[v]);
-                    const double direct = in.Idr0[v] * tbcum[j + 1] * (1.0 - tb[j]) * one_m_om;    // ref :145
-                    const double diffuse = (dn_above[v] + up[v]) * (1.0 - td[j]) * one_m_om;       // ref :146
-                    const double sun = diffuse * fsun[j] + direct;                                 // ref :147
-                    const double shade = diffuse * (1.0 - fsun[j]);                                // ref :148
-                    sl[v] = sun * inv_sl;                                                          // ref :154
-                    sh[v] = shade * inv_sh;                                                        // ref :155
+                    const double direct = Io[v] * gd;                                  // ref :145
+                    const double diffuse = (dn_above[v] + up[v]) * o * omo[v];         // ref :146
+                    sl[v] = (diffuse * fs + direct) * wsl;                             // ref :147, :154
+                    sh[v] = (diffuse * ofs) * wsh;                                     // ref :148, :155
                 }
                 out.st(F_X0, j, sl);
                 out.st(F_X1, j, sh);

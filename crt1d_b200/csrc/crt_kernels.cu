@@ -955,6 +955,9 @@ static cudaError_t launch_rows_t(const crt1d_batch& in, const crt1d_out& out, in
     return cudaGetLastError();
 }
 
+#ifndef CRT_4S_LV
+#define CRT_4S_LV 10
+#endif
 template <int SCHEME, int MAXT, int LV = 6>
 static cudaError_t launch_rows(const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream) {
     const size_t smem = rows_shared_bytes<SCHEME>(in.n_z, in.n_wl);
@@ -999,7 +1002,7 @@ cudaError_t launch_solve(int scheme, const crt1d_batch& in, const crt1d_out& out
                 break;
             case CRT1D_SCHEME_4S:
                 if (rows_shared_bytes<CRT1D_SCHEME_4S>(in.n_z, in.n_wl) <= cap)  // 0.82 vs 0.76 tiled (with the recurrence)
-                    return launch_rows<CRT1D_SCHEME_4S, 384, 10>(in, out, vec2, stream);
+                    return launch_rows<CRT1D_SCHEME_4S, 384, CRT_4S_LV>(in, out, vec2, stream);
                 break;
             default: break;
         }

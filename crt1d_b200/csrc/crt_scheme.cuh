@@ -16,7 +16,7 @@ CRT_HD int n_level_tables(int scheme) {
         case CRT1D_SCHEME_BL: return 3;   // L, tau_b, tau_d
         case CRT1D_SCHEME_BF: return 2;   // L, exp(-k_b L)
         case CRT1D_SCHEME_G77: return 2;  // L, exp(-k_b L)
-        case CRT1D_SCHEME_N79: return 5;  // tbcum, tb, td, fsun, dlai
+        case CRT1D_SCHEME_N79: return 8;  // tbcum, g, td, 1-td, fsun, 1-fsun, 1/(fsun dlai), 1/((1-fsun) dlai)
         case CRT1D_SCHEME_ZQ: return 1;   // exp(-K L)
         case CRT1D_SCHEME_ZQ_PA: return 12;  // lai, exp(-Kb lai), cum[0..M], exp(-Kb cum[0..M]) (M <= n_z; 3 slots), kk, tt, ww; in emission order: (level, kk), tt, ww, exp(-Kb lai)
         default: return 0;
@@ -59,15 +59,31 @@ CRT_HD void fill_level_tables(const crt1d_batch& in, int64_t s, int j, double* t
             }
         }
     } else if constexpr (SCHEME == CRT1D_SCHEME_N79) {
-        tab[j] = exp(-K_b * Lj);  // tbcum, _solve_n79.py:46
-        if (j < n_z - 1) {
-            const double dl = Lj - lai[j + 1];                                    // _solve_n79.py:41
-            tab[n_z + j] = exp(-K_b * dl);                                        // tb, :45
-            tab[2 * n_z + j] = in.tau_d_lev[(int64_t)in.lai_idx[s] * n_z + j];    // td, :53 (prologue quadrature / 9sky)
-            tab[3 * n_z + j] = exp(-K_b * ((Lj + lai[j + 1]) / 2.0));             // fracsun, :57-58
-            tab[4 * n_z + j] = dl;
+        // Everything of a row that does not depend on the band (ref _solve_n79.py:41-59, :85-129, :145-155):
+        //   [0] tbcum[j] = exp(-K_b L[j])
+        //   [1] g[j]     = tbcum[j] (1 - tb[j-1]): the beam source of the upward row of level j and of the downward
+        //                  row of level j-1 (j >= 1); g[0] = tbcum[1] (1 - tb[1]), the soil-adjacent row as shipped (:85-92)
+        //   [2] td[j], [3] 1 - td[j]   layer j (between levels j and j+1): tau_d(dlai[j]) from the prologue
+        //   [4] fsun[j], [5] 1 - fsun[j], [6] 1 / (fsun dlai), [7] 1 / ((1 - fsun) dlai)
+        auto tb_of = [&](int i) { return exp(-K_b * (lai[i] - lai[i + 1])); };  // tb[i], :45
+        tab[j] = exp(-K_b * Lj);
+        if (j == 0) {
+            tab[n_z] = exp(-K_b * lai[1]) * (1.0 - tb_of(1));
         } else {
-            tab[n_z + j] = tab[2 * n_z + j] = tab[3 * n_z + j] = tab[4 * n_z + j] = 0.0;
+            tab[n_z + j] = tab[j] * (1.0 - tb_of(j - 1));
+        }
+        if (j < n_z - 1) {
+            const double dl = Lj - lai[j + 1];                                    // :41
+            const double tdj = in.tau_d_lev[(int64_t)in.lai_idx[s] * n_z + j];    // :53 (prologue quadrature / 9sky)
+            const double fs = exp(-K_b * ((Lj + lai[j + 1]) / 2.0));              // fracsun, :57-58
+            tab[2 * n_z + j] = tdj;
+            tab[3 * n_z + j] = 1.0 - tdj;
+            tab[4 * n_z + j] = fs;
+            tab[5 * n_z + j] = 1.0 - fs;
+            tab[6 * n_z + j] = 1.0 / (fs * dl);
+            tab[7 * n_z + j] = 1.0 / ((1.0 - fs) * dl);
+        } else {
+            for (int q = 2; q < 8; ++q) tab[q * n_z + j] = 0.0;
         }
     }
 }
@@ -138,7 +154,7 @@ CRT_HD void solve_column_group(const crt1d_batch& in, int64_t s, const double* t
     } else if constexpr (SCHEME == CRT1D_SCHEME_N79) {
         ScenN79 sc;
         sc.inv_mu = 1.0 / cos(psi);
-        column_n79<VEC>(sc, tab, tab + n_z, tab + 2 * n_z, tab + 3 * n_z, tab + 4 * n_z, n_z, b, out, absorbed);
+        column_n79<VEC>(sc, tab, n_z, b, out, absorbed);
     } else if constexpr (SCHEME == CRT1D_SCHEME_ZQ_PA) {
         ScenZqPa sc;
         sc.cos_psi = cos(psi);
