@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--scheme", default="2s")
     ap.add_argument("--scenarios", type=int, default=1_000_000, help="scenarios per GPU (cross product is truncated)")
     ap.add_argument("--chunk", type=int, default=4144, help="scenarios per kernel launch")
+    ap.add_argument("--nz", type=int, default=60, help="canopy levels (1000 = the deep-canopy case, BASELINE.json configs[4])")
     ap.add_argument("--cpu-sample", type=int, default=0, help="scenarios in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default): every rank runs its own --scenarios sweep; strong: ONE sweep of --scenarios "
@@ -56,10 +57,10 @@ def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
-def make_spec(seed, n_scen):
+def make_spec(seed, n_scen, n_z=60):
     from crt1d_b200 import sweep
 
-    spec = sweep.synthetic_sweep_spec(seed=seed)
+    spec = sweep.synthetic_sweep_spec(seed=seed, n_z=n_z)
     return spec if n_scen >= spec.n_scen else spec.slice(0, n_scen)
 
 
@@ -67,12 +68,12 @@ def make_spec(seed, n_scen):
 # CPU baseline: the oracle port (numpy restatement of the reference solver) on the host cores
 # ------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    scheme, seed, idx = args
+    scheme, seed, idx, n_z = args
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import crt_oracle as oracle
 
-    spec = make_spec(seed, 10**9)
+    spec = make_spec(seed, 10**9, n_z)
     t0 = time.perf_counter()
     units = 0
     for s in idx:
@@ -81,26 +82,26 @@ def _cpu_worker(args):
     return units, time.perf_counter() - t0
 
 
-def cpu_baseline(scheme, n_sample, cores=None):
+def cpu_baseline(scheme, n_sample, cores=None, n_z=60):
     """Time the oracle port on a strided sample of the sweep, one process per host core."""
     import multiprocessing as mp
 
     cores = cores or os.cpu_count() or 1
     if n_sample <= 0:  # ~10-30 s of CPU work: per-scenario cost of the vectorised port, measured roughly
         per = {"2s": 0.012, "bf": 0.012, "g77": 0.012, "bl": 0.15, "zq": 0.45, "n79": 0.25, "4s": 25.0}.get(scheme, 0.05)
-        n_sample = int(max(cores, min(4096, 15.0 * cores / per)))
+        n_sample = int(max(cores, min(4096, 15.0 * cores / (per * n_z / 60.0))))
     idx = np.linspace(0, 999_999, n_sample).astype(np.int64)
     parts = [idx[i::cores] for i in range(cores)]
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(scheme, 0, p) for p in parts if len(p)])
+        res = pool.map(_cpu_worker, [(scheme, 0, p, n_z) for p in parts if len(p)])
     wall = time.perf_counter() - t0
     units = sum(r[0] for r in res)
     busy = max(r[1] for r in res)
     return {
         "value": units / busy, "unit": UNIT, "cores": cores, "kind": "port",
-        "sample": f"{n_sample} scenarios strided over the 10^6-scenario sweep, {scheme}, 2100 bands x 60 levels, "
+        "sample": f"{n_sample} scenarios strided over the 10^6-scenario sweep, {scheme}, 2100 bands x {n_z} levels, "
                   f"numpy oracle port, {cores} processes; busy {busy:.1f} s (wall incl. spawn {wall:.1f} s)",
     }
 
@@ -114,11 +115,11 @@ def run_reference(args):
         return
     vals = []
     for _ in range(max(1, args.warmup > 0)):
-        cpu_baseline(args.scheme, max(8, (os.cpu_count() or 1)))
+        cpu_baseline(args.scheme, max(8, (os.cpu_count() or 1)), n_z=args.nz)
     cb = None
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cb = cpu_baseline(args.scheme, args.cpu_sample)
+        cb = cpu_baseline(args.scheme, args.cpu_sample, n_z=args.nz)
         vals.append(cb["value"])
     ms = (time.perf_counter() - t0) * 1e3 / max(1, args.steps)
     v = float(np.mean(vals))
@@ -127,7 +128,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "scheme": args.scheme, "n_z": 60, "n_wl": 2100,
+        "config": {"workload": workload_name(args), "scheme": args.scheme, "n_z": args.nz, "n_wl": 2100,
                    "note": "each step = bounded strided sample of the sweep on the host cores"},
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -137,7 +138,7 @@ def run_reference(args):
 
 def workload_name(args):
     return (f"batched {args.scheme} sweep: {args.scenarios} scenarios (SZA x LAI x PROSPECT-style spectra) x 2100 "
-            f"1-nm bands x 60 levels per GPU (BASELINE.json configs[2])")
+            f"1-nm bands x {args.nz} levels per GPU (BASELINE.json configs[{2 if args.nz == 60 else 4}])")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -218,11 +219,11 @@ def main():
         torch.cuda.synchronize()
 
     if args.scaling == "strong":  # one sweep, contiguous scenario blocks per rank (distributed.shard_batch)
-        full = make_spec(0, args.scenarios)
+        full = make_spec(0, args.scenarios, args.nz)
         spec, _ = cdist.shard_batch(full, world, rank)
         n_total_strong = full.n_scen
     else:  # weak scaling: every rank owns a full sweep (seed = rank)
-        spec = make_spec(rank, args.scenarios)
+        spec = make_spec(rank, args.scenarios, args.nz)
         n_total_strong = None
     pdt = torch.float32 if args.profile_dtype == "f32" else None
     runner = sweep.SweepRunner(spec, args.scheme, chunk=args.chunk, device=dev, profile_dtype=pdt)
@@ -329,7 +330,7 @@ def main():
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb = cpu_baseline(args.scheme, args.cpu_sample)
+        cb = cpu_baseline(args.scheme, args.cpu_sample, n_z=args.nz)
 
     if rank == 0:
         line = {
