@@ -665,33 +665,12 @@ struct ScenZq {
     double inv_mu, cos_psi, tau_i, t_psi;
 };
 
-struct ZqRowSet {  // coefficients of rows 2li-1 ("A") and 2li ("B") for one li class
-    double subA, mainA, supA, subB, mainB, supB, m_lo, m_hi, s_lo, s_me, inv_m_lo;
-};
-
-CRT_HD ZqRowSet zq_rows(double r_lo, double a_lo, double t_lo, double r_me, double a_me, double t_me, double r_hi,
-                        double a_hi, double t_hi) {
-    ZqRowSet q;
-    const double pen = t_me + (1.0 - t_me) * (1.0 - a_me) * (1.0 - r_me);
-    q.s_lo = r_lo * (1.0 - a_lo) * (1.0 - t_lo);
-    q.s_me = r_me * (1.0 - a_me) * (1.0 - t_me);
-    const double s_hi = r_hi * (1.0 - a_hi) * (1.0 - t_hi);
-    q.m_lo = 1.0 - q.s_lo * q.s_me;
-    q.m_hi = 1.0 - q.s_me * s_hi;
-    q.inv_m_lo = 1.0 / q.m_lo;
-    q.subA = -pen;             // A[2li-1, 2li-2]  (ref :113)
-    q.mainA = -q.s_lo * pen;   // A[2li-1, 2li-1]  (ref :114)
-    q.supA = q.m_lo;           // A[2li-1, 2li]    (ref :115)
-    q.subB = q.m_hi;           // A[2li,   2li-1]  (ref :116)
-    q.mainB = -s_hi * pen;     // A[2li,   2li]    (ref :117)
-    q.supB = -pen;             // A[2li,   2li+1]  (ref :118)
-    return q;
-}
-
-// Per-column constants of the zq rows.  The middle layer of every row pair is a real layer, so the twelve
-// coefficients of zq_rows() reduce to: pen and s = s_me (always), s_lo in {s, s_bot} (soil ghost below
-// li = 1), s_hi in {s, 0} (top ghost above li = m), m_lo in {m_mid, m_bot}, m_hi in {m_mid, 1}.
-// Same expressions as zq_rows(), evaluated once per column instead of once per row class.
+// Per-column constants of the zq rows.  With r, a, t of the layer below (lo), the layer itself (me) and the
+// layer above (hi) of row pair li, the reference's coefficients (ref :113-118) are
+//   pen = t_me + (1 - t_me)(1 - a_me)(1 - r_me),   s_x = r_x (1 - a_x)(1 - t_x),   m_lo = 1 - s_lo s_me,  m_hi = 1 - s_me s_hi
+//   row 2li-1:  sub = -pen,  main = -s_lo pen,  sup = m_lo;      row 2li:  sub = m_hi,  main = -s_hi pen,  sup = -pen.
+// The middle layer is always a real layer, so only s_lo in {s, s_bot} (soil ghost below li = 1: r = 1, t = 0,
+// a = 1 - rho), s_hi in {s, 0} (top ghost above li = m), m_lo in {m_mid, m_bot} and m_hi in {m_mid, 1} vary.
 struct ZqCol {
     double pen, s, s_bot, m_mid, m_bot, im_mid, im_bot;
     double mainAB, kA, kB;  // interior rows: -s pen (both diagonals), m_mid cA, m_mid cB

@@ -92,10 +92,6 @@ struct GlobalOut {
             }
         }
     }
-    // one column at a time (zq_pa finishes each column before starting the next); float64 only
-    __device__ __forceinline__ void st1(int f, int j, int v, double x) const {
-        if (FAST || base[f] != nullptr) __stcs(base[f] + at(f, j) + v, x);
-    }
     // elimination scratch parked in the output arrays: re-read by the same thread during
     // back-substitution -> default (write-back, L2-resident) stores
     __device__ __forceinline__ void st_tmp(int f, int j, const double (&x)[VEC]) const {

@@ -121,9 +121,6 @@ CRT_HD void fill_level_tables_3(const crt1d_batch& in, int64_t s, int j, double*
         tab[11 * n_z + rank] = tab[n_z + j];
     }
 }
-// number of table passes a scheme needs
-CRT_HD int n_table_passes(int scheme) { return scheme == CRT1D_SCHEME_ZQ_PA ? 3 : 1; }
-
 // Solve VEC adjacent columns of scenario s.  `tab` = the level tables above.
 template <int SCHEME, int VEC, class Out>
 CRT_HD void solve_column_group(const crt1d_batch& in, int64_t s, const double* tab, const BandIn<VEC>& b, Out& out,

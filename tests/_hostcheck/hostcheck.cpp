@@ -21,9 +21,6 @@ struct HostOut {
         if (!p[f]) return;
         for (int v = 0; v < VEC; ++v) p[f][(int64_t)j * stride + v] = x[v];
     }
-    void st1(int f, int j, int v, double x) const {
-        if (p[f]) p[f][(int64_t)j * stride + v] = x;
-    }
     void st_tmp(int f, int j, const double (&x)[VEC]) const { st(f, j, x); }
     // segment store of the checkpointed Thomas sweeps (shared memory on the device)
     static constexpr int CK = 8;
