@@ -73,8 +73,8 @@ int validate(int scheme, const crt1d_batch* in, const crt1d_out* out) {
             return fail(CRT1D_ERR_NULL_POINTER, sn + ": I_dr, I_df_d, I_df_u and F are all required (used as elimination scratch)");
     }
     if (out->profile_f32 != 0 && out->profile_f32 != 1) return fail(CRT1D_ERR_INVALID_ARG, "crt1d_out.profile_f32 must be 0 or 1");
-    if (out->profile_f32 && (scheme == CRT1D_SCHEME_N79 || scheme == CRT1D_SCHEME_ZQ || scheme == CRT1D_SCHEME_ZQ_PA))
-        return fail(CRT1D_ERR_UNSUPPORTED, sn + ": float32 profile storage is not available (float64 elimination scratch lives in the profile arrays)");
+    if (out->profile_f32 && (scheme == CRT1D_SCHEME_N79 || scheme == CRT1D_SCHEME_ZQ))
+        return fail(CRT1D_ERR_UNSUPPORTED, sn + ": float32 profile storage is not available (float64 elimination checkpoints live in the profile arrays)");
     if (out->n_bw < 0 || out->n_bw > 4) return fail(CRT1D_ERR_INVALID_ARG, "crt1d_out.n_bw must be in 0..4");
     if (out->absorbed != nullptr && (out->band_w == nullptr || out->n_bw == 0))
         return fail(CRT1D_ERR_NULL_POINTER, "crt1d_out.absorbed needs band_w and n_bw >= 1");

@@ -740,23 +740,30 @@ struct RowsTraits<CRT1D_SCHEME_4S> {
     }
 };
 
-template <int SCHEME, int VEC, int LV, int MAXT, bool F32, bool FUSED>
-__global__ void __launch_bounds__(MAXT, 1) solve_rows_kernel(const crt1d_batch in, const crt1d_out out) {
+template <int SCHEME, int VEC, int LV, int MAXT, bool F32, bool FUSED, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) solve_rows_kernel(const crt1d_batch in, const crt1d_out out, int split) {
     using TR = RowsTraits<SCHEME>;
     constexpr int NC = TR::NC, NF = TR::NF;
-    extern __shared__ double sm[];
-    __shared__ double partial[ROWS_MAX_CHUNKS][4];
-    __shared__ int ready[ROWS_MAX_CHUNKS];
+    extern __shared__ double sm[];  // [level tables][coefficients NC x ld][partial sums chunks x 4][ready flags chunks]
     __shared__ int counter;
     __shared__ unsigned char grp_uniform[1024];  // 4s: level group is equally spaced (recurrence allowed)
 
-    const int64_t s = blockIdx.x;
+    // `split` CTAs share a scenario, each owning a contiguous range of band chunks (split = 2 for 4s: two CTAs
+    // per SM, so one CTA's store-free coefficient phase overlaps the other's level sweeps)
+    const int64_t s = blockIdx.x / split;
+    const int part = blockIdx.x - (int)s * split;
     const int n_z = in.n_z, n_wl = in.n_wl, T = blockDim.x;
-    const int ld = (n_wl + 1) & ~1;
     const int n_tab = n_level_tables(SCHEME) * n_z;
-    double* cf = sm + n_tab + (n_tab & 1);  // [NC][ld], 16-byte aligned
     const int n_grp = n_wl / VEC;
-    const int n_chunks = (n_grp + 31) / 32;
+    const int chunks_all = (n_grp + 31) / 32;
+    const int chunks_per_part = (chunks_all + split - 1) / split;
+    const int chunk_lo = part * chunks_per_part;
+    const int n_chunks = max(0, min(chunks_all, chunk_lo + chunks_per_part) - chunk_lo);  // this CTA's chunks
+    const int col_lo = chunk_lo * 32 * VEC;
+    const int ld = min((n_wl + 1) & ~1, chunks_per_part * 32 * VEC);
+    double* cf = sm + n_tab + (n_tab & 1) - col_lo;  // [NC][ld] indexed by GLOBAL column, 16-byte aligned
+    double (*partial)[4] = reinterpret_cast<double (*)[4]>(sm + n_tab + (n_tab & 1) + (size_t)NC * ld);
+    int* ready = reinterpret_cast<int*>(partial + chunks_per_part);
 
     // ---- phase A: level tables, flags
     for (int j = threadIdx.x; j < n_z; j += T) fill_level_tables<SCHEME>(in, s, j, sm);
@@ -792,7 +799,7 @@ __global__ void __launch_bounds__(MAXT, 1) solve_rows_kernel(const crt1d_batch i
     // Coefficients of one chunk (32*VEC bands, one lane per VEC adjacent bands) -> shared memory, plus the chunk's
     // contribution to the canopy-absorbed sums from its ground and top levels (warp-reduced in fixed lane order).
     auto produce = [&](int chunk, typename TR::Coef (&k)[VEC]) {
-        const int g = chunk * 32 + lane;
+        const int g = (chunk_lo + chunk) * 32 + lane;
         const bool valid = g < n_grp;
         const int c0 = (valid ? g : 0) * VEC;
         double a4[4] = {0.0, 0.0, 0.0, 0.0};
@@ -846,7 +853,7 @@ __global__ void __launch_bounds__(MAXT, 1) solve_rows_kernel(const crt1d_batch i
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
         const int lg = item / n_chunks, chunk = item - lg * n_chunks;
-        const int g = chunk * 32 + lane;
+        const int g = (chunk_lo + chunk) * 32 + lane;
         const bool valid = g < n_grp;
         const int c0 = (valid ? g : 0) * VEC;
         typename TR::Coef k[VEC];
@@ -927,16 +934,25 @@ __global__ void __launch_bounds__(MAXT, 1) solve_rows_kernel(const crt1d_batch i
         if (threadIdx.x < out.n_bw) {
             double v = 0.0;
             for (int q = 0; q < n_chunks; ++q) v += partial[q][threadIdx.x];
-            out.absorbed[s * out.n_bw + threadIdx.x] = v;
+            if (split == 1) {
+                out.absorbed[s * out.n_bw + threadIdx.x] = v;
+            } else {  // two parts into a zeroed sum: 0 + a + b = 0 + b + a exactly, so still deterministic
+                atomicAdd(&out.absorbed[s * out.n_bw + threadIdx.x], v);
+            }
         }
     }
 }
 
 template <int SCHEME>
-static size_t rows_shared_bytes(int n_z, int n_wl) {
-    const int ld = (n_wl + 1) & ~1;
+static size_t rows_shared_bytes(int n_z, int n_wl, int split = 1, int vec = 2) {
+    int ld = (n_wl + 1) & ~1;
+    if (split > 1) {
+        const int chunks_all = (n_wl / vec + 31) / 32;
+        ld = min(ld, (chunks_all + split - 1) / split * 32 * vec);
+    }
     const int n_tab = n_level_tables(SCHEME) * n_z;
-    return (size_t)(n_tab + (n_tab & 1) + RowsTraits<SCHEME>::NC * ld) * sizeof(double);
+    const int chunks_per_part = ((n_wl / vec + 31) / 32 + split - 1) / split;
+    return (size_t)(n_tab + (n_tab & 1) + RowsTraits<SCHEME>::NC * ld) * sizeof(double) + (size_t)chunks_per_part * (4 * sizeof(double) + sizeof(int));
 }
 
 template <int SCHEME, int VEC, int LV, int MAXT, bool F32>
@@ -944,19 +960,40 @@ static cudaError_t launch_rows_t(const crt1d_batch& in, const crt1d_out& out, in
     // 4s: its coefficient stage (eigen-system + 4x4 solve, 168 registers) is better kept as a separate phase
     // (0.82 vs 0.77 of HBM peak when fused into the first item); bl/bf/g77 fuse it (no store-free phase).
     constexpr bool FUSED = SCHEME != CRT1D_SCHEME_4S;
-    auto kern = solve_rows_kernel<SCHEME, VEC, LV, MAXT, F32, FUSED>;
+    if constexpr (SCHEME == CRT1D_SCHEME_4S) {
+        // Two CTAs per SM, each on half of the scenario's band chunks (half the coefficient array: 2 x ~106 KB):
+        // one CTA's store-free coefficient phase (~20 % of its life) overlaps the other's level sweeps.
+        const char* env = getenv("CRT1D_B200_4S_SPLIT");
+        const int split = env ? atoi(env) : 2;
+        const size_t smem2 = rows_shared_bytes<SCHEME>(in.n_z, in.n_wl, 2, VEC);
+        if (split == 2 && in.n_scen * 2 <= 2147483647LL && 2 * (smem2 + 3 * 1024) <= 228u * 1024u) {
+            auto kern2 = solve_rows_kernel<SCHEME, VEC, LV, MAXT / 2, F32, FUSED, 2>;
+            cudaError_t e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            if (e != cudaSuccess) return e;
+            if (out.absorbed) {
+                e = cudaMemsetAsync(out.absorbed, 0, (size_t)in.n_scen * out.n_bw * sizeof(double), stream);
+                if (e != cudaSuccess) return e;
+            }
+            kern2<<<(unsigned)(in.n_scen * 2), min(th, MAXT / 2), smem2, stream>>>(in, out, 2);
+            return cudaGetLastError();
+        }
+    }
+    auto kern = solve_rows_kernel<SCHEME, VEC, LV, MAXT, F32, FUSED, 1>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)in.n_scen, th, smem, stream>>>(in, out);
+    kern<<<(unsigned)in.n_scen, th, smem, stream>>>(in, out, 1);
     return cudaGetLastError();
 }
 
+// 4s level groups: 10 levels per work item.  Measured (two CTAs per SM): 15 levels 0.80, 30 levels 0.81 vs 0.77 --
+// but the gain is the smaller number of exact exponentials, and the drift of a 30-level recurrence times the
+// cancellation in weak bands reached 2.2e-9 (bar: 1e-9); 30-level items re-anchored every 10 levels: 0.786 vs 0.795.
 #ifndef CRT_4S_LV
 #define CRT_4S_LV 10
 #endif
 template <int SCHEME, int MAXT, int LV = 6>
 static cudaError_t launch_rows(const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream) {
-    const size_t smem = rows_shared_bytes<SCHEME>(in.n_z, in.n_wl);
+    const size_t smem = rows_shared_bytes<SCHEME>(in.n_z, in.n_wl, 1, vec2 ? 2 : 1);
     int th = MAXT;
     const char* env = getenv("CRT1D_B200_ROWS_THREADS");
     if (env && atoi(env) >= 64 && atoi(env) <= MAXT && atoi(env) % 32 == 0) th = atoi(env);
@@ -984,20 +1021,20 @@ cudaError_t launch_solve(int scheme, const crt1d_batch& in, const crt1d_out& out
             return vec2 ? launch_rows_2s<2>(in, out, stream) : launch_rows_2s<1>(in, out, stream);
     }
     if (in.n_scen >= scen_kernel_min_batch() && getenv("CRT1D_B200_NO_ROWS") == nullptr) {
-        const size_t cap = 227u * 1024u - 12288u;  // dynamic + ~10 KB static shared memory of one CTA
+        const size_t cap = 227u * 1024u - 2048u;  // dynamic + ~1 KB static shared memory of one CTA
         if ((in.n_wl / (vec2 ? 2 : 1) + 31) / 32 > ROWS_MAX_CHUNKS) goto tile;
         switch (scheme) {
             case CRT1D_SCHEME_BL:
-                if (rows_shared_bytes<CRT1D_SCHEME_BL>(in.n_z, in.n_wl) <= cap) return launch_rows<CRT1D_SCHEME_BL, 512>(in, out, vec2, stream);
+                if (rows_shared_bytes<CRT1D_SCHEME_BL>(in.n_z, in.n_wl, 1, vec2 ? 2 : 1) <= cap) return launch_rows<CRT1D_SCHEME_BL, 512>(in, out, vec2, stream);
                 break;
             case CRT1D_SCHEME_BF:
-                if (rows_shared_bytes<CRT1D_SCHEME_BF>(in.n_z, in.n_wl) <= cap) return launch_rows<CRT1D_SCHEME_BF, 512>(in, out, vec2, stream);
+                if (rows_shared_bytes<CRT1D_SCHEME_BF>(in.n_z, in.n_wl, 1, vec2 ? 2 : 1) <= cap) return launch_rows<CRT1D_SCHEME_BF, 512>(in, out, vec2, stream);
                 break;
             case CRT1D_SCHEME_G77:
-                if (rows_shared_bytes<CRT1D_SCHEME_G77>(in.n_z, in.n_wl) <= cap) return launch_rows<CRT1D_SCHEME_G77, 512>(in, out, vec2, stream);
+                if (rows_shared_bytes<CRT1D_SCHEME_G77>(in.n_z, in.n_wl, 1, vec2 ? 2 : 1) <= cap) return launch_rows<CRT1D_SCHEME_G77, 512>(in, out, vec2, stream);
                 break;
             case CRT1D_SCHEME_4S:
-                if (rows_shared_bytes<CRT1D_SCHEME_4S>(in.n_z, in.n_wl) <= cap)  // 0.82 vs 0.76 tiled (with the recurrence)
+                if (rows_shared_bytes<CRT1D_SCHEME_4S>(in.n_z, in.n_wl, 1, vec2 ? 2 : 1) <= cap)  // 0.82 vs 0.76 tiled (with the recurrence)
                     return launch_rows<CRT1D_SCHEME_4S, 384, CRT_4S_LV>(in, out, vec2, stream);
                 break;
             default: break;

@@ -215,9 +215,9 @@ class OutputBuffers:
         pdt = torch.float64 if profile_dtype in (None, "f64", torch.float64) else profile_dtype
         if pdt in ("f32", torch.float32):
             pdt = torch.float32
-            if scheme in ("n79", "zq", "zq_pa"):
-                raise ValueError(f"{scheme}: float32 profile storage is not available (the tridiagonal schemes park "
-                                 "float64 elimination scratch in the profile arrays)")
+            if scheme in ("n79", "zq"):
+                raise ValueError(f"{scheme}: float32 profile storage is not available (n79 and zq park float64 "
+                                 "elimination checkpoints in the profile arrays)")
         elif pdt is not torch.float64:
             raise ValueError("profile_dtype must be float64 (default) or float32")
         self.profile_f32 = pdt is torch.float32

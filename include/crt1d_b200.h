@@ -135,8 +135,8 @@ typedef struct crt1d_out {
      * 0 = float64 (the reference's layout, default); 1 = I_dr, I_df_d, I_df_u, F, x0, x1, x2 point to
      * float arrays of the same shapes.  All arithmetic stays float64 (fp64 coefficient stage AND level stage,
      * so the result is the float64 value rounded once: rel. err <= 6e-8); rho_c / absorbed stay float64.
-     * Halves the HBM traffic of the write-bound schemes.  Not available for n79, zq, zq_pa
-     * (CRT1D_ERR_UNSUPPORTED): they park float64 elimination scratch in the profile arrays. */
+     * Halves the HBM traffic of the write-bound schemes.  Not available for n79 and zq
+     * (CRT1D_ERR_UNSUPPORTED): they park float64 elimination checkpoints in the profile arrays. */
     int32_t profile_f32;
 } crt1d_out;
 

@@ -593,12 +593,12 @@ def test_reduced_diagnostic_mode(scheme):
     assert torch.equal(ob.t["absorbed"], full["absorbed"])
 
 
-@pytest.mark.parametrize("scheme", ["2s", "4s", "bl", "bf", "g77"])
+@pytest.mark.parametrize("scheme", ["2s", "4s", "bl", "bf", "g77", "zq_pa"])
 @pytest.mark.parametrize("n_scen", [5, 160])
 def test_float32_profile_storage(scheme, n_scen):
     """Optional float32 path of BASELINE.json (<= 1e-5): float64 arithmetic, float32 storage.  The stored value
     must be the float64 result rounded once (<= 2^-24 relative), through the tile kernel (5 scenarios) and the
-    row-sweep kernels (160); diagnostics stay float64 and identical.  Tridiagonal schemes refuse."""
+    row-sweep kernels (160); diagnostics stay float64 and identical.  n79 and zq refuse (checkpoints in the outputs)."""
     import torch
 
     from crt1d_b200 import engine
