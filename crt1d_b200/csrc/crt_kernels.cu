@@ -1035,7 +1035,10 @@ cudaError_t launch_solve(int scheme, const crt1d_batch& in, const crt1d_out& out
                 break;
             case CRT1D_SCHEME_4S:
                 if (rows_shared_bytes<CRT1D_SCHEME_4S>(in.n_z, in.n_wl, 1, vec2 ? 2 : 1) <= cap)  // 0.82 vs 0.76 tiled (with the recurrence)
-                    return launch_rows<CRT1D_SCHEME_4S, 384, CRT_4S_LV>(in, out, vec2, stream);
+#ifndef CRT_4S_MAXT
+#define CRT_4S_MAXT 512  // split: 2 x 256 threads at 128 registers 0.786 vs 2 x 192 at 168 registers 0.768
+#endif
+                    return launch_rows<CRT1D_SCHEME_4S, CRT_4S_MAXT, CRT_4S_LV>(in, out, vec2, stream);
                 break;
             default: break;
         }
