@@ -1,7 +1,7 @@
 """ctypes mirror of include/crt1d_b200.h (structs, constants, function prototypes)."""
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 OK = 0
 ERR_INVALID_ARG = -1
@@ -99,6 +99,7 @@ PROTOTYPES = {
                   C.c_void_p]),
     "crt1d_leaf_G": (C.c_int, [C.c_int, C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "crt1d_tau_d": (C.c_int, [C.c_int, C.c_double, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crt1d_smear_tuv": (C.c_int, [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "crt1d_leaf_integrals": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
 }
 

@@ -243,6 +243,17 @@ int crt1d_tau_d(int family, double param, int n_quad, int64_t n, const double* L
     return CRT1D_OK;
 }
 
+int crt1d_smear_tuv(int64_t n_rows, int32_t n_x, const double* x, const double* y, int32_t n_bins, const double* bins,
+                    double* out, void* stream) {
+    if (n_rows < 0 || n_x < 2 || n_bins < 0) return fail(CRT1D_ERR_INVALID_ARG, "crt1d_smear_tuv: need n_rows >= 0, n_x >= 2, n_bins >= 0");
+    if (n_rows * (int64_t)n_bins > 2147483647LL * 128) return fail(CRT1D_ERR_INVALID_ARG, "crt1d_smear_tuv: too many (row, bin) pairs");
+    if (n_rows > 0 && n_bins > 0 && (x == nullptr || y == nullptr || bins == nullptr || out == nullptr))
+        return fail(CRT1D_ERR_NULL_POINTER, "crt1d_smear_tuv: x / y / bins / out is NULL");
+    cudaError_t e = crt::launch_smear_tuv(n_rows, n_x, x, y, n_bins, bins, out, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "launch of smear_tuv kernel");
+    return CRT1D_OK;
+}
+
 int crt1d_leaf_integrals(int family, double param, double mu_s, int n_quad, double* out, void* stream) {
     if (family < 0 || family > CRT1D_G_ELLIPSOIDAL_APPROX_BONAN) return fail(CRT1D_ERR_INVALID_ARG, "unknown leaf-angle family");
     if (out == nullptr) return fail(CRT1D_ERR_NULL_POINTER, "out is NULL");

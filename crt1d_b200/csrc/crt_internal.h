@@ -20,5 +20,7 @@ cudaError_t launch_tau_d(int family, double param, const QuadRule& rule, int64_t
                          cudaStream_t stream);
 cudaError_t launch_leaf_integrals(int family, double param, double mu_s, const QuadRule& rule, double* out,
                                   cudaStream_t stream);
+cudaError_t launch_smear_tuv(int64_t n_rows, int n_x, const double* x, const double* y, int n_bins, const double* bins,
+                             double* out, cudaStream_t stream);
 
 }  // namespace crt

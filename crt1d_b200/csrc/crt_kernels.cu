@@ -17,6 +17,7 @@
 
 #include "crt_internal.h"
 #include "crt_scheme.cuh"
+#include "crt_spectra.cuh"
 
 namespace crt {
 
@@ -1234,6 +1235,27 @@ __global__ void leaf_integrals_kernel(int family, double param, double mu_s, Qua
 cudaError_t launch_leaf_integrals(int family, double param, double mu_s, const QuadRule& rule, double* out,
                                   cudaStream_t stream) {
     leaf_integrals_kernel<<<1, 32, 0, stream>>>(family, param, mu_s, rule, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// spectral binning: out[r][i] = average of y_r(x) over [bins[i], bins[i+1]]   (ref spectra.py smear_tuv)
+// one thread per (row, bin); rows are spectra of a library sharing the grid x
+// ---------------------------------------------------------------------------------------------
+__global__ void smear_tuv_kernel(int64_t n_rows, int n_x, const double* __restrict__ x, const double* __restrict__ y,
+                                 int n_bins, const double* __restrict__ bins, double* out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_rows * n_bins) return;
+    const int64_t r = t / n_bins;
+    const int i = (int)(t - r * n_bins);
+    out[t] = smear_tuv_bin(x, y + r * n_x, n_x, bins[i], bins[i + 1]);
+}
+
+cudaError_t launch_smear_tuv(int64_t n_rows, int n_x, const double* x, const double* y, int n_bins, const double* bins,
+                             double* out, cudaStream_t stream) {
+    const int64_t n = n_rows * n_bins;
+    if (n == 0) return cudaSuccess;
+    smear_tuv_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n_rows, n_x, x, y, n_bins, bins, out);
     return cudaGetLastError();
 }
 

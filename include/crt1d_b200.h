@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CRT1D_ABI_VERSION 2
+#define CRT1D_ABI_VERSION 3
 
 /* exported-symbol marker (the library is built with -fvisibility=hidden) */
 #if defined(__GNUC__)
@@ -203,6 +203,13 @@ CRT1D_API int crt1d_tau_d(int family, double param, int n_quad, int64_t n, const
 /* scalars that depend on the leaf-angle family only: out[0] = mu_bar (2s), out[1], out[2] = G sector
  * integrals for `mu_s` (4s); Gauss-Legendre with n_quad nodes.  `out` is a DEVICE pointer to 3 doubles. */
 CRT1D_API int crt1d_leaf_integrals(int family, double param, double mu_s, int n_quad, double* out, void* stream);
+
+/* ---- spectral binning (device pointers, asynchronous) ---------------------------------------------
+ * out[r][i] = trapezoidally integrated average of y_r(x) over [bins[i], bins[i+1]], i < n_bins, for n_rows
+ * spectra y[n_rows][n_x] on one ascending grid x[n_x]; bins[n_bins + 1] ascending
+ * (replaces spectra.smear_tuv / _smear_tuv_1, crt1d/spectra.py:221-300).            */
+CRT1D_API int crt1d_smear_tuv(int64_t n_rows, int32_t n_x, const double* x, const double* y, int32_t n_bins,
+                              const double* bins, double* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -651,3 +651,29 @@ ARGS = {
 def run(scheme, p, **extra):
     """Call an oracle solver from a full parameter dict (as `Model.run` does, ref model.py:305-310)."""
     return SOLVERS[scheme](**{k: p[k] for k in ARGS[scheme]}, **extra)
+
+
+def smear_tuv(x, y, bins):
+    """TUV / F0AM bin averaging: trapezoidally integrated average of y(x) in every bin
+    (ref crt1d/spectra.py:221-300, `_smear_tuv_1` + `smear_tuv`).  Restated per bin with the reference's
+    trapezoid loop (clipped trapezoids visited in increasing k, `area += (a2 - a1) (b2 + b1) / 2`), vectorised
+    over the rows of a 2-D `y`."""
+    x = np.asarray(x, dtype=np.float64)
+    y2 = np.atleast_2d(np.asarray(y, dtype=np.float64))
+    bins = np.asarray(bins, dtype=np.float64)
+    out = np.zeros((y2.shape[0], bins.size - 1))
+    for i, (xl, xu) in enumerate(zip(bins[:-1], bins[1:])):
+        area = np.zeros(y2.shape[0])
+        for k in range(x.size - 1):
+            if x[k + 1] < xl:
+                continue
+            if x[k] > xu:
+                break
+            a1 = max(x[k], xl)
+            a2 = min(x[k + 1], xu)
+            slope = (y2[:, k + 1] - y2[:, k]) / (x[k + 1] - x[k])
+            b1 = y2[:, k] + slope * (a1 - x[k])
+            b2 = y2[:, k] + slope * (a2 - x[k])
+            area = area + (a2 - a1) * (b2 + b1) / 2
+        out[:, i] = area / (xu - xl)
+    return out[0] if np.ndim(y) == 1 else out

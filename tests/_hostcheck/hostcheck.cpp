@@ -10,6 +10,7 @@
 
 #include "../../crt1d_b200/csrc/crt_leafangle.cuh"
 #include "../../crt1d_b200/csrc/crt_scheme.cuh"
+#include "../../crt1d_b200/csrc/crt_spectra.cuh"
 
 namespace {
 
@@ -123,4 +124,10 @@ __attribute__((visibility("default"))) double hostcheck_leaf_integral(int family
 
 extern "C" __attribute__((visibility("default"))) void hostcheck_exp_pm(int n, const double* x, double* em, double* ep) {
     for (int i = 0; i < n; ++i) crt::exp_pm(x[i], em[i], ep[i]);
+}
+
+extern "C" __attribute__((visibility("default"))) void hostcheck_smear_tuv(int n_rows, int n_x, const double* x, const double* y,
+                                                                           int n_bins, const double* bins, double* out) {
+    for (int r = 0; r < n_rows; ++r)
+        for (int i = 0; i < n_bins; ++i) out[(int64_t)r * n_bins + i] = crt::smear_tuv_bin(x, y + (int64_t)r * n_x, n_x, bins[i], bins[i + 1]);
 }

@@ -18,7 +18,7 @@ _lib = None
 
 
 def build(force=False):
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("crt_core.cuh", "crt_scheme.cuh", "crt_leafangle.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("crt_core.cuh", "crt_scheme.cuh", "crt_leafangle.cuh", "crt_spectra.cuh")]
     deps.append(os.path.join(HERE, "..", "include", "crt1d_b200.h"))
     if force or not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden",
@@ -38,6 +38,8 @@ def lib():
         L.hostcheck_tau_d.argtypes = [C.c_int, C.c_double, C.c_int, C.c_int, C.c_double]
         L.hostcheck_leaf_integral.restype = C.c_double
         L.hostcheck_leaf_integral.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
+        L.hostcheck_smear_tuv.restype = None
+        L.hostcheck_smear_tuv.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -88,4 +90,14 @@ def solve(batch, scheme, prologue, *, vec=None, band_w=None, mu_s=0.501):
         vec = 2 if nw % 2 == 0 else 1
     rc = lib().hostcheck_solve(_abi.SCHEME_IDS[scheme], C.byref(cb), C.byref(co), vec)
     assert rc == 0
+    return out
+
+
+def smear_tuv(x, y, bins):
+    """The device function `smear_tuv_bin` compiled for the host, over all (row, bin) pairs."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y2 = np.ascontiguousarray(np.atleast_2d(np.asarray(y, dtype=np.float64)))
+    bins = np.ascontiguousarray(bins, dtype=np.float64)
+    out = np.empty((y2.shape[0], bins.size - 1))
+    lib().hostcheck_smear_tuv(y2.shape[0], x.size, _ptr(x), _ptr(y2), bins.size - 1, _ptr(bins), _ptr(out))
     return out

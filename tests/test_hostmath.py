@@ -207,3 +207,14 @@ def test_4s_irregular_levels_and_huge_lai(default_p):
     a = _solve(dict(sub, lai=np.linspace(1, 0, 50) * 300.0), "4s")   # lam0 * LAI < 600 for these bands? checked below
     b = _solve(dict(sub, lai=np.linspace(1, 0, 50) * 300.0 * (1 + 1e-12)), "4s")
     assert_close(a["I_df_d"][-5:], b["I_df_d"][-5:], 1e-8, "continuity in LAI")
+
+
+def test_smear_tuv_device_function_matches_reference():
+    """`smear_tuv_bin` (bisection start + the reference's trapezoid loop) compiled for the host vs the
+    reference-generated vectors; without FMA contraction it is bit-identical."""
+    g = golden("ref_smear_tuv.npz")
+    for x, y, bins, res in (("a_x", "a_y", "a_bins10", "a_bins10_res"), ("a_x", "a_y", "a_bins37", "a_bins37_res"),
+                            ("a_x", "a_y", "a_bins_off", "a_bins_off_res"), ("b_x", "b_y", "b_bins", "b_res"),
+                            ("c_x", "c_y", "c_bins", "c_res")):
+        got = hostcheck.smear_tuv(g[x], g[y], g[bins])
+        assert np.array_equal(got, g[res]), bins
