@@ -50,6 +50,8 @@ def parse():
                          "reduced-precision path of BASELINE.json, NOT the headline configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-sample", type=int, default=256,
+                    help="scenarios in the host-profile e2e leg (crt1d_solve_host, profiles copied back to host); 0 = skip")
     return ap.parse_args()
 
 
@@ -328,6 +330,43 @@ def main():
             "ms_per_step": dt * 1e3,
         }
 
+    # ---------------- the reference-facing call with full profiles returned to the HOST (what one reference
+    # solver call returns, batched): crt1d_solve_host = H2D + kernel + D2H of every profile inside one C call.
+    # 4 TB per sweep cannot cross PCIe, so this leg runs a bounded sample of the same sweep and is PCIe-bound.
+    e2e_host = None
+    if not args.no_e2e and rank == 0 and args.host_sample > 0 and args.profile_dtype == "f64":
+        from crt1d_b200 import engine
+        from crt1d_b200.solvers._plugin import solve_batch_host
+
+        n_host = min(args.host_sample, S)
+        lo = max(0, min(S // 2, S - n_host))
+        sub = spec.slice(lo, lo + n_host)
+        pro = engine.host_prologue(sub, args.scheme)
+        n_fields = 4 + len(engine.EXTRA_NAMES.get(args.scheme, ()))
+        pool = torch.empty((n_fields, n_host, spec.n_z, spec.n_wl), dtype=torch.float64).pin_memory()
+        pool_np, taken = pool.numpy(), [0]
+
+        def pinned_alloc(shape):  # page-locked output arrays, reused by every call
+            a = pool_np[taken[0] % n_fields].reshape(-1)[:int(np.prod(shape))].reshape(shape)
+            taken[0] += 1
+            return a
+
+        legs = {}
+        for name, alloc in (("pageable", np.empty), ("pinned", pinned_alloc)):
+            solve_batch_host(sub, args.scheme, pro, device=local_rank, alloc=alloc)  # warm-up (workspace allocation)
+            t0 = time.perf_counter()
+            res = solve_batch_host(sub, args.scheme, pro, device=local_rank, alloc=alloc)
+            dt_h = time.perf_counter() - t0
+            d2h = int(sum(v.nbytes for v in res.values()))
+            legs[name] = {"value": n_host * spec.n_z * spec.n_wl / dt_h, "ms": dt_h * 1e3, "d2h_gb_per_s": d2h / dt_h / 1e9}
+        e2e_host = {
+            "value": legs["pinned"]["value"], "unit": UNIT, "scenarios": n_host, "d2h_bytes": d2h,
+            "pinned_output_arrays": legs["pinned"], "fresh_pageable_output_arrays": legs["pageable"],
+            "api": "crt1d_solve_host (C ABI, host pointers in and out): every profile of every scenario returned to "
+                   "host memory; bound by the D2H copy (PCIe with page-locked outputs; page faults of fresh numpy "
+                   "arrays, as the reference-style plugin call allocates them, otherwise)",
+        }
+
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline(args.scheme, args.cpu_sample, n_z=args.nz)
@@ -346,7 +385,7 @@ def main():
                     runner.chunk * spec.n_z * spec.n_wl * bpu / 1e9),
                 "parallelism": f"scenario-sharded x{world}, no data-path collective; NCCL all-gather of absorbed[S,2]",
             },
-            "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "e2e_host_profiles": e2e_host, "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:

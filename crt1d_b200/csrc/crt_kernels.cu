@@ -407,8 +407,12 @@ __device__ __forceinline__ void rows_wait(int* ready, int chunk, int lane) {
     __threadfence_block();
 }
 
-template <int VEC, int LV, int MAXT, bool REC, bool F32>
-__global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batch in, const crt1d_out out) {
+// DIAG = reduced-diagnostic instantiation (no profile requested): only the first item of every chunk exists, the
+// coefficients are never stored (shared memory = level tables only) and chunks are dealt round-robin.  Small CTAs,
+// several per SM: a CTA's serial parts (tables, barriers, final chunk sum) overlap the other CTAs' arithmetic --
+// as one 512-thread CTA per SM this mode was latency-bound at ~13 us per scenario.
+template <int VEC, int LV, int MAXT, bool REC, bool F32, int MINB = 1, bool DIAG = false>
+__global__ void __launch_bounds__(MAXT, MINB) solve_2s_rows_kernel(const crt1d_batch in, const crt1d_out out) {
     extern __shared__ double sm[];
     __shared__ double partial[ROWS_MAX_CHUNKS][4];  // per-chunk sums of the absorbed reduction (fixed final order)
     __shared__ int ready[ROWS_MAX_CHUNKS];
@@ -429,7 +433,7 @@ __global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batc
     for (int q = threadIdx.x; q < n_chunks; q += T) ready[q] = 0;
     if (threadIdx.x == 0) counter = 0;
     __syncthreads();
-    if (REC) {
+    if (REC && !DIAG) {
         const double tol = 8.0 * 2.220446049250313e-16 * L[0];
         for (int g = threadIdx.x; g < (n_z + LV - 1) / LV && g < 1024; g += T) {
             const int a = g * LV, b = min(n_z, a + LV);
@@ -448,17 +452,23 @@ __global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batc
     void* pF = prof_base(out.F, F32, s * prof);
     // Reduced-diagnostic mode: with no profile requested only the first item of every chunk runs (coefficients +
     // ground/top levels for the absorbed reduction); there is nothing to sweep.
-    const bool any_profile = pI || pD || pU || pF;
+    const bool any_profile = !DIAG && (pI || pD || pU || pF);
     const bool all_profiles = pI && pD && pU && pF;
     const int n_lg = any_profile ? (n_z + LV - 1) / LV : 1;
     const int n_items = n_chunks * n_lg;
     const int lane = threadIdx.x & 31;
 
     // ---- row-major work items
+    int item_rr = threadIdx.x >> 5;
     for (;;) {
         int item = 0;
-        if (lane == 0) item = atomicAdd(&counter, 1);
-        item = __shfl_sync(0xffffffffu, item, 0);
+        if constexpr (DIAG) {
+            item = item_rr;
+            item_rr += T >> 5;
+        } else {
+            if (lane == 0) item = atomicAdd(&counter, 1);
+            item = __shfl_sync(0xffffffffu, item, 0);
+        }
         if (item >= n_items) break;
         const int lg = item / n_chunks, chunk = item - lg * n_chunks;
         const int g = chunk * 32 + lane;
@@ -472,6 +482,7 @@ __global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batc
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
                     k[v] = coef_2s(sc, b.leaf_r[v], b.leaf_t[v], b.soil_r[v], b.Idr0[v], b.Idf0[v]);
+                    if constexpr (DIAG) continue;
                     cf[0 * ld + c0 + v] = k[v].h;
                     cf[1 * ld + c0 + v] = k[v].Au;
                     cf[2 * ld + c0 + v] = k[v].Bu;
@@ -505,6 +516,7 @@ __global__ void __launch_bounds__(MAXT, 1) solve_2s_rows_kernel(const crt1d_batc
                     if (lane == 0) partial[chunk][q] = v;
                 }
             }
+            if constexpr (DIAG) continue;
             rows_publish(ready, chunk, lane);
         } else {
             rows_wait(ready, chunk, lane);
@@ -614,8 +626,36 @@ static size_t rows_2s_shared_bytes(int n_z, int n_wl) {
     return (size_t)(2 * n_z + ((2 * n_z) & 1) + 8 * ld) * sizeof(double);
 }
 
+// Reduced-diagnostic kernels: __launch_bounds__(256, MINB) and threads per CTA, from the measured sweep
+// (profiles/r01_reduced_diagnostic_mode.json; ms per 10^6 scenarios x 2100 bands, (MINB, threads)):
+//   2s  (2,256) 58  (2,128) 51  (2,64) 49  (3,128) 45  (4,128) 44.7      bl  52 / 41 / 35 / 31 / 25.5
+//   bf  65 / 52 / 45 / 38 / 33                                           g77 70 / 57 / 50 / 44 / 41
+//   4s  114 / 102 / 100 / 104 / 107  -> 4s keeps 128 registers (its eigen-system spills badly below that)
+#ifndef CRT_DIAG_MINB
+#define CRT_DIAG_MINB 4
+#endif
+#ifndef CRT_DIAG_MINB_4S
+#define CRT_DIAG_MINB_4S 2
+#endif
+static bool no_profile_requested(const crt1d_out& out) {
+    return !out.I_dr && !out.I_df_d && !out.I_df_u && !out.F && !out.x0 && !out.x1 && !out.x2;
+}
+static int diag_threads(int dflt) {  // CRT1D_B200_DIAG_THREADS: tuning override (multiple of 32, <= 256)
+    const char* env = getenv("CRT1D_B200_DIAG_THREADS");
+    const int t = env ? atoi(env) : dflt;
+    return (t >= 32 && t <= 256 && t % 32 == 0) ? t : dflt;
+}
+
 template <int VEC, int LV, int MAXT, bool REC, bool F32 = false>
 static cudaError_t launch_rows_2s_t(const crt1d_batch& in, const crt1d_out& out, int threads, cudaStream_t stream) {
+    if (no_profile_requested(out)) {
+        const size_t smem = (size_t)(2 * in.n_z + 2) * sizeof(double);
+        auto kd = solve_2s_rows_kernel<VEC, 10, 256, false, false, CRT_DIAG_MINB, true>;  // LV, REC, F32 play no part
+        cudaError_t ed = cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ed != cudaSuccess) return ed;
+        kd<<<(unsigned)in.n_scen, diag_threads(128), smem, stream>>>(in, out);
+        return cudaGetLastError();
+    }
     const size_t smem = rows_2s_shared_bytes(in.n_z, in.n_wl);
     auto kern = solve_2s_rows_kernel<VEC, LV, MAXT, REC, F32>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -741,7 +781,7 @@ struct RowsTraits<CRT1D_SCHEME_4S> {
     }
 };
 
-template <int SCHEME, int VEC, int LV, int MAXT, bool F32, bool FUSED, int MINB>
+template <int SCHEME, int VEC, int LV, int MAXT, bool F32, bool FUSED, int MINB, bool DIAG = false>
 __global__ void __launch_bounds__(MAXT, MINB) solve_rows_kernel(const crt1d_batch in, const crt1d_out out, int split) {
     using TR = RowsTraits<SCHEME>;
     constexpr int NC = TR::NC, NF = TR::NF;
@@ -761,7 +801,7 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_rows_kernel(const crt1d_batc
     const int chunk_lo = part * chunks_per_part;
     const int n_chunks = max(0, min(chunks_all, chunk_lo + chunks_per_part) - chunk_lo);  // this CTA's chunks
     const int col_lo = chunk_lo * 32 * VEC;
-    const int ld = min((n_wl + 1) & ~1, chunks_per_part * 32 * VEC);
+    const int ld = DIAG ? 0 : min((n_wl + 1) & ~1, chunks_per_part * 32 * VEC);  // DIAG: no coefficient array
     double* cf = sm + n_tab + (n_tab & 1) - col_lo;  // [NC][ld] indexed by GLOBAL column, 16-byte aligned
     double (*partial)[4] = reinterpret_cast<double (*)[4]>(sm + n_tab + (n_tab & 1) + (size_t)NC * ld);
     int* ready = reinterpret_cast<int*>(partial + chunks_per_part);
@@ -771,7 +811,7 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_rows_kernel(const crt1d_batc
     for (int q = threadIdx.x; q < n_chunks; q += T) ready[q] = 0;
     if (threadIdx.x == 0) counter = 0;
     __syncthreads();
-    if constexpr (SCHEME == CRT1D_SCHEME_4S) {
+    if constexpr (SCHEME == CRT1D_SCHEME_4S && !DIAG) {
         const double tol = 8.0 * 2.220446049250313e-16 * sm[0];
         for (int g = threadIdx.x; g < (n_z + LV - 1) / LV; g += T) {
             const int a = g * LV, b = min(n_z, a + LV);
@@ -790,7 +830,7 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_rows_kernel(const crt1d_batc
 #pragma unroll
     for (int q = 0; q < 7; ++q) {
         pf[q] = prof_base(praw[q], F32, s * prof);
-        any_profile = any_profile || (q < NF && pf[q] != nullptr);
+        any_profile = any_profile || (!DIAG && q < NF && pf[q] != nullptr);
     }
     const double* idr0 = in.I_dr0_lib + (int64_t)in.sky_idx[s] * n_wl;
     const int n_lg = any_profile ? (n_z + LV - 1) / LV : 1;
@@ -817,8 +857,10 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_rows_kernel(const crt1d_batc
                 k[v] = TR::coef(sc, b1);
                 double a[NC];
                 TR::pack(k[v], a);
+                if constexpr (!DIAG) {  // reduced-diagnostic instantiation: coefficients are never stored
 #pragma unroll
-                for (int i = 0; i < NC; ++i) cf[i * ld + c0 + v] = a[i];
+                    for (int i = 0; i < NC; ++i) cf[i * ld + c0 + v] = a[i];
+                }
                 if (SCHEME == CRT1D_SCHEME_BF && out.rho_c) out.rho_c[s * n_wl + c0 + v] = TR::rho_c(k[v]);
                 if (out.absorbed) {
                     double gnd[NF], top[NF];
@@ -840,15 +882,15 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_rows_kernel(const crt1d_batc
         }
     };
 
-    if constexpr (!FUSED) {  // separate coefficient phase: warps take chunks round-robin, then everyone sweeps
+    if constexpr (!FUSED || DIAG) {  // separate coefficient phase: warps take chunks round-robin, then everyone sweeps
         typename TR::Coef kk[VEC];
         for (int chunk = threadIdx.x >> 5; chunk < n_chunks; chunk += T >> 5) produce(chunk, kk);
-        __syncthreads();
+        if constexpr (!DIAG) __syncthreads();
     }
 
     // ---- row-major work items (LV levels x 32*VEC bands); FUSED: a chunk's first item produces its coefficients
     const int first_item = (FUSED || any_profile) ? 0 : n_items;  // !FUSED + no profiles: nothing left to do
-    for (;;) {
+    for (; !DIAG;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(&counter, 1) + first_item;
         item = __shfl_sync(0xffffffffu, item, 0);
@@ -961,6 +1003,17 @@ static cudaError_t launch_rows_t(const crt1d_batch& in, const crt1d_out& out, in
     // 4s: its coefficient stage (eigen-system + 4x4 solve, 168 registers) is better kept as a separate phase
     // (0.82 vs 0.77 of HBM peak when fused into the first item); bl/bf/g77 fuse it (no store-free phase).
     constexpr bool FUSED = SCHEME != CRT1D_SCHEME_4S;
+    if (no_profile_requested(out)) {  // reduced-diagnostic mode: small CTAs, several per SM, level tables only
+        const int n_tab = n_level_tables(SCHEME) * in.n_z;
+        const int chunks = (in.n_wl / VEC + 31) / 32;
+        const size_t smem_d = (size_t)(n_tab + (n_tab & 1)) * sizeof(double) + (size_t)chunks * (4 * sizeof(double) + sizeof(int));
+        constexpr int DM = SCHEME == CRT1D_SCHEME_4S ? CRT_DIAG_MINB_4S : CRT_DIAG_MINB;
+        auto kd = solve_rows_kernel<SCHEME, VEC, 10, 256, false, FUSED, DM, true>;  // LV, F32 play no part
+        cudaError_t e = cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
+        if (e != cudaSuccess) return e;
+        kd<<<(unsigned)in.n_scen, diag_threads(SCHEME == CRT1D_SCHEME_4S ? 64 : 128), smem_d, stream>>>(in, out, 1);
+        return cudaGetLastError();
+    }
     if constexpr (SCHEME == CRT1D_SCHEME_4S) {
         // Two CTAs per SM, each on half of the scenario's band chunks (half the coefficient array: 2 x ~106 KB):
         // one CTA's store-free coefficient phase (~20 % of its life) overlaps the other's level sweeps.

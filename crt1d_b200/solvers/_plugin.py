@@ -25,9 +25,10 @@ def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def solve_batch_host(batch, scheme, prologue, *, mu_s=0.501, band_w=None, device=None):
+def solve_batch_host(batch, scheme, prologue, *, mu_s=0.501, band_w=None, device=None, alloc=np.empty):
     """`crt1d_solve_host` on a ScenarioBatch with a host prologue dict; returns numpy arrays with a
-    leading scenario axis."""
+    leading scenario axis.  `alloc(shape)` makes the float64 output arrays (default: fresh pageable numpy
+    arrays like the reference's; a page-locked allocator lets the D2H copies run at PCIe speed)."""
     lib = _lib.load()
     S, nz, nw = batch.n_scen, batch.n_z, batch.n_wl
     keep = {}
@@ -45,10 +46,10 @@ def solve_batch_host(batch, scheme, prologue, *, mu_s=0.501, band_w=None, device
     cb.mla_deg = float(batch.mla)
     cb.mu_s = float(mu_s)
 
-    out = {k: np.empty((S, nz, nw)) for k in ("I_dr", "I_df_d", "I_df_u", "F")}
+    out = {k: alloc((S, nz, nw)) for k in ("I_dr", "I_df_d", "I_df_u", "F")}
     rows = nz - 1 if scheme == "n79" else nz
     for k in EXTRA_NAMES.get(scheme, ()):
-        out[k] = np.empty((S, rows, nw))
+        out[k] = alloc((S, rows, nw))
     if scheme == "bf":
         out["rho_c"] = np.empty((S, nw))
     co = _abi.Out()

@@ -569,8 +569,10 @@ def test_energy_balance_kernel(default_p):
 @pytest.mark.parametrize("scheme", ["2s", "4s", "bl", "bf", "g77", "zq"])
 def test_reduced_diagnostic_mode(scheme):
     """Profiles are optional outputs for the closed-form schemes (NULL pointers in crt1d_out): the fused
-    canopy-absorbed reduction must come out bit-identical with or without them (row-sweep kernels skip the
-    level sweep entirely in that mode).  zq/n79 use the profiles as scratch and must refuse loudly."""
+    canopy-absorbed reduction must come out the same with or without them (the row-sweep kernels have a
+    reduced-diagnostic instantiation that never stores coefficients or sweeps levels: same arithmetic, same
+    summation order, but a separate compilation, so FMA contraction may differ in the last bits -- bar 1e-13,
+    three orders below the parity bar).  zq/n79 use the profiles as scratch and must refuse loudly."""
     import torch
 
     from crt1d_b200 import _lib
@@ -590,7 +592,8 @@ def test_reduced_diagnostic_mode(scheme):
     engine.solve_into(db, ob)
     full = engine.solve(db, scheme, band_w=bw)
     torch.cuda.synchronize()
-    assert torch.equal(ob.t["absorbed"], full["absorbed"])
+    a, b = ob.t["absorbed"].cpu().numpy(), full["absorbed"].cpu().numpy()
+    assert_close(a, b, 1e-13, f"{scheme} reduced-diagnostic absorbed")
 
 
 @pytest.mark.parametrize("scheme", ["2s", "4s", "bl", "bf", "g77", "zq_pa"])

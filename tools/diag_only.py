@@ -32,9 +32,9 @@ def main(schemes):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
-        same = bool(torch.equal(r.absorbed[:66304], ref))
+        same = float(((r.absorbed[:66304] - ref).abs() / ref.abs().clamp_min(1e-300)).max())
         rows.append(dict(scheme=scheme, ms_per_1e6_scenarios=ms, scenarios_per_s=spec.n_scen / ms * 1e3,
-                         band_columns_per_s=spec.n_scen * spec.n_wl / ms * 1e3, identical_to_full_profile_run=same))
+                         band_columns_per_s=spec.n_scen * spec.n_wl / ms * 1e3, max_rel_diff_vs_full_profile_run=same))
         print(rows[-1])
     json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "diag_only.json"), "w"), indent=1)
 
