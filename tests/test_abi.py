@@ -124,3 +124,17 @@ def test_product_never_imports_the_oracle():
                 assert not pat.search(text), f"{f} reaches into test infrastructure"
                 assert "sys.path" not in text or f == "build.py", f"{f} manipulates sys.path"
     assert n > 20
+
+
+def test_graft_entry_build_runs():
+    """The driver's build check: `__graft_entry__.build()` compiles (or finds up to date) the CUDA library and the
+    host math checker, loads the library and checks its ABI version against the Python layer's."""
+    import importlib
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    ge = importlib.import_module("__graft_entry__")
+    ge.build()

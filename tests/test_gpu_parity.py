@@ -594,6 +594,26 @@ def test_reduced_diagnostic_mode(scheme):
     torch.cuda.synchronize()
     a, b = ob.t["absorbed"].cpu().numpy(), full["absorbed"].cpu().numpy()
     assert_close(a, b, 1e-13, f"{scheme} reduced-diagnostic absorbed")
+    # odd band count (VEC = 1 instantiation), irregular level spacing, one band group; vs the full run and the oracle
+    import copy
+
+    odd = copy.copy(sub.slice(0, 150))
+    for k in ("leaf_r_lib", "leaf_t_lib", "soil_r_lib", "I_dr0_lib", "I_df0_lib"):
+        setattr(odd, k, np.ascontiguousarray(getattr(sub, k)[:, 100:433]))
+    odd.wl, odd.dwl = sub.wl[100:433], sub.dwl[100:433]
+    odd.lai_lib = np.ascontiguousarray(sub.lai_lib * np.linspace(1.0, 0.6, sub.n_z) ** 0.5)
+    bw1 = np.linspace(0.5, 1.5, 333)[None]
+    db = engine.DeviceBatch(odd, scheme)
+    ob = engine.OutputBuffers(scheme, odd.n_scen, odd.n_z, odd.n_wl, device=db.device, fields=(), extras=False, band_w=bw1)
+    engine.solve_into(db, ob)
+    full = engine.solve(db, scheme, band_w=bw1)
+    torch.cuda.synchronize()
+    a, b = ob.t["absorbed"].cpu().numpy(), full["absorbed"].cpu().numpy()
+    assert_close(a, b, 1e-13, f"{scheme} reduced-diagnostic absorbed, odd n_wl")
+    if scheme != "4s":  # canopy-absorbed = (I_dr + I_df_d - I_df_u) at the top minus at the ground, band-weighted
+        ref = oracle.run(scheme, odd.scenario_params(77))
+        net = ref["I_dr"] + ref["I_df_d"] - ref["I_df_u"]
+        assert_close(a[77], [np.sum(bw1[0] * (net[-1] - net[0]))], 1e-10, f"{scheme} reduced-diagnostic vs oracle")
 
 
 @pytest.mark.parametrize("scheme", ["2s", "4s", "bl", "bf", "g77", "zq_pa"])
