@@ -159,15 +159,21 @@ struct Coef2s {
     double h, Au, Bu, Cu, Ad, Bd, Cd, Idr0;
 };
 
+// RCP: reciprocals by rcp_nr instead of IEEE divisions.  Measured A/B on one box: the reduced-diagnostic kernel gains
+// 10 % (44.2 -> 40.0 ms per 10^6 scenarios), the full row-sweep kernel LOSES 1 % (0.961 -> 0.951 of HBM peak: the
+// first-touch item shares 128 registers with the level sweep), so only the reduced-diagnostic instantiation uses it.
+template <bool RCP = false>
 CRT_HD Coef2s coef_2s(const Scen2s& s, double alpha, double tau, double rho_s, double Idr0, double Idf0) {
+    auto rcp_coef = [](double x) { return RCP ? rcp_nr(x) : 1.0 / x; };
     // The reference divides by S1, D1, D2, sigma in a dozen places (ref :96-120); here each reciprocal is
-    // formed once (1/S1 = e^{+h L_T} falls out of exp_pm) -- same algebra, results within a few ulp.
+    // formed once (1/S1 = e^{+h L_T} falls out of exp_pm; the others by division, or with RCP by rcp_nr: seed +
+    // two Newton steps instead of the ~20-slot IEEE division sequence) -- same algebra, results within a few ulp.
     const double mu_bar = s.mu_bar, K = s.K;
     const double omega = alpha + tau;                                                   // ref :65
-    const double beta = (0.5 * (alpha + tau + (alpha - tau) * s.cos2_tl)) / omega;      // ref :68 (eq. 3)
+    const double beta = (0.5 * (alpha + tau + (alpha - tau) * s.cos2_tl)) * rcp_coef(omega);  // ref :68 (eq. 3)
     const double a_s = omega / 2.0 * s.as_fac;                                          // ref :73
     const double mK = mu_bar * K;
-    const double beta_0 = (1.0 + mK) / (omega * mK) * a_s;                              // ref :76 (eq. 4)
+    const double beta_0 = (1.0 + mK) * rcp_coef(omega * mK) * a_s;                        // ref :76 (eq. 4)
     const double b = 1.0 - (1.0 - beta) * omega;                                        // ref :80-85
     const double c = omega * beta;
     const double d = omega * mK * beta_0;
@@ -182,9 +188,9 @@ CRT_HD Coef2s coef_2s(const Scen2s& s, double alpha, double tau, double rho_s, d
     const double S2 = s.S2;
     const double mh = mu_bar * h;
     const double p1 = b + mh, p2 = b - mh, p3 = b + mK, p4 = b - mK;
-    const double iD1 = 1.0 / (p1 * (u1 - mh) * iS1 - p2 * (u1 + mh) * S1);
-    const double iD2 = 1.0 / ((u2 + mh) * iS1 - (u2 - mh) * S1);
-    const double isig = 1.0 / sigma;
+    const double iD1 = rcp_coef(p1 * (u1 - mh) * iS1 - p2 * (u1 + mh) * S1);
+    const double iD2 = rcp_coef((u2 + mh) * iS1 - (u2 - mh) * S1);
+    const double isig = rcp_coef(sigma);
     const double h1s = (-d * p4 - c * f) * isig;                                        // h1 / sigma, ref :99
     const double t1 = d - h1s * p3;
     const double t2 = d - c - h1s * (u1 + mK);
@@ -1181,7 +1187,7 @@ CRT_HD void solve4(double (&A)[4][4], double (&b)[4]) {
             b[c] = sw ? b[r] : tb;
             b[r] = sw ? tb : b[r];
         }
-        inv[c] = 1.0 / A[c][c];
+        inv[c] = rcp_nr(A[c][c]);
 #pragma unroll
         for (int r = c + 1; r < 4; ++r) {
             const double f = A[r][c] * inv[c];
@@ -1232,7 +1238,7 @@ CRT_HD Coef4s coef_4s(const Scen4s& s, double r, double t, double rho, double Id
     const double det = N00 * N11 - N01 * N10;
     double l2[2];
     l2[0] = 0.5 * (tr + disc);
-    l2[1] = det / l2[0];
+    l2[1] = det * rcp_nr(l2[0]);
     double phi[2][2];
     if (dif >= 0.0) {
         phi[0][0] = l2[0] - N11; phi[0][1] = N10;
@@ -1245,19 +1251,19 @@ CRT_HD Coef4s coef_4s(const Scen4s& s, double r, double t, double rho, double Id
     double psi_[2][2], g[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        const double nrm = 1.0 / fmax(fabs(phi[i][0]), fabs(phi[i][1]));
+        const double nrm = rcp_nr(fmax(fabs(phi[i][0]), fabs(phi[i][1])));
         phi[i][0] *= nrm;
         phi[i][1] *= nrm;
         k.lam[i] = sqrt(l2[i]);
         psi_[i][0] = -k.lam[i] * phi[i][0] * s.inv_q0;   // (P-Q)^{-1} phi lambda
         psi_[i][1] = -k.lam[i] * phi[i][1] * s.inv_q1;
-        g[i] = exp(-k.lam[i] * s.L_T);
+        g[i] = exp_neg(k.lam[i] * s.L_T);
     }
     // particular solution of the direct problem: (kappa^2 I - N) s_p = 2 (P-Q) vD
     const double kap = s.kappa, k2 = kap * kap;
     const double B00 = k2 - N00, B01 = -N01, B10 = -N10, B11 = k2 - N11;
     const double r0 = -2.0 * q0 * vD0, r1 = -2.0 * q1 * vD1;
-    const double idB = 1.0 / (B00 * B11 - B01 * B10);
+    const double idB = rcp_nr(B00 * B11 - B01 * B10);
     const double sp0 = (r0 * B11 - B01 * r1) * idB, sp1 = (B00 * r1 - B10 * r0) * idB;
     const double wp0 = kap * sp0 * s.inv_q0, wp1 = kap * sp1 * s.inv_q1;  // (P-Q)^{-1} (-kappa s_p)
     const double Dp0 = 0.5 * (sp0 + wp0), Dp1 = 0.5 * (sp1 + wp1);

@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_2s_rows_kernel(const crt1d_b
                 const BandIn<VEC> b = load_bands<VEC>(in, s, c0);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
-                    k[v] = coef_2s(sc, b.leaf_r[v], b.leaf_t[v], b.soil_r[v], b.Idr0[v], b.Idf0[v]);
+                    k[v] = coef_2s<DIAG>(sc, b.leaf_r[v], b.leaf_t[v], b.soil_r[v], b.Idr0[v], b.Idf0[v]);
                     if constexpr (DIAG) continue;
                     cf[0 * ld + c0 + v] = k[v].h;
                     cf[1 * ld + c0 + v] = k[v].Au;
