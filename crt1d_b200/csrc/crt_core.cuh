@@ -478,7 +478,9 @@ CRT_HD void column_n79(const ScenN79& s, const double* tab, int n_z, const BandI
                        double (&absorbed)[VEC]) {
     const double *tbcum = tab, *g = tab + n_z, *td = tab + 2 * n_z, *omtd = tab + 3 * n_z, *fsun = tab + 4 * n_z,
                  *omfs = tab + 5 * n_z, *isl = tab + 6 * n_z, *ish = tab + 7 * n_z;
-    const int CK = out.seg_levels();
+    // Segment store: the back sweep keeps BOTH rows' pairs of a recomputed level (downward row in slots 0..CK-1,
+    // upward row in slots CK..2CK-1), so it never re-derives a layer or an upward row; half the levels per segment.
+    const int CK = out.seg_levels() / 2;
     using Lay = N79Layer<VEC>;
     auto layer = [&](int i, Lay& L) {
         const double t = td[i], o = omtd[i];
@@ -494,6 +496,11 @@ CRT_HD void column_n79(const ScenN79& s, const double* tab, int n_z, const BandI
             L.wd[v] = tau - rho * L.e[v];
         }
     };
+    // Equal layer thickness (every profile the reference's LAI generators make, ref ../leaf_area.py:82-88): tau_d is
+    // the same in every layer up to the rounding of lai[j] - lai[j+1], so the layer coefficients are formed once per
+    // column instead of once per level and sweep (|td[j] - td[0]| <= 8 eps td[0]; effect on the solution ~1e-15).
+    bool uni = true;
+    for (int i = 1; i < n_z - 1; ++i) uni = uni && fabs(td[i] - td[0]) <= 1.8e-15 * td[0];
     // Forward-sweep coefficients of the UPWARD row of level j >= 1 (a = -eiv, c = -fiv of the layer below, L) from
     // those of the downward row of level j-1 (e_in, f_in); unit diagonal (ref :101-108 / :122-129, tdma :186, :191).
     // Used identically in both sweeps, so the back-substitution recomputes the forward values.
@@ -517,8 +524,7 @@ CRT_HD void column_n79(const ScenN79& s, const double* tab, int n_z, const BandI
     };
     // One level of the forward recurrence: (e, f) holds the downward row's pair of level j-1 on entry and of level j
     // on exit; La holds layer j-1 on entry (j >= 1) and layer j on exit (the layer the next upward row needs).
-    auto step = [&](int j, Lay& La, double (&e)[VEC], double (&f)[VEC]) {
-        double eu[VEC], fu[VEC];
+    auto step = [&](int j, Lay& La, double (&e)[VEC], double (&f)[VEC], double (&eu)[VEC], double (&fu)[VEC]) {
         if (j == 0) {
             soil_row(eu, fu);
         } else {
@@ -533,14 +539,9 @@ CRT_HD void column_n79(const ScenN79& s, const double* tab, int n_z, const BandI
             return;
         }
         // downward row (a = -aiv, c = -biv; ref :85-92 / :111-118): the soil row uses layer 1 as shipped
-        Lay L1;
-        if (j == 0) {
-            layer(1, L1);
-            layer(0, La);
-        } else {
-            layer(j, La);
-        }
-        const Lay& Ld = (j == 0) ? L1 : La;
+        if (!uni) layer(j, La);  // (uni: La holds THE layer from the start of the sweep)
+        Lay Ld = La;
+        if (!uni && j == 0) layer(1, Ld);
         const double gj = (j == 0) ? g[0] : g[j + 1];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
@@ -559,8 +560,10 @@ CRT_HD void column_n79(const ScenN79& s, const double* tab, int n_z, const BandI
     const int g_last = (n_z - 1) / CK;  // segment g covers levels g CK .. min((g+1) CK, n_z) - 1
     {
         Lay La;
+        double eu[VEC], fu[VEC];
+        layer(0, La);
         for (int j = 0; j < g_last * CK; ++j) {  // the top segment is left to the back sweep's recomputation
-            step(j, La, e_prev, f_prev);
+            step(j, La, e_prev, f_prev, eu, fu);
             if ((j + 1) % CK == 0) {
                 out.st_tmp(F_F, j, e_prev);
                 out.st_tmp(F_DN, j, f_prev);
@@ -590,37 +593,27 @@ CRT_HD void column_n79(const ScenN79& s, const double* tab, int n_z, const BandI
             for (int v = 0; v < VEC; ++v) e0[v] = f0[v] = 0.0;
         }
         {
-            double e[VEC], f[VEC];
+            double e[VEC], f[VEC], eu[VEC], fu[VEC];
             Lay La;
-            if (base > 0) layer(base - 1, La);
+            layer((base > 0 && !uni) ? base - 1 : 0, La);
 #pragma unroll
             for (int v = 0; v < VEC; ++v) { e[v] = e0[v]; f[v] = f0[v]; }
             for (int i = 0; i < len; ++i) {
-                step(base + i, La, e, f);
+                step(base + i, La, e, f, eu, fu);
                 out.seg_st(i, 0, e);
                 out.seg_st(i, 1, f);
+                out.seg_st(CK + i, 0, eu);
+                out.seg_st(CK + i, 1, fu);
             }
         }
         for (int i = len - 1; i >= 0; --i) {
             const int j = base + i;
-            double ed[VEC], fd[VEC], edl[VEC], fdl[VEC], eu[VEC], fu[VEC];  // (e, f) of this level and the level below
+            double ed[VEC], fd[VEC], eu[VEC], fu[VEC];  // forward pairs of this level's downward and upward rows
             double Idr[VEC], dn[VEC], up[VEC], F[VEC];
             out.seg_ld(i, 0, ed);
             out.seg_ld(i, 1, fd);
-            if (i > 0) {
-                out.seg_ld(i - 1, 0, edl);
-                out.seg_ld(i - 1, 1, fdl);
-            } else {
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) { edl[v] = e0[v]; fdl[v] = f0[v]; }
-            }
-            if (j == 0) {
-                soil_row(eu, fu);
-            } else {
-                Lay Lb;
-                layer(j - 1, Lb);
-                up_row(j, Lb, edl, fdl, eu, fu);
-            }
+            out.seg_ld(CK + i, 0, eu);
+            out.seg_ld(CK + i, 1, fu);
             const double tbc = tbcum[j];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
