@@ -334,7 +334,7 @@ def main():
     # solver call returns, batched): crt1d_solve_host = H2D + kernel + D2H of every profile inside one C call.
     # 4 TB per sweep cannot cross PCIe, so this leg runs a bounded sample of the same sweep and is PCIe-bound.
     e2e_host = None
-    if not args.no_e2e and rank == 0 and args.host_sample > 0 and args.profile_dtype == "f64":
+    if not args.no_e2e and world == 1 and args.host_sample > 0 and args.profile_dtype == "f64":  # N = 1 only, like cpu_baseline
         from crt1d_b200 import engine
         from crt1d_b200.solvers._plugin import solve_batch_host
 
