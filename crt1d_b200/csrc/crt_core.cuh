@@ -372,16 +372,25 @@ CRT_HD CoefBf coef_g77(const ScenBf& s, double r_l, double t_l, double soil_r, d
 }
 
 // f = {I_dr, I_df_d, I_df_u, F, aI_lsl, aI_lsh, aI_l}; eb = exp(-k_b L) from the scenario level table
+// level_bfg_e: the level given its exponentials ed = exp(-k_d L), ep = exp(+k_d L), eg = exp(-kg L) (g77 only)
+template <bool G77>
+CRT_HD void level_bfg_e(const ScenBf& s, const CoefBf& k, double eb, double ed, double ep, double eg, double (&f)[7]);
+
 template <bool G77>
 CRT_HD void level_bfg(const ScenBf& s, const CoefBf& k, double L, double eb, double (&f)[7]) {
     double ed, ep;                                  // exp(-k_d L), exp(+k_d L)
     exp_pm(k.k_d * L, ed, ep);
+    level_bfg_e<G77>(s, k, eb, ed, ep, G77 ? exp_neg(k.kg * L) : 0.0, f);
+}
+
+template <bool G77>
+CRT_HD void level_bfg_e(const ScenBf& s, const CoefBf& k, double eb, double ed, double ep, double eg, double (&f)[7]) {
     const double e2 = k.ed0 * ep;                   // exp(-k_d (L_T - L))   (ref _solve_bf.py:114)
     const double I_df = k.adf * ed;                 // ref _solve_bf.py:86 / _solve_g77.py:73
     const double Idr = k.Idr0 * eb;                 // ref :90
     double I_sc_d, I_sc_u;
     if (G77) {
-        const double I_sc = k.a1 * exp_neg(k.kg * L) + k.a2 * eb;   // eq. 5 (ref _solve_g77.py:84-86)
+        const double I_sc = k.a1 * eg + k.a2 * eb;                  // eq. 5 (ref _solve_g77.py:84-86)
         I_sc_d = 0.5 * I_sc;                                        // ref :89-90
         I_sc_u = 0.5 * I_sc;
     } else {

@@ -811,7 +811,10 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_rows_kernel(const crt1d_batc
     for (int q = threadIdx.x; q < n_chunks; q += T) ready[q] = 0;
     if (threadIdx.x == 0) counter = 0;
     __syncthreads();
-    if constexpr (SCHEME == CRT1D_SCHEME_4S && !DIAG) {
+    // level recurrence for g77 (two exponentials per level): A/B on one box 0.863 -> 0.900 of HBM peak.  bf (one
+    // exponential per level) gained nothing (0.929 -> 0.931) and keeps the direct evaluation.
+    constexpr bool BFG = SCHEME == CRT1D_SCHEME_G77;
+    if constexpr ((SCHEME == CRT1D_SCHEME_4S || BFG) && !DIAG) {
         const double tol = 8.0 * 2.220446049250313e-16 * sm[0];
         for (int g = threadIdx.x; g < (n_z + LV - 1) / LV; g += T) {
             const int a = g * LV, b = min(n_z, a + LV);
@@ -945,12 +948,39 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_rows_kernel(const crt1d_batc
                 }
             }
         }
+        // g77 on an equally spaced group: exp(-+k_d L) and exp(-kg L) anchored at the group's first level
+        // and advanced by constant factors (levels run from the ground up: L decreases by dL per level)
+        bool bfg_rec = false;
+        if constexpr (BFG) {
+            if (lg < 1024 && grp_uniform[lg]) {
+                bfg_rec = true;
+                const double dL = sm[j0] - sm[j0 + 1];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    exp_pm(k[v].k_d * sm[j0], m0[v], p0[v]);    // ed, ep
+                    exp_pm(k[v].k_d * dL, qd0[v], qi0[v]);      // qd0 = e^{-k_d dL} multiplies ep; qi0 = e^{+k_d dL} multiplies ed
+                    if constexpr (SCHEME == CRT1D_SCHEME_G77) {
+                        m1[v] = exp_neg(k[v].kg * sm[j0]);
+                        exp_pm(k[v].kg * dL, qd1[v], qi1[v]);   // qi1 = e^{+kg dL} multiplies eg
+                    }
+                }
+            }
+        }
         for (int j = j0; j < j1; ++j) {
             double o[NF][VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 double f[NF];
-                if constexpr (SCHEME == CRT1D_SCHEME_4S) {
+                if constexpr (BFG) {
+                    if (bfg_rec) {
+                        level_bfg_e<SCHEME == CRT1D_SCHEME_G77>(sc, k[v], sm[n_z + j], m0[v], p0[v], m1[v], f);
+                        m0[v] *= qi0[v];
+                        p0[v] *= qd0[v];
+                        if constexpr (SCHEME == CRT1D_SCHEME_G77) m1[v] *= qi1[v];
+                    } else {
+                        TR::level(sc, k[v], sm, n_z, j, f);
+                    }
+                } else if constexpr (SCHEME == CRT1D_SCHEME_4S) {
                     if (rec[v]) {
                         level_4s_e(sc, k[v], sm[n_z + j], m0[v], p0[v], m1[v], p1[v], f[0], f[1], f[2], f[3]);
                         m0[v] *= qi0[v];
