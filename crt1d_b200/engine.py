@@ -28,10 +28,29 @@ BATCH_ARRAYS = ("psi", "lai_lib", "leaf_r_lib", "leaf_t_lib", "soil_r_lib", "I_d
                 "lai_idx", "leaf_idx", "soil_idx", "sky_idx")
 
 
+_INDEX_OF = {"lai_idx": "lai_lib", "leaf_idx": "leaf_r_lib", "soil_idx": "soil_r_lib", "sky_idx": "I_dr0_lib"}
+
+
+def _abi_array(batch, k):
+    """Array `k` of a batch in the dtype / layout the C ABI reads (float64, int32 row indices; C order), with the
+    index ranges re-checked: attributes assigned after construction bypass `ScenarioBatch.__post_init__`, and an
+    int64 or out-of-range index array would be read as garbage rows by the kernels."""
+    a = getattr(batch, k)
+    if k in _INDEX_OF:
+        v = np.ascontiguousarray(a, dtype=np.int32)
+        if v.shape != (batch.n_scen,):
+            raise ValueError(f"{k} must have one entry per scenario ({batch.n_scen}), got shape {v.shape}")
+        rows = getattr(batch, _INDEX_OF[k]).shape[0]
+        if v.size and (v.min() < 0 or v.max() >= rows):
+            raise IndexError(f"{k} out of range for a library of {rows} rows")
+        return v
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
 def pin_batch(batch):
     """Page-locked host copies of a batch's arrays (made once; H2D from them is asynchronous DMA)."""
     torch = _torch()
-    return {k: torch.as_tensor(np.ascontiguousarray(getattr(batch, k))).pin_memory() for k in BATCH_ARRAYS}
+    return {k: torch.as_tensor(_abi_array(batch, k)).pin_memory() for k in BATCH_ARRAYS}
 
 
 def _torch():
@@ -101,7 +120,7 @@ class DeviceBatch:
                 if pinned is not None:  # page-locked staging copies made once by the caller (pin_batch)
                     self._t[k] = pinned[k].to(self.device, non_blocking=True)
                 else:
-                    self._t[k] = put(getattr(batch, k))
+                    self._t[k] = put(_abi_array(batch, k))
             if isinstance(prologue, dict):
                 for k, v in prologue.items():
                     self._t[k] = put(np.asarray(v, dtype=np.float64))

@@ -13,6 +13,7 @@ import numpy as np
 from .. import _abi
 from .. import _lib
 from ..engine import EXTRA_NAMES
+from ..engine import _abi_array
 from ..engine import host_prologue
 from ..scenarios import ScenarioBatch
 
@@ -38,7 +39,7 @@ def solve_batch_host(batch, scheme, prologue, *, mu_s=0.501, band_w=None, device
     cb.n_soil, cb.n_sky = batch.soil_r_lib.shape[0], batch.I_dr0_lib.shape[0]
     for k in ("psi", "lai_lib", "leaf_r_lib", "leaf_t_lib", "soil_r_lib", "I_dr0_lib", "I_df0_lib",
               "lai_idx", "leaf_idx", "soil_idx", "sky_idx"):
-        keep[k] = np.ascontiguousarray(getattr(batch, k))
+        keep[k] = _abi_array(batch, k)
         setattr(cb, k, _ptr(keep[k]))
     for k, v in prologue.items():
         keep[k] = np.ascontiguousarray(np.asarray(v, dtype=np.float64))

@@ -357,6 +357,77 @@ def test_errors_are_loud():
                              leaf_t=p["leaf_t"], leaf_r=p["leaf_r"], K_b_fn=K_b_fn)
 
 
+@pytest.mark.parametrize("nz,uniform", [(23, False), (40, True)])
+def test_random_scenarios_all_schemes(nz, uniform):
+    """Seeded random scenarios (zenith angles up to 87 deg, random leaf / soil / sky spectra, random monotone or
+    equally spaced LAI profiles, an odd band count) through the device-pointer batch path with the HOST prologue
+    (the oracle's own scalars), every scheme, every returned array vs the oracle."""
+    import torch
+
+    from crt1d_b200 import engine
+    from crt1d_b200.leaf_angle import LeafAngle
+    from crt1d_b200.scenarios import ScenarioBatch
+    from crt1d_b200.solvers import common
+    from util import assert_close_conditioned
+    from util import sigma_rel_2s
+
+    rng = np.random.default_rng(20261018 + nz)
+    S, nw = 6, 41
+    if uniform:
+        lai_lib = np.linspace(1, 0, nz)[None] * rng.uniform(0.3, 7.0, (3, 1))
+    else:
+        steps = rng.uniform(0.2, 1.8, (3, nz - 1))
+        prof = np.concatenate([np.cumsum(steps[:, ::-1], axis=1)[:, ::-1], np.zeros((3, 1))], axis=1)
+        lai_lib = prof / prof[:, :1] * rng.uniform(0.3, 7.0, (3, 1))
+    r = rng.uniform(0.02, 0.5, (4, nw))
+    t = rng.uniform(0.02, 0.45, (4, nw)) * (1 - r)
+    b = ScenarioBatch(
+        psi=np.radians(rng.uniform(0.0, 87.0, S)), lai_lib=lai_lib, leaf_r_lib=r, leaf_t_lib=t,
+        soil_r_lib=rng.uniform(0.03, 0.45, (2, nw)), I_dr0_lib=rng.uniform(0.0, 8.0, (2, nw)),
+        I_df0_lib=rng.uniform(0.1, 4.0, (2, nw)), lai_idx=rng.integers(0, 3, S), leaf_idx=rng.integers(0, 4, S),
+        soil_idx=rng.integers(0, 2, S), sky_idx=rng.integers(0, 2, S), leaf_angle=LeafAngle(), mla=57.0,
+    )
+    srel = sigma_rel_2s(b, common.mu_bar_fn(b.leaf_angle.G_fn))
+    for scheme in FAST:
+        kw = {"tau_d_method": "9sky"} if scheme == "n79" else {}
+        pro = engine.host_prologue(b, scheme, **kw)
+        res = engine.solve(engine.DeviceBatch(b, scheme, prologue=pro), scheme)
+        torch.cuda.synchronize()
+        for i in range(S):
+            ref = oracle.run(scheme, b.scenario_params(i), **kw)
+            for k in ref:
+                if k == "rho_c":
+                    continue
+                got = res[k][i].cpu().numpy()
+                if scheme == "2s" and k != "I_dr":
+                    assert_close_conditioned(got[None], ref[k][None], RTOL, srel[i:i + 1], f"random 2s[{i}].{k}")
+                else:
+                    assert_close(got, ref[k], RTOL, f"random nz={nz} {scheme}[{i}].{k}", atol=1e-300)
+    # the same libraries as a 160-scenario batch: the row-sweep kernels (level recurrences on the equally spaced
+    # profile, plain evaluation on the irregular one), odd band count -> VEC = 1
+    big = ScenarioBatch(
+        psi=np.radians(rng.uniform(0.0, 87.0, 160)), lai_lib=b.lai_lib, leaf_r_lib=b.leaf_r_lib, leaf_t_lib=b.leaf_t_lib,
+        soil_r_lib=b.soil_r_lib, I_dr0_lib=b.I_dr0_lib, I_df0_lib=b.I_df0_lib, lai_idx=rng.integers(0, 3, 160),
+        leaf_idx=rng.integers(0, 4, 160), soil_idx=rng.integers(0, 2, 160), sky_idx=rng.integers(0, 2, 160),
+        leaf_angle=b.leaf_angle, mla=57.0,
+    )
+    srel = sigma_rel_2s(big, common.mu_bar_fn(big.leaf_angle.G_fn))
+    for scheme in ("2s", "bl", "bf", "g77"):
+        pro = engine.host_prologue(big, scheme)
+        res = engine.solve(engine.DeviceBatch(big, scheme, prologue=pro), scheme)
+        torch.cuda.synchronize()
+        for i in (0, 31, 97, 159):
+            ref = oracle.run(scheme, big.scenario_params(i))
+            for k in ref:
+                if k == "rho_c":
+                    continue
+                got = res[k][i].cpu().numpy()
+                if scheme == "2s" and k != "I_dr":
+                    assert_close_conditioned(got[None], ref[k][None], RTOL, srel[i:i + 1], f"random rows 2s[{i}].{k}")
+                else:
+                    assert_close(got, ref[k], RTOL, f"random rows nz={nz} {scheme}[{i}].{k}", atol=1e-300)
+
+
 # ---------------------------------------------------------------------------------- kernel variants
 @pytest.mark.parametrize("mode,cfg", [("rows", "6,512,1"), ("rows", "6,512,0"), ("rows", "4,512,1"), ("rows", "4,480,0"),
                                       ("rows", "3,1024,1"), ("rows", "10,96,1")])

@@ -89,6 +89,18 @@ def test_scenario_batch_validation(default_p):
         ScenarioBatch(**{**kw, "lai_lib": default_p["lai"][::-1]})
     with pytest.raises(ValueError):
         crt.LeafAngle("conical", 1.0)
+    # attributes assigned after construction bypass __post_init__: the ABI staging step re-checks them
+    from crt1d_b200.engine import _abi_array
+
+    b2 = ScenarioBatch(**kw)
+    b2.lai_idx = np.array([0, 0], dtype=np.int64)
+    assert _abi_array(b2, "lai_idx").dtype == np.int32 and _abi_array(b2, "psi").dtype == np.float64
+    b2.leaf_idx = np.array([0, 3])
+    with pytest.raises(IndexError):
+        _abi_array(b2, "leaf_idx")
+    b2.sky_idx = np.array([0])
+    with pytest.raises(ValueError):
+        _abi_array(b2, "sky_idx")
 
 
 def test_synthetic_sweep_definition():
