@@ -562,6 +562,13 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_2s_rows_kernel(const crt1d_b
                 exp_pm(k[v].h * L[j0], em[v], ep[v]);
                 exp_pm(k[v].h * dL, qp[v], qm[v]);  // qp = e^{-h dL} multiplies e^{+hL}; qm = e^{+h dL} multiplies e^{-hL}
             }
+            // one per-thread cursor + the CTA-uniform byte distances between the fields: 42 instead of 49 instructions per
+            // level (four 64-bit cursors cost four IMAD.WIDE and ~10 register moves); A/B on one box 0.9345 -> 0.9366
+            const int64_t dD = reinterpret_cast<char*>(qD) - reinterpret_cast<char*>(qI);
+            const int64_t dU = reinterpret_cast<char*>(qU) - reinterpret_cast<char*>(qI);
+            const int64_t dF = reinterpret_cast<char*>(qF) - reinterpret_cast<char*>(qI);
+            char* q = reinterpret_cast<char*>(qI);
+            const int64_t row_bytes = (int64_t)n_wl * (int64_t)sizeof(ST);
             for (int j = j0; j < j1; ++j) {
                 const double eKj = eK[j];
                 double Idr[VEC], dn[VEC], up[VEC], F[VEC];
@@ -571,14 +578,11 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_2s_rows_kernel(const crt1d_b
                     em[v] *= qm[v];
                     ep[v] *= qp[v];
                 }
-                st_raw<VEC>(qI, Idr);
-                st_raw<VEC>(qD, dn);
-                st_raw<VEC>(qU, up);
-                st_raw<VEC>(qF, F);
-                qI += n_wl;
-                qD += n_wl;
-                qU += n_wl;
-                qF += n_wl;
+                st_raw<VEC>(reinterpret_cast<ST*>(q), Idr);
+                st_raw<VEC>(reinterpret_cast<ST*>(q + dD), dn);
+                st_raw<VEC>(reinterpret_cast<ST*>(q + dU), up);
+                st_raw<VEC>(reinterpret_cast<ST*>(q + dF), F);
+                q += row_bytes;
             }
         } else {  // general path: irregular spacing and/or some profiles not requested
             double em[VEC], ep[VEC], qm[VEC], qp[VEC];
