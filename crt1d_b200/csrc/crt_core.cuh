@@ -507,9 +507,11 @@ CRT_HD void column_n79(const ScenN79& s, const double* tab, int n_z, const BandI
     };
     // Equal layer thickness (every profile the reference's LAI generators make, ref ../leaf_area.py:82-88): tau_d is
     // the same in every layer up to the rounding of lai[j] - lai[j+1], so the layer coefficients are formed once per
-    // column instead of once per level and sweep (|td[j] - td[0]| <= 8 eps td[0]; effect on the solution ~1e-15).
+    // column instead of once per level and sweep.  Criterion |td[j] - td[0]| <= 16 eps td[0]: the synthetic sweep's 100
+    // profiles deviate by up to 8.7 eps (device prologue), and 16 eps times the conditioning of the solve (1e2..4e3)
+    // stays an order of magnitude inside the 1e-10 parity bar.
     bool uni = true;
-    for (int i = 1; i < n_z - 1; ++i) uni = uni && fabs(td[i] - td[0]) <= 1.8e-15 * td[0];
+    for (int i = 1; i < n_z - 1; ++i) uni = uni && fabs(td[i] - td[0]) <= 3.6e-15 * td[0];
     // Forward-sweep coefficients of the UPWARD row of level j >= 1 (a = -eiv, c = -fiv of the layer below, L) from
     // those of the downward row of level j-1 (e_in, f_in); unit diagonal (ref :101-108 / :122-129, tdma :186, :191).
     // Used identically in both sweeps, so the back-substitution recomputes the forward values.
