@@ -533,27 +533,9 @@ CRT_HD void column_n79(const ScenN79& s, const double* tab, int n_z, const BandI
             fu[v] = in.Idr0[v] * tbcum[0] * in.soil_r[v];
         }
     };
-    // One level of the forward recurrence: (e, f) holds the downward row's pair of level j-1 on entry and of level j
-    // on exit; La holds layer j-1 on entry (j >= 1) and layer j on exit (the layer the next upward row needs).
-    auto step = [&](int j, Lay& La, double (&e)[VEC], double (&f)[VEC], double (&eu)[VEC], double (&fu)[VEC]) {
-        if (j == 0) {
-            soil_row(eu, fu);
-        } else {
-            up_row(j, La, e, f, eu, fu);
-        }
-        if (j == n_z - 1) {  // top boundary: dn = sky diffuse (ref :132-135); a = c = 0
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                e[v] = 0.0;
-                f[v] = in.Idf0[v];
-            }
-            return;
-        }
-        // downward row (a = -aiv, c = -biv; ref :85-92 / :111-118): the soil row uses layer 1 as shipped
-        if (!uni) layer(j, La);  // (uni: La holds THE layer from the start of the sweep)
-        Lay Ld = La;
-        if (!uni && j == 0) layer(1, Ld);
-        const double gj = (j == 0) ? g[0] : g[j + 1];
+    // Downward row of a level (a = -aiv, c = -biv of layer Ld; ref :85-92 / :111-118) from the upward row's pair.
+    auto down_row = [&](double gj, const Lay& Ld, const double (&eu)[VEC], const double (&fu)[VEC], double (&e)[VEC],
+                        double (&f)[VEC]) {
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             const double d = in.Idr0[v] * gj * Ld.wd[v];
@@ -562,6 +544,34 @@ CRT_HD void column_n79(const ScenN79& s, const double* tab, int n_z, const BandI
             f[v] = (d + Ld.f[v] * fu[v]) * r;
         }
     };
+    // One level of the forward recurrence: (e, f) holds the downward row's pair of level j-1 on entry and of level j
+    // on exit; La holds layer j-1 on entry and layer j on exit (the layer the next upward row needs; with `uni` it
+    // holds THE layer throughout).  The soil level and the interior/top levels are separate functions, so the level
+    // loops carry no per-level selects or struct copies (they were 35 of 166 instructions per layer.band).
+    auto step_soil = [&](Lay& La, double (&e)[VEC], double (&f)[VEC], double (&eu)[VEC], double (&fu)[VEC]) {
+        soil_row(eu, fu);
+        if (uni) {
+            down_row(g[0], La, eu, fu, e, f);
+        } else {  // the soil-adjacent downward row uses layer 1 as shipped (ref :85-92)
+            Lay L1;
+            layer(1, L1);
+            down_row(g[0], L1, eu, fu, e, f);
+            layer(0, La);
+        }
+    };
+    auto step_in = [&](int j, Lay& La, double (&e)[VEC], double (&f)[VEC], double (&eu)[VEC], double (&fu)[VEC]) {
+        up_row(j, La, e, f, eu, fu);
+        if (j == n_z - 1) {  // top boundary: dn = sky diffuse (ref :132-135); a = c = 0
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                e[v] = 0.0;
+                f[v] = in.Idf0[v];
+            }
+            return;
+        }
+        if (!uni) layer(j, La);
+        down_row(g[j + 1], La, eu, fu, e, f);
+    };
     // ---- forward sweep (ref tdma :183-192).  Checkpointed: the DOWNWARD row's (e, f) of every CK-th level is
     // parked (F <- e_dn, I_df_d <- f_dn), 16/CK B per layer.band; the back sweep re-runs the recurrence from a
     // checkpoint through the CK levels above it into the Out object's segment store.
@@ -569,12 +579,17 @@ CRT_HD void column_n79(const ScenN79& s, const double* tab, int n_z, const BandI
 #pragma unroll
     for (int v = 0; v < VEC; ++v) e_prev[v] = f_prev[v] = 0.0;
     const int g_last = (n_z - 1) / CK;  // segment g covers levels g CK .. min((g+1) CK, n_z) - 1
-    {
+    if (g_last > 0) {  // the top segment is left to the back sweep's recomputation
         Lay La;
         double eu[VEC], fu[VEC];
         layer(0, La);
-        for (int j = 0; j < g_last * CK; ++j) {  // the top segment is left to the back sweep's recomputation
-            step(j, La, e_prev, f_prev, eu, fu);
+        step_soil(La, e_prev, f_prev, eu, fu);
+        if (CK == 1) {
+            out.st_tmp(F_F, 0, e_prev);
+            out.st_tmp(F_DN, 0, f_prev);
+        }
+        for (int j = 1; j < g_last * CK; ++j) {
+            step_in(j, La, e_prev, f_prev, eu, fu);
             if ((j + 1) % CK == 0) {
                 out.st_tmp(F_F, j, e_prev);
                 out.st_tmp(F_DN, j, f_prev);
@@ -589,6 +604,46 @@ CRT_HD void column_n79(const ScenN79& s, const double* tab, int n_z, const BandI
         omo[v] = 1.0 - (in.leaf_r[v] + in.leaf_t[v]);
         Io[v] = in.Idr0[v] * omo[v];
     }
+    // Output stage of level j = base + i from the segment store.  At the top level ed = 0 and up_above = 0, so
+    // dn = fd exactly (ref :132-135) without a special case.  Leaves this level's values in up_above / dn_above.
+    auto level_out = [&](int i, int j, double (&Idr)[VEC]) {
+        double ed[VEC], fd[VEC], eu[VEC], fu[VEC];  // forward pairs of this level's downward and upward rows
+        double dn[VEC], up[VEC], F[VEC];
+        out.seg_ld(i, 0, ed);
+        out.seg_ld(i, 1, fd);
+        out.seg_ld(CK + i, 0, eu);
+        out.seg_ld(CK + i, 1, fu);
+        const double tbc = tbcum[j];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            dn[v] = fd[v] - ed[v] * up_above[v];
+            up[v] = fu[v] - eu[v] * dn[v];
+            Idr[v] = in.Idr0[v] * tbc;                                       // ref :151
+            F[v] = Idr[v] * s.inv_mu + 2.0 * dn[v] + 2.0 * up[v];            // ref :161
+        }
+        if (j < n_z - 1) {  // layer j (between levels j and j+1): absorbed per unit sunlit/shaded leaf area
+            double sl[VEC], sh[VEC];
+            const double gd = g[j + 1], o = omtd[j], fs = fsun[j], ofs = omfs[j], wsl = isl[j], wsh = ish[j];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const double direct = Io[v] * gd;                                  // ref :145
+                const double diffuse = (dn_above[v] + up[v]) * o * omo[v];         // ref :146
+                sl[v] = (diffuse * fs + direct) * wsl;                             // ref :147, :154
+                sh[v] = (diffuse * ofs) * wsh;                                     // ref :148, :155
+            }
+            out.st(F_X0, j, sl);
+            out.st(F_X1, j, sh);
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            up_above[v] = up[v];
+            dn_above[v] = dn[v];
+        }
+        out.st(F_IDR, j, Idr);
+        out.st(F_DN, j, dn);
+        out.st(F_UP, j, up);
+        out.st(F_F, j, F);
+    };
     for (int sg = g_last; sg >= 0; --sg) {
         const int base = sg * CK;
         const int len = (n_z - base < CK) ? n_z - base : CK;
@@ -604,59 +659,39 @@ CRT_HD void column_n79(const ScenN79& s, const double* tab, int n_z, const BandI
             for (int v = 0; v < VEC; ++v) e0[v] = f0[v] = 0.0;
         }
         {
-            double e[VEC], f[VEC], eu[VEC], fu[VEC];
+            double eu[VEC], fu[VEC];
             Lay La;
             layer((base > 0 && !uni) ? base - 1 : 0, La);
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) { e[v] = e0[v]; f[v] = f0[v]; }
-            for (int i = 0; i < len; ++i) {
-                step(base + i, La, e, f, eu, fu);
-                out.seg_st(i, 0, e);
-                out.seg_st(i, 1, f);
+            int i = 0;
+            if (base == 0) {
+                step_soil(La, e0, f0, eu, fu);
+                out.seg_st(0, 0, e0);
+                out.seg_st(0, 1, f0);
+                out.seg_st(CK, 0, eu);
+                out.seg_st(CK, 1, fu);
+                i = 1;
+            }
+            for (; i < len; ++i) {
+                step_in(base + i, La, e0, f0, eu, fu);
+                out.seg_st(i, 0, e0);
+                out.seg_st(i, 1, f0);
                 out.seg_st(CK + i, 0, eu);
                 out.seg_st(CK + i, 1, fu);
             }
         }
-        for (int i = len - 1; i >= 0; --i) {
-            const int j = base + i;
-            double ed[VEC], fd[VEC], eu[VEC], fu[VEC];  // forward pairs of this level's downward and upward rows
-            double Idr[VEC], dn[VEC], up[VEC], F[VEC];
-            out.seg_ld(i, 0, ed);
-            out.seg_ld(i, 1, fd);
-            out.seg_ld(CK + i, 0, eu);
-            out.seg_ld(CK + i, 1, fu);
-            const double tbc = tbcum[j];
+        int i = len - 1;
+        double Idr[VEC];
+        if (sg == g_last) {  // the top level: remember its values for the canopy-absorbed sum
+            level_out(i, base + i, Idr);
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                dn[v] = (j == n_z - 1) ? fd[v] : fd[v] - ed[v] * up_above[v];
-                up[v] = fu[v] - eu[v] * dn[v];
-                Idr[v] = in.Idr0[v] * tbc;                                       // ref :151
-                F[v] = Idr[v] * s.inv_mu + 2.0 * dn[v] + 2.0 * up[v];            // ref :161
-            }
-            if (j < n_z - 1) {  // layer j (between levels j and j+1): absorbed per unit sunlit/shaded leaf area
-                double sl[VEC], sh[VEC];
-                const double gd = g[j + 1], o = omtd[j], fs = fsun[j], ofs = omfs[j], wsl = isl[j], wsh = ish[j];
+            for (int v = 0; v < VEC; ++v) { top[v][0] = Idr[v]; top[v][1] = dn_above[v]; top[v][2] = up_above[v]; }
+            --i;
+        }
+        for (; i >= 0; --i) level_out(i, base + i, Idr);
+        if (sg == 0) {  // the ground level was the last one written
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    const double direct = Io[v] * gd;                                  // ref :145
-                    const double diffuse = (dn_above[v] + up[v]) * o * omo[v];         // ref :146
-                    sl[v] = (diffuse * fs + direct) * wsl;                             // ref :147, :154
-                    sh[v] = (diffuse * ofs) * wsh;                                     // ref :148, :155
-                }
-                out.st(F_X0, j, sl);
-                out.st(F_X1, j, sh);
-            }
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                if (j == n_z - 1) { top[v][0] = Idr[v]; top[v][1] = dn[v]; top[v][2] = up[v]; }
-                if (j == 0) absorbed[v] = absorbed_from_ends(top[v][0], Idr[v], top[v][1], dn[v], top[v][2], up[v]);
-                up_above[v] = up[v];
-                dn_above[v] = dn[v];
-            }
-            out.st(F_IDR, j, Idr);
-            out.st(F_DN, j, dn);
-            out.st(F_UP, j, up);
-            out.st(F_F, j, F);
+            for (int v = 0; v < VEC; ++v)
+                absorbed[v] = absorbed_from_ends(top[v][0], Idr[v], top[v][1], dn_above[v], top[v][2], up_above[v]);
         }
     }
 }
