@@ -18,7 +18,22 @@
 #define CRT_HD inline
 #endif
 
+#if defined(__CUDACC__)
+#define CRT_HD_NOINLINE static __host__ __device__ __noinline__
+#else
+#define CRT_HD_NOINLINE static
+#endif
+
 namespace crt {
+
+// Remember three values of one level (a canopy-end level, for the absorbed reduction) -- deliberately NOT inlined:
+// as inline assignments under `if (j == 0)` the compiler turns them into per-level selects (zq_pa: 12 FSEL of 224
+// instructions per layer.band); a call stays a branch that is taken twice per column.
+CRT_HD_NOINLINE void keep3(double* dst, double a, double b, double c) {
+    dst[0] = a;
+    dst[1] = b;
+    dst[2] = c;
+}
 
 // Output field slots of the column accessors.
 enum Field : int { F_IDR = 0, F_DN = 1, F_UP = 2, F_F = 3, F_X0 = 4, F_X1 = 5, F_X2 = 6, N_FIELDS = 7 };
@@ -1061,8 +1076,10 @@ CRT_HD void column_zq_pa(const ScenZqPa& s, const double* eC, const double* lk, 
                 up[v] = (t < 0.0) ? Uk1[v] : ((Uk1[v] - Uk[v]) * w) * t + Uk[v];
                 Idr[v] = in.Idr0[v] * eKj;
                 F[v] = Idr[v] * s.inv_mu + 2.0 * up[v] + 2.0 * dn[v];
-                if (j == 0) { gnd[v][0] = Idr[v]; gnd[v][1] = dn[v]; gnd[v][2] = up[v]; }
-                if (j == n_z - 1) { top[v][0] = Idr[v]; top[v][1] = dn[v]; top[v][2] = up[v]; }
+            }
+            if (j == 0 || j == n_z - 1) {  // uniform, twice per column
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) keep3(j == 0 ? gnd[v] : top[v], Idr[v], dn[v], up[v]);
             }
             out.st(F_IDR, j, Idr);
             out.st(F_DN, j, dn);
