@@ -978,7 +978,7 @@ CRT_HD void interp_np_prepare(double x, const double* xp, int n, double dl, int&
 // of that level.
 //
 // The M-grid solve is the checkpointed Thomas sweep of column_zq (checkpoints in the Out object's segment
-// store: slots CK.. hold the checkpoints, slots 0..CK-1 the segment being back-substituted).  The back sweep
+// store: slots CK+1.. hold the checkpoints, slots 0..CK the segment being back-substituted, slot 0 = the pair below it).  The back sweep
 // runs from the top of the canopy down and the corrected fluxes (eq. 24/25, ref :286-345) of grid pair k are
 // final at step k, so the interpolation to the caller's levels (ref :350-361) is streamed: as soon as both
 // ends of a grid interval are final, every caller level inside it is interpolated and written.  Nothing of
@@ -1054,8 +1054,8 @@ CRT_HD void column_zq_pa(const ScenZqPa& s, const double* eC, const double* lk, 
 #pragma unroll
         for (int v = 0; v < VEC; ++v) fwd(k, v, e_prev[v], f_prev[v], e_prev[v], f_prev[v]);
         if (k % CK == 0) {
-            out.seg_st(CK + k / CK, 0, e_prev);
-            out.seg_st(CK + k / CK, 1, f_prev);
+            out.seg_st(CK + 1 + k / CK, 0, e_prev);
+            out.seg_st(CK + 1 + k / CK, 1, f_prev);
         }
     }
     // ---- streamed interpolation + outputs (ref :350-361, :403-407).  D[k] = SWd[k], U[k] = SWu[k] after the
@@ -1081,10 +1081,7 @@ CRT_HD void column_zq_pa(const ScenZqPa& s, const double* eC, const double* lk, 
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) keep3(j == 0 ? gnd[v] : top[v], Idr[v], dn[v], up[v]);
             }
-            out.st(F_IDR, j, Idr);
-            out.st(F_DN, j, dn);
-            out.st(F_UP, j, up);
-            out.st(F_F, j, F);
+            out.st4(j, Idr, dn, up, F);
         }
     };
     double D_prev[VEC], U_prev[VEC], U_prev2[VEC];  // D[t+2], U[t+1], U[t+2] when pair t arrives
@@ -1110,8 +1107,8 @@ CRT_HD void column_zq_pa(const ScenZqPa& s, const double* eC, const double* lk, 
 #pragma unroll
             for (int v = 0; v < VEC; ++v) { e0[v] = e_prev[v]; f0[v] = f_prev[v]; }
         } else if (g > 0) {
-            out.seg_ld(CK + g, 0, e0);
-            out.seg_ld(CK + g, 1, f0);
+            out.seg_ld(CK + 1 + g, 0, e0);
+            out.seg_ld(CK + 1 + g, 1, f0);
         } else {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) { e0[v] = 0.0; f0[v] = x0[v]; }
@@ -1120,25 +1117,22 @@ CRT_HD void column_zq_pa(const ScenZqPa& s, const double* eC, const double* lk, 
             double e[VEC], f[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) { e[v] = e0[v]; f[v] = f0[v]; }
+            out.seg_st(0, 0, e0);  // slot 0 = the pair below the segment, slot i = level base + i: the back sweep
+            out.seg_st(0, 1, f0);  // reads "this level" and "the level below" without a per-level special case
             for (int i = 1; i <= len; ++i) {
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) fwd(base + i, v, e[v], f[v], e[v], f[v]);
-                out.seg_st(i - 1, 0, e);
-                out.seg_st(i - 1, 1, f);
+                out.seg_st(i, 0, e);
+                out.seg_st(i, 1, f);
             }
         }
         for (int i = len; i >= 1; --i) {
             const int k = base + i;
             double eB[VEC], fB[VEC], eBl[VEC], fBl[VEC];
-            out.seg_ld(i - 1, 0, eB);
-            out.seg_ld(i - 1, 1, fB);
-            if (i >= 2) {
-                out.seg_ld(i - 2, 0, eBl);
-                out.seg_ld(i - 2, 1, fBl);
-            } else {
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) { eBl[v] = e0[v]; fBl[v] = f0[v]; }
-            }
+            out.seg_ld(i, 0, eB);
+            out.seg_ld(i, 1, fB);
+            out.seg_ld(i - 1, 0, eBl);
+            out.seg_ld(i - 1, 1, fBl);
             double SWu0_k[VEC], SWd0_k[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {

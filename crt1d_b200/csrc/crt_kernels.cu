@@ -35,7 +35,7 @@ __host__ __device__ constexpr bool uses_segments(int scheme) {
 __host__ __device__ inline int seg_slots(int scheme, int n_z) {
     if (scheme != CRT1D_SCHEME_ZQ_PA) return SEG_CK;
     const int M = n_z < ZQPA_MAX_M ? n_z : ZQPA_MAX_M;
-    return SEG_CK + (M - 1) / SEG_CK + 1;
+    return SEG_CK + 1 + (M - 1) / SEG_CK + 1;  // segment slots 0..CK (slot 0 = the pair below the segment) + checkpoints
 }
 // doubles of level tables, rounded up so that the segment store behind them is 16-byte aligned
 __host__ __device__ inline size_t tab_doubles(int scheme, int n_z) { return ((size_t)n_level_tables(scheme) * n_z + 1) & ~(size_t)1; }
@@ -91,6 +91,22 @@ struct GlobalOut {
             } else {
                 st_raw<VEC>(base[f] + at(f, j), x);
             }
+        }
+    }
+    // the four profile fields of one level: one row offset for all of them
+    __device__ __forceinline__ void st4(int j, const double (&a)[VEC], const double (&b)[VEC], const double (&c)[VEC],
+                                        const double (&d)[VEC]) const {
+        if constexpr (FAST) {
+            const int64_t o = off + (int64_t)j * stride;
+            st_raw<VEC>(base[F_IDR] + o, a);
+            st_raw<VEC>(base[F_DN] + o, b);
+            st_raw<VEC>(base[F_UP] + o, c);
+            st_raw<VEC>(base[F_F] + o, d);
+        } else {
+            st(F_IDR, j, a);
+            st(F_DN, j, b);
+            st(F_UP, j, c);
+            st(F_F, j, d);
         }
     }
     // elimination scratch parked in the output arrays: re-read by the same thread during

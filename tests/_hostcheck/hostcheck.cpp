@@ -22,10 +22,16 @@ struct HostOut {
         if (!p[f]) return;
         for (int v = 0; v < VEC; ++v) p[f][(int64_t)j * stride + v] = x[v];
     }
+    void st4(int j, const double (&a)[VEC], const double (&b)[VEC], const double (&c)[VEC], const double (&d)[VEC]) const {
+        st(crt::F_IDR, j, a);
+        st(crt::F_DN, j, b);
+        st(crt::F_UP, j, c);
+        st(crt::F_F, j, d);
+    }
     void st_tmp(int f, int j, const double (&x)[VEC]) const { st(f, j, x); }
     // segment store of the checkpointed Thomas sweeps (shared memory on the device)
     static constexpr int CK = 8;
-    mutable double seg_buf[CK + 100 / CK + 2][2][VEC];  // + zq_pa's checkpoint slots
+    mutable double seg_buf[CK + 100 / CK + 4][2][VEC];  // + zq_pa's checkpoint slots
     int seg_levels() const { return CK; }
     void seg_st(int slot, int k, const double (&x)[VEC]) const {
         for (int v = 0; v < VEC; ++v) seg_buf[slot][k][v] = x[v];
