@@ -1,7 +1,7 @@
 """ctypes mirror of include/crt1d_b200.h (structs, constants, function prototypes)."""
 import ctypes as C
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 OK = 0
 ERR_INVALID_ARG = -1
@@ -10,6 +10,8 @@ ERR_UNSUPPORTED = -3
 ERR_CUDA = -4
 ERR_NO_DEVICE = -5
 ERR_NO_MEMORY = -6
+NONFINITE = 1  # positive finding of crt1d_solve_host: results delivered, some scenario is non-finite
+STATUS_NONFINITE = 1
 
 SCHEME_IDS = {"2s": 0, "4s": 1, "bf": 2, "bl": 3, "g77": 4, "n79": 5, "zq": 6, "zq_pa": 7}
 
@@ -66,6 +68,7 @@ class Out(C.Structure):
         ("n_bw", C.c_int32),
         ("absorbed", _pd),
         ("profile_f32", C.c_int32),
+        ("status", _pd),
     ]
 
 
@@ -92,6 +95,7 @@ PROTOTYPES = {
     "crt1d_solve_zq_pa": (C.c_int, [C.POINTER(Batch), C.POINTER(Out), C.c_void_p]),
     "crt1d_solve_host": (C.c_int, [C.c_int, C.POINTER(Batch), C.POINTER(Out), C.c_int]),
     "crt1d_release_workspace": (C.c_int, []),
+    "crt1d_reload_tuning": (C.c_int, []),
     "crt1d_calc_absorption": (
         C.c_int, [C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AbsorptionOut), C.c_void_p]),
     "crt1d_energy_balance": (

@@ -36,8 +36,16 @@ def load():
 
 
 def check(code):
-    """Raise Crt1dB200Error for a negative return code."""
-    if code != _abi.OK:
-        lib = load()
-        detail = lib.crt1d_last_error().decode() or lib.crt1d_strerror(code).decode()
-        raise Crt1dB200Error(code, detail)
+    """Raise Crt1dB200Error for a negative return code.  The positive finding CRT1D_NONFINITE (results delivered,
+    some scenario holds NaN/Inf) becomes a RuntimeWarning: the reference returns such arrays with at most a
+    numpy RuntimeWarning, and a drop-in must not turn that into an exception."""
+    if code == _abi.OK:
+        return code
+    lib = load()
+    detail = lib.crt1d_last_error().decode() or lib.crt1d_strerror(code).decode()
+    if code == _abi.NONFINITE:
+        import warnings
+
+        warnings.warn(f"crt1d_b200: {detail}", RuntimeWarning, stacklevel=3)
+        return code
+    raise Crt1dB200Error(code, detail)

@@ -11,6 +11,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define CRT_HD __host__ __device__ __forceinline__
@@ -1188,6 +1189,21 @@ CRT_HD void column_zq_pa(const ScenZqPa& s, const double* eC, const double* lk, 
 // downward irradiance plus the direct beam.  Direct and diffuse problems share the matrix and their
 // solutions are only ever used summed (ref :274-281), so one 4x4 solve per band suffices.
 // Accuracy: limited by roundoff (~1e-13), i.e. far tighter than the reference's tol = 1e-6 BVP.
+//
+// The reference integrates the ODE numerically and is indifferent to the spectrum of N; a closed form is not:
+//   * lambda_0^2 (the larger eigenvalue) is positive for every omega <= 1, but lambda_1^2 falls through zero at
+//     omega* < 1 (0.99536 for the default ellipsoidal G with mu_s = 0.501) and is NEGATIVE up to omega = 1:
+//     the mode turns from exponential to oscillatory, and e^{-lam x}, e^{-lam (LAI - x)} become linearly
+//     dependent as lam -> 0.  Columns with lambda_1^2 LAI^2 < 1/4 therefore use the ENTIRE basis
+//     c(x) = cosh(lam x), sh(x) = sinh(lam x)/lam (= cos, sin/nu for lambda^2 = -nu^2 < 0; power series near
+//     0), which is analytic in lambda^2 and well conditioned through the crossing.
+//   * kappa = K_b equal to lambda_k (an ordinary place: omega = 0.594 at psi = 10 deg) makes the particular
+//     solution e^{-kappa x}/(kappa^2 - lambda_k^2) blow up and cancel against the homogeneous mode.  Within 5 %
+//     of a resonance the particular solution's component along that eigenvector is carried as the divided
+//     difference R_k(x) = (e^{-kappa x} - e^{-lam_k x})/(kappa^2 - lam_k^2) = -x e^{-kappa x} phi1((kappa - lam_k) x)/(kappa + lam_k),
+//     phi1(u) = expm1(u)/u, which is finite through the resonance (entire-basis variant: the solution of
+//     R'' = lambda^2 R + e^{-kappa x}, R(0) = R'(0) = 0, by its power series).
+// Both are rare columns: they take `coef_4s_general` (not inlined) and the direct-evaluation level path.
 // =================================================================================================
 struct Scen4s {
     double mu0, inv_mu, kappa, L_T, eKT;  // cos psi, 1/cos psi, K_b = G/mu0, total LAI, exp(-kappa L_T)
@@ -1257,12 +1273,234 @@ CRT_HD void solve4(double (&A)[4][4], double (&b)[4]) {
 
 // Folded per-band coefficients: I_dn(x) = sum_k dnP[k] e^{-lam_k (LAI-x)} + dnM[k] e^{-lam_k x} + dnK e^{-kappa x}
 struct Coef4s {
-    // I_dn(x) = sum_k dnP[k] p_k + dnM[k] m_k + dnK e^{-kappa x},  m_k = e^{-lam_k x},  p_k = e^{-lam_k (LAI - x)}.
+    // I_dn(x) = sum_k dnP[k] p_k + dnM[k] m_k + dnK X,  m_k = e^{-lam_k x},  p_k = e^{-lam_k (LAI - x)},  X = e^{-kappa x}.
     // Fast form (lam[0] > 0): dnP/upP are pre-multiplied by g_k = e^{-lam_k LAI}, so p_k's factor is just e^{+lam_k x},
-    // the other half of the exp_pm that yields m_k.  If lam_0 LAI >= 600 that product could overflow: the
-    // coefficients stay unscaled and lam[0] is stored NEGATED as the flag for direct exponentials.
+    // the other half of the exp_pm that yields m_k.
+    // Slow form (lam[0] < 0, direct evaluation of every basis function, unscaled coefficients): lam[0] holds
+    // -lambda_0 with a 3-bit mode word in its lowest mantissa bits (a relative perturbation of lambda_0 below
+    // 2^-49; e^{-lam x} moves by at most that / e in absolute terms):
+    //   mode & 1        mode 1 uses the entire basis: lam[1] = lambda_1^2 (any sign), m_1 = c(x), p_1 = sh(x)
+    //   (mode >> 1) & 3 resonant mode + 1 (0 = none): X = R_k(x) instead of e^{-kappa x}
+    // Reasons for the slow form: lam_0 LAI >= 600 (the scaled product could overflow), lambda_1^2 LAI^2 < 1/4,
+    // |kappa^2 - lambda_k^2| <= 0.05 kappa^2.
     double lam[2], dnP[2], dnM[2], upP[2], upM[2], dnK, upK, Idr0;
 };
+
+CRT_HD double pack_mode_4s(double lam0, int mode) {  // -(lam0 with its three lowest mantissa bits = mode)
+#if defined(__CUDA_ARCH__)
+    return -__longlong_as_double((__double_as_longlong(lam0) & ~7LL) | (long long)mode);
+#else
+    int64_t b;
+    memcpy(&b, &lam0, 8);
+    b = (b & ~(int64_t)7) | (int64_t)mode;
+    double r;
+    memcpy(&r, &b, 8);
+    return -r;
+#endif
+}
+CRT_HD int unpack_mode_4s(double lam0_stored) {
+#if defined(__CUDA_ARCH__)
+    return (int)(__double_as_longlong(lam0_stored) & 7LL);
+#else
+    int64_t b;
+    memcpy(&b, &lam0_stored, 8);
+    return (int)(b & 7);
+#endif
+}
+
+// c(x) = cosh(sqrt(l2) x), sh(x) = sinh(sqrt(l2) x)/sqrt(l2): entire functions of l2 (cos, sin/nu for l2 = -nu^2).
+CRT_HD void csh_entire(double l2, double x, double& c, double& sh) {
+    const double u2 = l2 * x * x;
+    if (fabs(u2) < 1e-4) {  // truncation u2^5/10! < 3e-27
+        c = 1.0 + u2 * (1.0 / 2.0) * (1.0 + u2 * (1.0 / 12.0) * (1.0 + u2 * (1.0 / 30.0) * (1.0 + u2 * (1.0 / 56.0))));
+        sh = x * (1.0 + u2 * (1.0 / 6.0) * (1.0 + u2 * (1.0 / 20.0) * (1.0 + u2 * (1.0 / 42.0) * (1.0 + u2 * (1.0 / 72.0)))));
+    } else if (l2 > 0.0) {
+        const double lam = sqrt(l2);
+        c = cosh(lam * x);
+        sh = sinh(lam * x) / lam;
+    } else {
+        const double nu = sqrt(-l2);
+        c = cos(nu * x);
+        sh = sin(nu * x) / nu;
+    }
+}
+
+// R(x) = (e^{-kappa x} - e^{-lam x})/(kappa^2 - lam^2), finite through kappa = lam.  eK = e^{-kappa x}.
+CRT_HD double res_exp_4s(double kappa, double lam, double x, double eK) {
+    const double u = (kappa - lam) * x;
+    const double phi1 = fabs(u) < 1e-8 ? 1.0 + 0.5 * u : expm1(u) / u;
+    return -eK * x * phi1 / (kappa + lam);
+}
+
+// R(x): R'' = l2 R + e^{-kappa x}, R(0) = R'(0) = 0, by its power series (used for kappa x, |l2| x^2 <~ 1 only).
+CRT_HD double res_series_4s(double kappa, double l2, double x) {
+    double a0 = 0.0, a1 = 0.0;     // a_n, a_{n+1}
+    double e = 1.0;                // (-kappa)^n / n!
+    double xn = x * x;             // x^{n+2}
+    double sum = 0.0;
+    for (int n = 0; n < 40; ++n) {
+        const double a2 = (l2 * a0 + e) / ((n + 2.0) * (n + 1.0));
+        sum += a2 * xn;
+        a0 = a1;
+        a1 = a2;
+        e *= -kappa / (n + 1.0);
+        xn *= x;
+    }
+    return sum;
+}
+
+// General form of the 4s coefficients: any sign of lambda_1^2, kappa at or near lambda_k (see the header above).
+// s(x) = D + U = sum_i phi_i u_i(x), u_i'' = lambda_i^2 u_i + c_i e^{-kappa x} (c from 2 (P-Q) vD = sum c_i phi_i),
+// w = D - U = (P-Q)^{-1} s' = sum_i chi_i u_i', chi_i = -phi_i / diag(q).  Each u_i = a_i A_i + b_i B_i + c_i F_i with
+// a homogeneous pair (A_i, B_i) and a particular F_i chosen per mode:
+//   exponential pair  A = e^{-lam x}, B = e^{-lam (LAI - x)};  entire pair  A = c(x), B = sh(x)  (A' = l2 B, B' = A);
+//   F = e^{-kappa x}/(kappa^2 - l2), or the resonance-safe R (R' = -kappa R - A/(kappa + lam); entire pair: R' = -kappa R + B).
+// In the resonant case e^{-kappa x} = A_k [- kappa B_k] + (kappa^2 - l2_k) R_k is eliminated from the other mode's
+// particular term, so the level stage still sums five products (X := R_k takes the e^{-kappa x} slot).
+CRT_HD_NOINLINE void coef_4s_general(const Scen4s& s, double r, double t, double rho, double Idr0, double Idf0,
+                                     const double (&N)[2][2], const double (&l2)[2], const double (&phi)[2][2],
+                                     Coef4s& k) {
+    const double omega = r + t;
+    const double R_dr0 = Idr0 * s.inv_pi_mu0, R_df0 = Idf0 * (1.0 / CRT_PI);
+    const double e1 = 0.25 * omega * R_dr0 * s.mu_s, e2 = 0.25 * omega * R_dr0 * (1.0 - s.mu_s);
+    const double m1 = s.m1, m2 = s.m2, L = s.L_T, kap = s.kappa, k2 = kap * kap;
+    const double G = kap * s.mu0;
+    const double vD0 = G * e2 * s.inv_m2, vD1 = G * e1 * s.inv_m1;
+    const double r0 = -2.0 * s.q0 * vD0, r1 = -2.0 * s.q1 * vD1;
+    (void)N;
+    // forcing in the eigenbasis
+    const double dphi = phi[0][0] * phi[1][1] - phi[1][0] * phi[0][1];
+    double c[2];
+    c[0] = (r0 * phi[1][1] - r1 * phi[1][0]) / dphi;
+    c[1] = (phi[0][0] * r1 - phi[0][1] * r0) / dphi;
+
+    const bool entire1 = !(l2[1] * L * L >= 0.25);
+    int res = 0;
+    if (fabs(k2 - l2[0]) <= 0.05 * k2) res = 1;
+    else if (fabs(k2 - l2[1]) <= 0.05 * k2) res = 2;
+
+    double chi[2][2], mphi[2], mchi[2], lam[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        chi[i][0] = -phi[i][0] * s.inv_q0;
+        chi[i][1] = -phi[i][1] * s.inv_q1;
+        mphi[i] = m2 * phi[i][0] + m1 * phi[i][1];
+        mchi[i] = m2 * chi[i][0] + m1 * chi[i][1];
+        lam[i] = l2[i] > 0.0 ? sqrt(l2[i]) : 0.0;
+    }
+    // boundary data (f(0), f'(0), f(L), f'(L)) of A_i, B_i, F_i
+    double Ab[2][4], Bb[2][4], Fb[2][4];
+    double shL = 0.0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        if (i == 1 && entire1) {
+            double cL;
+            csh_entire(l2[1], L, cL, shL);
+            Ab[i][0] = 1.0; Ab[i][1] = 0.0; Ab[i][2] = cL;  Ab[i][3] = l2[1] * shL;
+            Bb[i][0] = 0.0; Bb[i][1] = 1.0; Bb[i][2] = shL; Bb[i][3] = cL;
+        } else {
+            const double g = exp(-lam[i] * L);
+            Ab[i][0] = 1.0; Ab[i][1] = -lam[i];    Ab[i][2] = g;   Ab[i][3] = -lam[i] * g;
+            Bb[i][0] = g;   Bb[i][1] = lam[i] * g; Bb[i][2] = 1.0; Bb[i][3] = lam[i];
+        }
+        if (res == i + 1) {
+            if (i == 1 && entire1) {
+                const double RL = res_series_4s(kap, l2[1], L);
+                Fb[i][0] = 0.0; Fb[i][1] = 0.0; Fb[i][2] = RL; Fb[i][3] = -kap * RL + shL;
+            } else {
+                const double RL = res_exp_4s(kap, lam[i], L, s.eKT);
+                const double ik = 1.0 / (kap + lam[i]);
+                Fb[i][0] = 0.0; Fb[i][1] = -ik; Fb[i][2] = RL; Fb[i][3] = -kap * RL - Ab[i][2] * ik;
+            }
+        } else {
+            const double id = 1.0 / (k2 - l2[i]);
+            Fb[i][0] = id; Fb[i][1] = -kap * id; Fb[i][2] = s.eKT * id; Fb[i][3] = -kap * s.eKT * id;
+        }
+    }
+    // 4x4 system for [B_0, B_1, A_0, A_1] coefficients (the slot order P0, P1, M0, M1 of the level stage)
+    double A[4][4], rhs[4];
+    auto fill = [&](int col, int i, const double (&f)[4]) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            A[cc][col] = 0.5 * (phi[i][cc] * f[0] + chi[i][cc] * f[1]);               // D_cc(0)
+            A[2 + cc][col] = 0.5 * (phi[i][cc] * f[2] - chi[i][cc] * f[3])            // U_cc(L)
+                             - rho * (mphi[i] * f[2] + mchi[i] * f[3]);              //  - 2 rho (m2 D_0 + m1 D_1)(L)
+        }
+    };
+    fill(0, 0, Bb[0]);
+    fill(1, 1, Bb[1]);
+    fill(2, 0, Ab[0]);
+    fill(3, 1, Ab[1]);
+    const double beam = rho * s.mu0 * R_dr0 * s.eKT;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+        double Dp0 = 0.0, botp = 0.0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            Dp0 += 0.5 * c[i] * (phi[i][cc] * Fb[i][0] + chi[i][cc] * Fb[i][1]);
+            botp += c[i] * (0.5 * (phi[i][cc] * Fb[i][2] - chi[i][cc] * Fb[i][3]) - rho * (mphi[i] * Fb[i][2] + mchi[i] * Fb[i][3]));
+        }
+        rhs[cc] = R_df0 - Dp0;
+        rhs[2 + cc] = beam - botp;
+    }
+    solve4(A, rhs);
+    // irradiances: I_dn = pi sum coef (mphi f + mchi f'),  I_up = pi sum coef (mphi f - mchi f')
+    double dK = 0.0, uK = 0.0;  // coefficient of the X slot
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double aB = rhs[i], aA = rhs[2 + i];
+        if (i == 1 && entire1) {
+            k.dnM[i] = CRT_PI * (aA * mphi[i] + aB * mchi[i]);
+            k.dnP[i] = CRT_PI * (aA * l2[1] * mchi[i] + aB * mphi[i]);
+            k.upM[i] = CRT_PI * (aA * mphi[i] - aB * mchi[i]);
+            k.upP[i] = CRT_PI * (-aA * l2[1] * mchi[i] + aB * mphi[i]);
+        } else {
+            k.dnM[i] = CRT_PI * aA * (mphi[i] - lam[i] * mchi[i]);
+            k.dnP[i] = CRT_PI * aB * (mphi[i] + lam[i] * mchi[i]);
+            k.upM[i] = CRT_PI * aA * (mphi[i] + lam[i] * mchi[i]);
+            k.upP[i] = CRT_PI * aB * (mphi[i] - lam[i] * mchi[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double dn_i = CRT_PI * c[i] * (mphi[i] - kap * mchi[i]);  // coefficient of F_i in I_dn (F' = -kappa F + ...)
+        const double up_i = CRT_PI * c[i] * (mphi[i] + kap * mchi[i]);
+        if (res == i + 1) {
+            dK += dn_i;
+            uK += up_i;
+            if (i == 1 && entire1) {  // R' = -kappa R + B
+                k.dnP[i] += CRT_PI * c[i] * mchi[i];
+                k.upP[i] -= CRT_PI * c[i] * mchi[i];
+            } else {                  // R' = -kappa R - A/(kappa + lam)
+                const double ik = 1.0 / (kap + lam[i]);
+                k.dnM[i] -= CRT_PI * c[i] * mchi[i] * ik;
+                k.upM[i] += CRT_PI * c[i] * mchi[i] * ik;
+            }
+        } else {
+            const double id = 1.0 / (k2 - l2[i]);
+            if (res == 0) {
+                dK += dn_i * id;
+                uK += up_i * id;
+            } else {  // the other mode is resonant: e^{-kappa x} = A_k [- kappa B_k] + (kappa^2 - l2_k) R_k
+                const int kk = res - 1;
+                const double dk = dn_i * id, uk = up_i * id;
+                k.dnM[kk] += dk;
+                k.upM[kk] += uk;
+                if (kk == 1 && entire1) {
+                    k.dnP[kk] -= kap * dk;
+                    k.upP[kk] -= kap * uk;
+                }
+                dK += dk * (k2 - l2[kk]);
+                uK += uk * (k2 - l2[kk]);
+            }
+        }
+    }
+    k.dnK = dK;
+    k.upK = uK;
+    k.Idr0 = Idr0;
+    k.lam[0] = pack_mode_4s(lam[0], (entire1 ? 1 : 0) | (res << 1));
+    k.lam[1] = entire1 ? l2[1] : lam[1];
+}
 
 CRT_HD Coef4s coef_4s(const Scen4s& s, double r, double t, double rho, double Idr0, double Idf0) {
     const double omega = r + t;                                   // ref :180
@@ -1304,6 +1542,18 @@ CRT_HD Coef4s coef_4s(const Scen4s& s, double r, double t, double rho, double Id
         const double nrm = rcp_nr(fmax(fabs(phi[i][0]), fabs(phi[i][1])));
         phi[i][0] *= nrm;
         phi[i][1] *= nrm;
+    }
+    {   // rare columns: vanishing / negative lambda_1^2, kappa near lambda_k  (also catches NaN inputs)
+        const double k2g = s.kappa * s.kappa;
+        const bool ordinary = l2[1] * s.L_T * s.L_T >= 0.25 && fabs(k2g - l2[0]) > 0.05 * k2g && fabs(k2g - l2[1]) > 0.05 * k2g;
+        if (!ordinary) {
+            const double Nm[2][2] = {{N00, N01}, {N10, N11}};
+            coef_4s_general(s, r, t, rho, Idr0, Idf0, Nm, l2, phi, k);
+            return k;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
         k.lam[i] = sqrt(l2[i]);
         psi_[i][0] = -k.lam[i] * phi[i][0] * s.inv_q0;   // (P-Q)^{-1} phi lambda
         psi_[i][1] = -k.lam[i] * phi[i][1] * s.inv_q1;
@@ -1359,18 +1609,41 @@ CRT_HD Coef4s coef_4s(const Scen4s& s, double r, double t, double rho, double Id
             k.upP[i] *= g[i];
         }
     } else {
-        k.lam[0] = -k.lam[0];
+        k.lam[0] = pack_mode_4s(k.lam[0], 0);
     }
     return k;
 }
 
-// One level of one 4s column from its exponentials m_k = e^{-lam_k x}, p_k = (scaled) e^{-lam_k (LAI - x)}.
-CRT_HD void level_4s_e(const Scen4s& s, const Coef4s& k, double eK, double m0, double p0, double m1, double p1,
+// One level of one 4s column from its basis functions: m_k = e^{-lam_k x}, p_k = (scaled) e^{-lam_k (LAI - x)} (or the
+// entire pair), X = e^{-kappa x} (or the resonance-safe R_k); eK = e^{-kappa x} for the direct beam.
+CRT_HD void level_4s_x(const Scen4s& s, const Coef4s& k, double eK, double X, double m0, double p0, double m1, double p1,
                        double& Idr, double& dn, double& up, double& F) {
-    dn = k.dnK * eK + (k.dnP[0] * p0 + k.dnM[0] * m0) + (k.dnP[1] * p1 + k.dnM[1] * m1);
-    up = k.upK * eK + (k.upP[0] * p0 + k.upM[0] * m0) + (k.upP[1] * p1 + k.upM[1] * m1);
+    dn = k.dnK * X + (k.dnP[0] * p0 + k.dnM[0] * m0) + (k.dnP[1] * p1 + k.dnM[1] * m1);
+    up = k.upK * X + (k.upP[0] * p0 + k.upM[0] * m0) + (k.upP[1] * p1 + k.upM[1] * m1);
     Idr = k.Idr0 * eK;                        // ref :284
     F = Idr * s.inv_mu + 2.0 * up + 2.0 * dn; // ref :290
+}
+CRT_HD void level_4s_e(const Scen4s& s, const Coef4s& k, double eK, double m0, double p0, double m1, double p1,
+                       double& Idr, double& dn, double& up, double& F) {
+    level_4s_x(s, k, eK, eK, m0, p0, m1, p1, Idr, dn, up, F);
+}
+
+// Slow form: every basis function of level x evaluated directly (mode word: see Coef4s).
+CRT_HD_NOINLINE void basis_4s_slow(const Scen4s& s, const Coef4s& k, double x, double eK, double* b5) {
+    const int mode = unpack_mode_4s(k.lam[0]);
+    const double l0 = -k.lam[0], xr = s.L_T - x;
+    double X = eK, m1, p1;
+    const double m0 = exp(-l0 * x), p0 = exp(-l0 * xr);
+    if (mode & 1) {
+        csh_entire(k.lam[1], x, m1, p1);
+    } else {
+        m1 = exp(-k.lam[1] * x);
+        p1 = exp(-k.lam[1] * xr);
+    }
+    const int res = mode >> 1;
+    if (res == 1) X = res_exp_4s(s.kappa, l0, x, eK);
+    else if (res == 2) X = (mode & 1) ? res_series_4s(s.kappa, k.lam[1], x) : res_exp_4s(s.kappa, k.lam[1], x, eK);
+    b5[0] = X; b5[1] = m0; b5[2] = p0; b5[3] = m1; b5[4] = p1;
 }
 
 // One level of one 4s column: x = cumulative LAI of the level, eK = exp(-kappa x)   (ref :246-290)
@@ -1380,14 +1653,12 @@ CRT_HD void level_4s(const Scen4s& s, const Coef4s& k, double x, double eK, doub
     if (k.lam[0] > 0.0) {
         exp_pm(k.lam[0] * x, m0, p0);
         exp_pm(k.lam[1] * x, m1, p1);
+        level_4s_e(s, k, eK, m0, p0, m1, p1, Idr, dn, up, F);
     } else {
-        const double l0 = -k.lam[0], xr = s.L_T - x;
-        m0 = exp(-l0 * x);
-        p0 = exp(-l0 * xr);
-        m1 = exp(-k.lam[1] * x);
-        p1 = exp(-k.lam[1] * xr);
+        double b5[5];
+        basis_4s_slow(s, k, x, eK, b5);
+        level_4s_x(s, k, eK, b5[0], b5[1], b5[2], b5[3], b5[4], Idr, dn, up, F);
     }
-    level_4s_e(s, k, eK, m0, p0, m1, p1, Idr, dn, up, F);
 }
 
 // L[j], eK[j] = exp(-kappa L[j]) level tables.

@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <mutex>
 #include <type_traits>
 
 #include "crt_internal.h"
@@ -22,6 +23,65 @@
 namespace crt {
 
 constexpr int BLOCK = 128;  // threads per CTA of the elementwise kernels (absorption)
+
+// ---------------------------------------------------------------------------------------------
+// Tuning hooks (CRT1D_B200_* environment variables): kernel-selection overrides for experiments and for the
+// tests that force a specific kernel.  Read ONCE, at the first launch (or again on crt1d_reload_tuning());
+// the steady state of the ABI touches neither getenv nor sscanf.
+// ---------------------------------------------------------------------------------------------
+struct Tuning {
+    int tile_threads = 0;        // CRT1D_B200_TILE_THREADS   (0 = per-scheme default)
+    int diag_threads = 0;        // CRT1D_B200_DIAG_THREADS
+    int rows_lv = 10, rows_th = 512, rows_rec = 1;  // CRT1D_B200_ROWS_CFG "LV,threads,rec"
+    int split_4s = 2;            // CRT1D_B200_4S_SPLIT
+    int rows_threads = 0;        // CRT1D_B200_ROWS_THREADS
+    long long scen_min = 148;    // CRT1D_B200_SCEN_MIN
+    bool force_vec1 = false;     // CRT1D_B200_FORCE_VEC1
+    bool tile_2s = false;        // CRT1D_B200_2S_KERNEL=tile
+    bool no_rows = false;        // CRT1D_B200_NO_ROWS
+};
+static Tuning read_tuning() {
+    Tuning t;
+    if (const char* e = getenv("CRT1D_B200_TILE_THREADS")) t.tile_threads = atoi(e);
+    if (const char* e = getenv("CRT1D_B200_DIAG_THREADS")) t.diag_threads = atoi(e);
+    if (const char* e = getenv("CRT1D_B200_ROWS_CFG")) sscanf(e, "%d,%d,%d", &t.rows_lv, &t.rows_th, &t.rows_rec);
+    if (const char* e = getenv("CRT1D_B200_4S_SPLIT")) t.split_4s = atoi(e);
+    if (const char* e = getenv("CRT1D_B200_ROWS_THREADS")) t.rows_threads = atoi(e);
+    if (const char* e = getenv("CRT1D_B200_SCEN_MIN")) t.scen_min = atoll(e);
+    t.force_vec1 = getenv("CRT1D_B200_FORCE_VEC1") != nullptr;
+    if (const char* e = getenv("CRT1D_B200_2S_KERNEL")) t.tile_2s = e[0] != 'r';
+    t.no_rows = getenv("CRT1D_B200_NO_ROWS") != nullptr;
+    return t;
+}
+static Tuning g_tuning = read_tuning();
+static const Tuning& tuning() { return g_tuning; }
+void reload_tuning() { g_tuning = read_tuning(); }
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel) and only when the request grows.
+static cudaError_t ensure_dyn_smem(const void* kern, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    struct Entry { const void* k; int dev; size_t bytes; };
+    static Entry cache[256];
+    static int n_cache = 0;
+    static std::mutex mu;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    Entry* hit = nullptr;
+    for (int i = 0; i < n_cache; ++i)
+        if (cache[i].k == kern && cache[i].dev == dev) { hit = &cache[i]; break; }
+    if (hit && hit->bytes >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    if (hit) hit->bytes = bytes;
+    else if (n_cache < 256) cache[n_cache++] = {kern, dev, bytes};
+    return cudaSuccess;
+}
+template <class K>
+static cudaError_t ensure_smem(K kern, size_t bytes) { return ensure_dyn_smem(reinterpret_cast<const void*>(kern), bytes); }
+// one-CTA-per-scenario grids: blockIdx.x is 31 bits
+static bool grid_ok(int64_t ctas) { return ctas > 0 && ctas <= 2147483647LL; }
 
 // Checkpoint spacing of the zq / n79 Thomas sweeps (levels recomputed per segment in the back sweep).
 #ifndef CRT_SEG_CK
@@ -281,6 +341,12 @@ __global__ void __launch_bounds__(BLK, MINB) solve_kernel(const crt1d_batch in, 
                 for (int v = 0; v < VEC; ++v) acc[k] += out.band_w[(int64_t)k * n_wl + b0 + v] * ab[v];
             }
         }
+        if (out.status) {  // `ab` combines all three irradiances of the ground and top levels
+            bool bad = false;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) bad = bad || !isfinite(ab[v]);
+            if (bad) atomicOr(out.status + s, CRT1D_STATUS_NONFINITE);
+        }
     }
 
     if (out.absorbed) {  // fixed-order block reduction (deterministic); launcher guarantees ctas_per_scen == 1
@@ -320,10 +386,8 @@ constexpr int ZQPA_VEC = 1, ZQPA_THREADS = 128;  // zq_pa: one column per thread
 // zq_pa 96 0.47 | 128 0.50 | 192 0.45 | 256 0.50 (early-exiting warps free their issue slots; longer row
 // fragments help the stores).
 static int tile_threads(int cfg, int blk) {
-    if (const char* e = getenv("CRT1D_B200_TILE_THREADS")) {
-        const int t = atoi(e);
-        if (t >= 32 && t <= blk && t % 32 == 0) return t;
-    }
+    const int t = tuning().tile_threads;
+    if (t >= 32 && t <= blk && t % 32 == 0) return t;
     return cfg;
 }
 
@@ -345,10 +409,7 @@ static cudaError_t launch_one(const crt1d_batch& in, const crt1d_out& out, cudaS
         for (int q = 0; q < n_out_fields(SCHEME); ++q) all = all && f[q] != nullptr;
         if (all) kern = solve_kernel<SCHEME, VEC, BLK, MINB, true>;
     }
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
+    if (cudaError_t e = ensure_smem(kern, smem); e != cudaSuccess) return e;
     kern<<<(unsigned)grid, nthr, smem, stream>>>(in, out, tiles_per_scen, tiles_per_cta);
     return cudaGetLastError();
 }
@@ -509,27 +570,32 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_2s_rows_kernel(const crt1d_b
                     cf[7 * ld + c0 + v] = k[v].Idr0;
                 }
             }
-            if (out.absorbed) {  // ground/top levels -> canopy-absorbed sums of this chunk, fixed lane order
+            if (out.absorbed || out.status) {  // ground/top levels -> canopy-absorbed sums of this chunk, fixed lane order
                 double a4[4] = {0.0, 0.0, 0.0, 0.0};
                 if (valid) {
+                    bool bad = false;
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) {
                         double Ig, dg, ug, Fg, It, dt, ut, Ft;
                         level_2s(k[v], sc.inv_mu, L[0], eK[0], Ig, dg, ug, Fg);
                         level_2s(k[v], sc.inv_mu, L[n_z - 1], eK[n_z - 1], It, dt, ut, Ft);
                         ab[v] = absorbed_from_ends(It, Ig, dt, dg, ut, ug);
+                        bad = bad || !isfinite(ab[v]);
                     }
-                    for (int q = 0; q < out.n_bw; ++q) {
+                    if (out.status && bad) atomicOr(out.status + s, CRT1D_STATUS_NONFINITE);
+                    for (int q = 0; q < (out.absorbed ? out.n_bw : 0); ++q) {
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) a4[q] += out.band_w[(int64_t)q * n_wl + c0 + v] * ab[v];
                     }
                 }
+                if (out.absorbed) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    double v = a4[q];
+                    for (int q = 0; q < 4; ++q) {
+                        double v = a4[q];
 #pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-                    if (lane == 0) partial[chunk][q] = v;
+                        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+                        if (lane == 0) partial[chunk][q] = v;
+                    }
                 }
             }
             if constexpr (DIAG) continue;
@@ -560,7 +626,7 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_2s_rows_kernel(const crt1d_b
         // Equally spaced levels inside the group (every profile the reference's LAI generators make:
         // lai = linspace(1, 0, n) * LAI, ref ../leaf_area.py:82-88): e^{-+h L_j} advance by the constant
         // factor e^{+-h dL}, so only the first level of the group needs exponentials.  Drift <= LV ulp.
-        const bool uniform = REC && grp_uniform[lg] != 0;
+        const bool uniform = REC && lg < 1024 && grp_uniform[lg] != 0;
         // Running store cursors (one add per field per level instead of 64-bit multiply-adds), and the common
         // "all four profiles requested, equally spaced group" case gets a loop without per-store null checks
         // and without per-level path selects: the sweep is issue/energy sensitive under the 1 kW power cap.
@@ -661,25 +727,23 @@ static bool no_profile_requested(const crt1d_out& out) {
     return !out.I_dr && !out.I_df_d && !out.I_df_u && !out.F && !out.x0 && !out.x1 && !out.x2;
 }
 static int diag_threads(int dflt) {  // CRT1D_B200_DIAG_THREADS: tuning override (multiple of 32, <= 256)
-    const char* env = getenv("CRT1D_B200_DIAG_THREADS");
-    const int t = env ? atoi(env) : dflt;
+    const int t = tuning().diag_threads;
     return (t >= 32 && t <= 256 && t % 32 == 0) ? t : dflt;
 }
 
 template <int VEC, int LV, int MAXT, bool REC, bool F32 = false>
 static cudaError_t launch_rows_2s_t(const crt1d_batch& in, const crt1d_out& out, int threads, cudaStream_t stream) {
+    if (!grid_ok(in.n_scen)) return cudaErrorInvalidConfiguration;
     if (no_profile_requested(out)) {
         const size_t smem = (size_t)(2 * in.n_z + 2) * sizeof(double);
         auto kd = solve_2s_rows_kernel<VEC, 10, 256, false, false, CRT_DIAG_MINB, true>;  // LV, REC, F32 play no part
-        cudaError_t ed = cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (ed != cudaSuccess) return ed;
+        if (cudaError_t ed = ensure_smem(kd, smem); ed != cudaSuccess) return ed;
         kd<<<(unsigned)in.n_scen, diag_threads(128), smem, stream>>>(in, out);
         return cudaGetLastError();
     }
     const size_t smem = rows_2s_shared_bytes(in.n_z, in.n_wl);
     auto kern = solve_2s_rows_kernel<VEC, LV, MAXT, REC, F32>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    if (cudaError_t e = ensure_smem(kern, smem); e != cudaSuccess) return e;
     kern<<<(unsigned)in.n_scen, threads, smem, stream>>>(in, out);
     return cudaGetLastError();
 }
@@ -690,12 +754,12 @@ static cudaError_t launch_rows_2s_t(const crt1d_batch& in, const crt1d_out& out,
 // 6,<=512,0|1   4,<=512,0|1   3,<=1024,1.
 template <int VEC>
 static cudaError_t launch_rows_2s(const crt1d_batch& in, const crt1d_out& out, cudaStream_t stream) {
-    int lv = 10, th = 512, rec = 1;
-    const char* env = getenv("CRT1D_B200_ROWS_CFG");
-    if (env) sscanf(env, "%d,%d,%d", &lv, &th, &rec);
+    int lv = tuning().rows_lv, th = tuning().rows_th, rec = tuning().rows_rec;
     if (th % 32 != 0 || th < 64 || th > 1024) th = 512;
-    if (in.n_z > 1024 * 2) rec = 0;
-    if (out.profile_f32) return launch_rows_2s_t<VEC, 10, 512, true, true>(in, out, th > 512 ? 512 : th, stream);
+    if (in.n_z > 1024 * 2) rec = 0;  // the per-group spacing flags cover 1024 level groups (guarded again in the kernel)
+    if (out.profile_f32)
+        return rec ? launch_rows_2s_t<VEC, 10, 512, true, true>(in, out, th > 512 ? 512 : th, stream)
+                   : launch_rows_2s_t<VEC, 10, 512, false, true>(in, out, th > 512 ? 512 : th, stream);
     if (lv == 3 && rec) return launch_rows_2s_t<VEC, 3, 1024, true>(in, out, th, stream);
     if (th > 512) th = 512;
     if (lv == 4) return rec ? launch_rows_2s_t<VEC, 4, 512, true>(in, out, th, stream)
@@ -885,12 +949,13 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_rows_kernel(const crt1d_batc
                     for (int i = 0; i < NC; ++i) cf[i * ld + c0 + v] = a[i];
                 }
                 if (SCHEME == CRT1D_SCHEME_BF && out.rho_c) out.rho_c[s * n_wl + c0 + v] = TR::rho_c(k[v]);
-                if (out.absorbed) {
+                if (out.absorbed || out.status) {
                     double gnd[NF], top[NF];
                     TR::level(sc, k[v], sm, n_z, 0, gnd);
                     TR::level(sc, k[v], sm, n_z, n_z - 1, top);
                     const double ab = absorbed_from_ends(top[0], gnd[0], top[1], gnd[1], top[2], gnd[2]);
-                    for (int q = 0; q < out.n_bw; ++q) a4[q] += out.band_w[(int64_t)q * n_wl + c0 + v] * ab;
+                    if (out.status && !isfinite(ab)) atomicOr(out.status + s, CRT1D_STATUS_NONFINITE);
+                    for (int q = 0; q < (out.absorbed ? out.n_bw : 0); ++q) a4[q] += out.band_w[(int64_t)q * n_wl + c0 + v] * ab;
                 }
             }
         }
@@ -1088,26 +1153,25 @@ static cudaError_t launch_rows_t(const crt1d_batch& in, const crt1d_out& out, in
     // 4s: its coefficient stage (eigen-system + 4x4 solve, 168 registers) is better kept as a separate phase
     // (0.82 vs 0.77 of HBM peak when fused into the first item); bl/bf/g77 fuse it (no store-free phase).
     constexpr bool FUSED = SCHEME != CRT1D_SCHEME_4S;
+    if (!grid_ok(in.n_scen)) return cudaErrorInvalidConfiguration;
     if (no_profile_requested(out)) {  // reduced-diagnostic mode: small CTAs, several per SM, level tables only
         const int n_tab = n_level_tables(SCHEME) * in.n_z;
         const int chunks = (in.n_wl / VEC + 31) / 32;
         const size_t smem_d = (size_t)(n_tab + (n_tab & 1)) * sizeof(double) + (size_t)chunks * (4 * sizeof(double) + sizeof(int));
         constexpr int DM = SCHEME == CRT1D_SCHEME_4S ? CRT_DIAG_MINB_4S : CRT_DIAG_MINB;
         auto kd = solve_rows_kernel<SCHEME, VEC, 10, 256, false, FUSED, DM, true>;  // LV, F32 play no part
-        cudaError_t e = cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
-        if (e != cudaSuccess) return e;
+        if (cudaError_t e = ensure_smem(kd, smem_d); e != cudaSuccess) return e;
         kd<<<(unsigned)in.n_scen, diag_threads(SCHEME == CRT1D_SCHEME_4S ? 64 : 128), smem_d, stream>>>(in, out, 1);
         return cudaGetLastError();
     }
     if constexpr (SCHEME == CRT1D_SCHEME_4S) {
         // Two CTAs per SM, each on half of the scenario's band chunks (half the coefficient array: 2 x ~106 KB):
         // one CTA's store-free coefficient phase (~20 % of its life) overlaps the other's level sweeps.
-        const char* env = getenv("CRT1D_B200_4S_SPLIT");
-        const int split = env ? atoi(env) : 2;
+        const int split = tuning().split_4s;
         const size_t smem2 = rows_shared_bytes<SCHEME>(in.n_z, in.n_wl, 2, VEC);
         if (split == 2 && in.n_scen * 2 <= 2147483647LL && 2 * (smem2 + 3 * 1024) <= 228u * 1024u) {
             auto kern2 = solve_rows_kernel<SCHEME, VEC, LV, MAXT / 2, F32, FUSED, 2>;
-            cudaError_t e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            cudaError_t e = ensure_smem(kern2, smem2);
             if (e != cudaSuccess) return e;
             if (out.absorbed) {
                 e = cudaMemsetAsync(out.absorbed, 0, (size_t)in.n_scen * out.n_bw * sizeof(double), stream);
@@ -1118,8 +1182,7 @@ static cudaError_t launch_rows_t(const crt1d_batch& in, const crt1d_out& out, in
         }
     }
     auto kern = solve_rows_kernel<SCHEME, VEC, LV, MAXT, F32, FUSED, 1>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    if (cudaError_t e = ensure_smem(kern, smem); e != cudaSuccess) return e;
     kern<<<(unsigned)in.n_scen, th, smem, stream>>>(in, out, 1);
     return cudaGetLastError();
 }
@@ -1134,8 +1197,8 @@ template <int SCHEME, int MAXT, int LV = 6>
 static cudaError_t launch_rows(const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream) {
     const size_t smem = rows_shared_bytes<SCHEME>(in.n_z, in.n_wl, 1, vec2 ? 2 : 1);
     int th = MAXT;
-    const char* env = getenv("CRT1D_B200_ROWS_THREADS");
-    if (env && atoi(env) >= 64 && atoi(env) <= MAXT && atoi(env) % 32 == 0) th = atoi(env);
+    const int rt = tuning().rows_threads;
+    if (rt >= 64 && rt <= MAXT && rt % 32 == 0) th = rt;
     if (out.profile_f32)
         return vec2 ? launch_rows_t<SCHEME, 2, LV, MAXT, true>(in, out, th, smem, stream)
                     : launch_rows_t<SCHEME, 1, LV, MAXT, true>(in, out, th, smem, stream);
@@ -1145,21 +1208,27 @@ static cudaError_t launch_rows(const crt1d_batch& in, const crt1d_out& out, bool
 
 // Batches with at least this many scenarios go to the row-sweep kernels (one CTA per SM needs >= n_SM
 // scenarios in flight); smaller ones (the single-scenario plugin path) use the band-tile kernel.
-static int64_t scen_kernel_min_batch() {
-    const char* env = getenv("CRT1D_B200_SCEN_MIN");
-    return env ? atoll(env) : 148;
-}
+static int64_t scen_kernel_min_batch() { return tuning().scen_min; }
+
+static cudaError_t launch_solve_impl(int scheme, const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream);
 
 cudaError_t launch_solve(int scheme, const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream) {
-    if (getenv("CRT1D_B200_FORCE_VEC1") != nullptr) vec2 = false;  // tuning experiments
+    if (out.status) {
+        cudaError_t e = cudaMemsetAsync(out.status, 0, (size_t)in.n_scen * sizeof(int32_t), stream);
+        if (e != cudaSuccess) return e;
+    }
+    return launch_solve_impl(scheme, in, out, vec2, stream);
+}
+
+static cudaError_t launch_solve_impl(int scheme, const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream) {
+    if (tuning().force_vec1) vec2 = false;  // tuning experiments
     if (scheme == CRT1D_SCHEME_2S && in.n_scen >= scen_kernel_min_batch()) {
-        const char* mode = getenv("CRT1D_B200_2S_KERNEL");  // "rows" (default) | "tile" (tuning / tests)
         const int n_chunks = (in.n_wl / (vec2 ? 2 : 1) + 31) / 32;
         const bool rows_fit = rows_2s_shared_bytes(in.n_z, in.n_wl) <= 227u * 1024u - 12288u && n_chunks <= ROWS_MAX_CHUNKS;
-        if ((mode == nullptr || mode[0] == 'r') && rows_fit)
+        if (!tuning().tile_2s && rows_fit)
             return vec2 ? launch_rows_2s<2>(in, out, stream) : launch_rows_2s<1>(in, out, stream);
     }
-    if (in.n_scen >= scen_kernel_min_batch() && getenv("CRT1D_B200_NO_ROWS") == nullptr) {
+    if (in.n_scen >= scen_kernel_min_batch() && !tuning().no_rows) {
         const size_t cap = 227u * 1024u - 2048u;  // dynamic + ~1 KB static shared memory of one CTA
         if ((in.n_wl / (vec2 ? 2 : 1) + 31) / 32 > ROWS_MAX_CHUNKS) goto tile;
         switch (scheme) {
@@ -1269,10 +1338,10 @@ cudaError_t launch_absorption(const crt1d_batch& in, const double* I_dr, const d
     if (grid <= 0 || grid > 2147483647LL) return cudaErrorInvalidConfiguration;
     const size_t smem = 2 * (size_t)in.n_z * sizeof(double);
     if (vec2) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(absorption_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaError_t e = ensure_smem(absorption_kernel<2>, smem); e != cudaSuccess) return e;
         absorption_kernel<2><<<(unsigned)grid, BLOCK, smem, stream>>>(in, I_dr, I_df_d, I_df_u, out, tiles);
     } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(absorption_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaError_t e = ensure_smem(absorption_kernel<1>, smem); e != cudaSuccess) return e;
         absorption_kernel<1><<<(unsigned)grid, BLOCK, smem, stream>>>(in, I_dr, I_df_d, I_df_u, out, tiles);
     }
     return cudaGetLastError();

@@ -158,39 +158,60 @@ class DeviceBatch:
                 self._buf(torch, "mu_bar", (S,)).copy_(tri[0].expand(S))
             else:
                 self._buf(torch, "G_int", (S, 2)).copy_(tri[1:3].expand(S, 2))
-        elif self.scheme == "bl":
+        elif self.scheme == "bl":  # the reference's solve_bl has no `tau_d_method`: always the quadrature (_solve_bl.py:35-37)
             td = self._buf(torch, "tau_d_lev", tuple(self._t["lai_lib"].shape))
-            _lib.check(lib.crt1d_tau_d(la.family_id, la.param, nq, td.numel(), self._t["lai_lib"].data_ptr(), td.data_ptr(), st))
+            _lib.check(lib.crt1d_tau_d(la.family_id, la.param, int(n_quad), td.numel(), self._t["lai_lib"].data_ptr(), td.data_ptr(), st))
         elif self.scheme == "n79":
-            dl = np.zeros_like(b.lai_lib)
-            dl[:, :-1] = b.lai_lib[:, :-1] - b.lai_lib[:, 1:]
-            dl_d = torch.as_tensor(dl).to(self.device)
+            # layer thicknesses from the lai_lib that is ON THE DEVICE (after reload() the host mirror may lag)
+            lai_d = self._t["lai_lib"]
+            dl_d = torch.zeros_like(lai_d)
+            dl_d[:, :-1] = lai_d[:, :-1] - lai_d[:, 1:]
             td = self._buf(torch, "tau_d_lev", tuple(dl_d.shape))
             _lib.check(lib.crt1d_tau_d(la.family_id, la.param, nq, td.numel(), dl_d.data_ptr(), td.data_ptr(), st))
         elif self.scheme == "zq_pa":
             M = min(100, b.n_z)
-            dl_d = torch.as_tensor(np.ascontiguousarray(b.lai_lib[:, 0] / M)).to(self.device)
+            dl_d = (self._t["lai_lib"][:, 0] / M).contiguous()
             td = torch.empty_like(dl_d)
             _lib.check(lib.crt1d_tau_d(la.family_id, la.param, int(n_quad), td.numel(), dl_d.data_ptr(), td.data_ptr(), st))
             self._buf(torch, "tau_i", (S,)).copy_(td[self._t["lai_idx"].long()])
         elif self.scheme == "zq":
-            dm = np.array([_common.mean_dlai(row) for row in b.lai_lib])
-            dm_d = torch.as_tensor(dm).to(self.device)
+            # |mean of the non-zero level differences| per profile (ref _solve_zq.py:50), from the device copy
+            d = self._t["lai_lib"][:, 1:] - self._t["lai_lib"][:, :-1]
+            nz_ = d != 0
+            dm_d = ((d * nz_).sum(dim=1) / nz_.sum(dim=1)).abs().contiguous()
             ti = torch.empty_like(dm_d)
             _lib.check(lib.crt1d_tau_d(la.family_id, la.param, int(n_quad), ti.numel(), dm_d.data_ptr(), ti.data_ptr(), st))
             idx = self._t["lai_idx"].long()
             self._buf(torch, "tau_i", (S,)).copy_(ti[idx])
             self._buf(torch, "tau_psi", (S,)).copy_(torch.exp(-K_b * dm_d[idx]))  # tau_b_fn at the mean dlai (prologue scalar)
 
-    def reload(self, pinned, tau_d_method="quad", n_quad=DEFAULT_N_QUAD):
+    def reload(self, pinned, batch=None, tau_d_method="quad", n_quad=DEFAULT_N_QUAD):
         """Copy a new batch of the SAME shape from page-locked host tensors into the existing device
         tensors (asynchronous DMA on the current stream) and redo the device prologue.  Device pointers --
-        and therefore every ctypes call struct built from them -- stay valid."""
+        and therefore every ctypes call struct built from them -- stay valid.
+
+        `batch`: the `ScenarioBatch` the pinned copies were made from (`pin_batch(batch)`); it becomes
+        `self.batch`, the host mirror that `narrow()` slices.  If omitted, the mirror is rebuilt from the pinned
+        tensors.  The prologue itself reads only device tensors, so the kernels never see a mix of old and new
+        tables."""
+        import copy
+
         torch = _torch()
+        for k in BATCH_ARRAYS:
+            if tuple(pinned[k].shape) != tuple(self._t[k].shape):
+                raise ValueError(f"reload(): {k} has shape {tuple(pinned[k].shape)}, the resident batch {tuple(self._t[k].shape)}")
+        if batch is None:
+            batch = copy.copy(self.batch)
+            for k in BATCH_ARRAYS:
+                setattr(batch, k, pinned[k].numpy())
+        elif (batch.n_scen, batch.n_z, batch.n_wl) != (self.batch.n_scen, self.batch.n_z, self.batch.n_wl):
+            raise ValueError("reload(): the new batch must have the shape of the resident one")
+        self.batch = batch
         with torch.cuda.device(self.device):
             for k in BATCH_ARRAYS:
                 self._t[k].copy_(pinned[k], non_blocking=True)
             self._device_prologue(torch, tau_d_method, n_quad)
+        self.cbatch.mla_deg = float(batch.mla)
         return self
 
     def _make_cbatch(self):
@@ -257,6 +278,8 @@ class OutputBuffers:
                 raise ValueError("band_w must be (1..4, n_wl)")
             self.band_w = torch.as_tensor(bw).to(device)
             self.t["absorbed"] = torch.empty((self.capacity, bw.shape[0]), **f64)
+        # per-scenario status words (CRT1D_STATUS_NONFINITE): zeroed by the library at every launch
+        self.t["status"] = torch.zeros((self.capacity,), dtype=torch.int32, device=device)
 
     def cout(self, n_scen):
         if n_scen > self.capacity:
@@ -274,6 +297,7 @@ class OutputBuffers:
             co.n_bw = self.band_w.shape[0]
             co.absorbed = self.t["absorbed"].data_ptr()
         co.profile_f32 = 1 if self.profile_f32 else 0
+        co.status = self.t["status"].data_ptr()
         return co
 
     def bytes_written_per_scenario(self):
@@ -304,11 +328,27 @@ def solve(batch, scheme, *, device=None, prologue="device", band_w=None, extras=
     return ob.t
 
 
+def _profile_f64(torch, t, shape, device, name):
+    """The kernels read raw pointers as contiguous float64 (S, n_z, n_wl) on `device`: check, or convert where
+    that is exact (float32 storage -> float64, non-contiguous views -> packed copies)."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch tensor in HBM, got {type(t).__name__}")
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+    if t.device != torch.device(device):
+        raise ValueError(f"{name} lives on {t.device}, the batch on {device}")
+    if t.dtype not in (torch.float64, torch.float32):
+        raise TypeError(f"{name} must be float64 (or float32 storage), got {t.dtype}")
+    return t.to(torch.float64).contiguous()
+
+
 def calc_absorption(dbatch: DeviceBatch, I_dr, I_df_d, I_df_u):
     """Layerwise absorption of every scenario (replaces `_calc_absorption`, ref model.py:573-647).
     Inputs/outputs are torch tensors in HBM; outputs (S, n_z-1, n_wl)."""
     torch = _torch()
     S, nz, nw = dbatch.batch.n_scen, dbatch.batch.n_z, dbatch.batch.n_wl
+    I_dr, I_df_d, I_df_u = (_profile_f64(torch, t, (S, nz, nw), dbatch.device, k)
+                            for t, k in ((I_dr, "I_dr"), (I_df_d, "I_df_d"), (I_df_u, "I_df_u")))
     names = ("aI", "aI_df", "aI_dr", "aI_sh", "aI_sl", "aI_df_sl", "aI_df_sh")
     outs = {k: torch.empty((S, nz - 1, nw), dtype=torch.float64, device=dbatch.device) for k in names}
     ao = _abi.AbsorptionOut()
@@ -330,7 +370,11 @@ def energy_balance(I_dr, I_df_d, I_df_u, band_w):
     `(n_bw, n_wl)` weights (e.g. `spectra.band_weights`, or photon-flux weights).  Returns a tensor
     `(S, n_bw, 4)` with columns `EBAL_COLUMNS`; `incoming - outgoing - soil` closes against `canopy abs`."""
     torch = _torch()
+    if not isinstance(I_dr, torch.Tensor) or I_dr.dim() != 3:
+        raise ValueError("I_dr must be a (S, n_z, n_wl) torch tensor")
     S, nz, nw = I_dr.shape
+    I_dr, I_df_d, I_df_u = (_profile_f64(torch, t, (S, nz, nw), I_dr.device, k)
+                            for t, k in ((I_dr, "I_dr"), (I_df_d, "I_df_d"), (I_df_u, "I_df_u")))
     bw = np.ascontiguousarray(np.atleast_2d(np.asarray(band_w, dtype=np.float64)))
     if bw.shape[1] != nw or not 1 <= bw.shape[0] <= 4:
         raise ValueError("band_w must be (1..4, n_wl)")

@@ -109,6 +109,8 @@ class Model:
                 self._p[k] = v
                 if k == "G_fn" and "leaf_angle" not in kwargs:
                     self._p.pop("leaf_angle", None)  # a custom callable invalidates the parametric family
+                if k == "leaf_angle" and "G_fn" not in kwargs and v is not None:
+                    self._p["G_fn"] = v.G_fn  # one canopy for run() (G_fn) and run_batch() (leaf_angle)
             self._check_inputs()
         except Exception:
             warnings.warn(
@@ -158,6 +160,15 @@ class Model:
         assert p["wl"].size == p["dwl"].size
         p["wle"] = np.r_[p["wl"][0] - 0.5 * p["dwl"][0], p["wl"] + 0.5 * p["dwl"]]
         G_fn = p["G_fn"]
+        la = p.get("leaf_angle")
+        if la is not None:  # the plugin path uses G_fn, the batched path the parametric family: they must be one canopy
+            probe = (0.0, 0.4, 0.9, 1.3)
+            if not np.allclose([la.G_fn(a) for a in probe], [G_fn(a) for a in probe], rtol=1e-12, atol=0.0):
+                warnings.warn(
+                    "`leaf_angle` does not describe the same canopy as `G_fn`; dropping `leaf_angle` "
+                    "(the batched path needs `update_p(leaf_angle=...)`, which also sets `G_fn`)."
+                )
+                del p["leaf_angle"]
         p["K_b_fn"] = lambda psi_: G_fn(psi_) / np.cos(psi_)
         p["G"] = G_fn(psi)
         p["K_b"] = p["K_b_fn"](psi)

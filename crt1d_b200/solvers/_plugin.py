@@ -26,10 +26,11 @@ def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def solve_batch_host(batch, scheme, prologue, *, mu_s=0.501, band_w=None, device=None, alloc=np.empty):
+def solve_batch_host(batch, scheme, prologue, *, mu_s=0.501, band_w=None, device=None, alloc=np.empty, status=False):
     """`crt1d_solve_host` on a ScenarioBatch with a host prologue dict; returns numpy arrays with a
     leading scenario axis.  `alloc(shape)` makes the float64 output arrays (default: fresh pageable numpy
-    arrays like the reference's; a page-locked allocator lets the D2H copies run at PCIe speed)."""
+    arrays like the reference's; a page-locked allocator lets the D2H copies run at PCIe speed).
+    `status=True` adds the per-scenario int32 status words (`_abi.STATUS_NONFINITE`) as `out["status"]`."""
     lib = _lib.load()
     S, nz, nw = batch.n_scen, batch.n_z, batch.n_wl
     keep = {}
@@ -66,9 +67,12 @@ def solve_batch_host(batch, scheme, prologue, *, mu_s=0.501, band_w=None, device
         co.n_bw = keep["band_w"].shape[0]
         out["absorbed"] = np.empty((S, co.n_bw))
         co.absorbed = _ptr(out["absorbed"])
+    if status:
+        out["status"] = np.zeros(S, dtype=np.int32)
+        co.status = _ptr(out["status"])
     rc = lib.crt1d_solve_host(_abi.SCHEME_IDS[scheme], ctypes.byref(cb), ctypes.byref(co),
                               _device_index() if device is None else int(device))
-    _lib.check(rc)
+    _lib.check(rc)  # raises on errors; warns (RuntimeWarning) when some scenario is non-finite
     return out
 
 

@@ -134,7 +134,7 @@ class SweepRunner:
 
         eng = self.engine
         if self.db is not None and self.pinned is not None and self._calls is not None:
-            self.db.reload(self.pinned, n_quad=self.n_quad)  # same shapes: DMA into place, call structs stay valid
+            self.db.reload(self.pinned, self.spec, n_quad=self.n_quad)  # same shapes: DMA into place, call structs stay valid
             return self
         self.db = eng.DeviceBatch(self.spec, self.scheme, device=self.device, prologue="device", n_quad=self.n_quad,
                                   pinned=self.pinned)

@@ -16,8 +16,9 @@
  *   - `crt1d_solve*` take DEVICE pointers and enqueue work on `stream` (a cudaStream_t, may be NULL for
  *     the legacy default stream); they never allocate, free or synchronise.  `crt1d_solve_host` takes HOST
  *     pointers, does H2D + solve + D2H itself and returns when the results are in the caller's buffers.
- *   - Return value: CRT1D_OK (0) or a negative error code; `crt1d_last_error()` gives the message of the
- *     last failure on the calling thread.  No entry point aborts, throws, or falls back to the CPU.
+ *   - Return value: CRT1D_OK (0) or a negative error code (`crt1d_solve_host` may also return the positive
+ *     finding CRT1D_NONFINITE); `crt1d_last_error()` gives the message of the last failure on the calling
+ *     thread.  No entry point aborts, throws, or falls back to the CPU.
  *   - Re-entrant; no global mutable state except a per-thread error string and (host path only) a
  *     per-thread device workspace that is grown on demand and released by `crt1d_release_workspace`.
  */
@@ -30,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CRT1D_ABI_VERSION 3
+#define CRT1D_ABI_VERSION 4
 
 /* exported-symbol marker (the library is built with -fvisibility=hidden) */
 #if defined(__GNUC__)
@@ -47,6 +48,13 @@ extern "C" {
 #define CRT1D_ERR_CUDA (-4)          /* a CUDA runtime call failed; see crt1d_last_error() */
 #define CRT1D_ERR_NO_DEVICE (-5)     /* no CUDA device visible */
 #define CRT1D_ERR_NO_MEMORY (-6)     /* device workspace allocation failed (host path) */
+/* positive = results delivered, with a finding (host path only; the asynchronous device path reports it in
+ * crt1d_out.status): at least one scenario holds a non-finite value (NaN / Inf inputs, r + t = 0 in 2s, ...).
+ * The reference returns such arrays silently (numpy RuntimeWarning at most). */
+#define CRT1D_NONFINITE 1
+
+/* crt1d_out.status bits, per scenario */
+#define CRT1D_STATUS_NONFINITE 1 /* a non-finite value at the ground or top level of some band column */
 
 /* scheme ids -- the reference's scheme names (crt1d/solvers/__init__.py:17-30) */
 #define CRT1D_SCHEME_2S 0   /* Dickinson-Sellers two-stream         crt1d/solvers/_solve_2s.py:11-163  */
@@ -138,6 +146,11 @@ typedef struct crt1d_out {
      * Halves the HBM traffic of the write-bound schemes.  Not available for n79 and zq
      * (CRT1D_ERR_UNSUPPORTED): they park float64 elimination checkpoints in the profile arrays. */
     int32_t profile_f32;
+
+    /* optional per-scenario status word [S] (int32; NULL = not wanted): the library zeroes it on the launch
+     * stream and the kernels OR in CRT1D_STATUS_* bits.  Checked where every column is evaluated anyway: the
+     * ground and top levels (all fields; a NaN/Inf coefficient reaches every level of its column). */
+    int32_t* status;
 } crt1d_out;
 
 /* ---- library info ---------------------------------------------------------------------------- */
@@ -159,12 +172,18 @@ CRT1D_API int crt1d_solve_zq(const crt1d_batch* in, const crt1d_out* out, void* 
 CRT1D_API int crt1d_solve_zq_pa(const crt1d_batch* in, const crt1d_out* out, void* stream); /* replaces solve_zq_pa _solve_zq_pa.py:24 */
 
 /* ---- solver: host pointers, synchronous (H2D + kernels + D2H inside) -------------------------
- * Any host memory works.  Output buffers that are page-locked (cudaHostAlloc / cudaHostRegister) receive the
- * profiles at PCIe speed (measured 49 GB/s, 1.5e9 layer.band/s for 2s); freshly allocated pageable buffers are
- * bound by first-touch page faults (4.8 GB/s).  Index arrays are not range-checked on this side of the ABI:
- * every *_idx[s] must be a valid row of its library. */
+ * Any host memory works and any batch size: the scenarios go through two 128 MB device slots on two streams
+ * (kernel of chunk k+1 overlaps the D2H of chunk k), so the call is PCIe-bound and not limited by HBM capacity.
+ * Page-locked output buffers (cudaHostAlloc / cudaHostRegister) receive the DMA directly; pageable buffers are
+ * filled from a page-locked staging ring by a few copy threads (first-touch page faults are their limit).
+ * Returns CRT1D_NONFINITE (> 0) when results were delivered but some scenario holds NaN/Inf (out->status, if set,
+ * says which).  Index arrays are not range-checked on this side of the ABI: every *_idx[s] must be a valid row
+ * of its library. */
 CRT1D_API int crt1d_solve_host(int scheme, const crt1d_batch* in_host, const crt1d_out* out_host, int device);
-CRT1D_API int crt1d_release_workspace(void); /* frees the calling thread's cached device workspace */
+CRT1D_API int crt1d_release_workspace(void); /* frees the calling thread's cached device workspace, streams and staging ring */
+/* test / tuning hook: re-read the CRT1D_B200_* kernel-selection environment variables (they are read once, when
+ * the library is loaded; no getenv on the launch path). */
+CRT1D_API int crt1d_reload_tuning(void);
 
 /* ---- layer absorption  (replaces _calc_absorption, crt1d/model.py:573-647) -------------------
  * Inputs: profiles [S][n_z][n_wl], K_b [S], lai/leaf libraries + indices as in crt1d_batch.

@@ -26,3 +26,14 @@ def default_p():
     p["G"] = G_fn(p["psi"])
     p["K_b"] = p["K_b_fn"](p["psi"])
     return p
+
+
+@pytest.fixture(autouse=True)
+def _restore_kernel_tuning():
+    """Set up before `monkeypatch`, so finalised after its undo: make the library re-read the CRT1D_B200_*
+    variables once a test's overrides are gone (they are cached at load time; see util.tune)."""
+    yield
+    from crt1d_b200 import _lib
+
+    if _lib._lib is not None:
+        _lib._lib.crt1d_reload_tuning()

@@ -12,6 +12,7 @@ from util import VARIANTS
 from util import assert_close
 from util import assert_close_4s
 from util import golden
+from util import tune
 from util import variant_case
 
 pytestmark = pytest.mark.gpu
@@ -155,8 +156,8 @@ def test_batched_sweep_sample_matches_reference_golden(kernel, monkeypatch):
     kernels (the row-sweep kernel that large batches use is forced on for this small one)."""
     import torch
 
-    monkeypatch.setenv("CRT1D_B200_2S_KERNEL", kernel)
-    monkeypatch.setenv("CRT1D_B200_SCEN_MIN", "1")
+    tune(monkeypatch, "CRT1D_B200_2S_KERNEL", kernel)
+    tune(monkeypatch, "CRT1D_B200_SCEN_MIN", "1")
 
     from crt1d_b200 import engine
     from crt1d_b200 import sweep
@@ -451,12 +452,12 @@ def test_large_batch_kernels_equal_tile_kernel(mode, cfg, monkeypatch):
     sub = spec.slice(431900, 431900 + 160)
     srel = sigma_rel_2s(sub, common.mu_bar_fn(sub.leaf_angle.G_fn))
     bw = np.stack([np.ones(spec.n_wl), np.linspace(0, 1, spec.n_wl)])
-    monkeypatch.setenv("CRT1D_B200_2S_KERNEL", "tile")
+    tune(monkeypatch, "CRT1D_B200_2S_KERNEL", "tile")
     a = engine.solve(sub, "2s", band_w=bw)
     torch.cuda.synchronize()
-    monkeypatch.setenv("CRT1D_B200_2S_KERNEL", mode)
-    monkeypatch.setenv("CRT1D_B200_SCEN_MIN", "1")
-    monkeypatch.setenv("CRT1D_B200_ROWS_CFG", cfg)
+    tune(monkeypatch, "CRT1D_B200_2S_KERNEL", mode)
+    tune(monkeypatch, "CRT1D_B200_SCEN_MIN", "1")
+    tune(monkeypatch, "CRT1D_B200_ROWS_CFG", cfg)
     b = engine.solve(sub, "2s", band_w=bw)
     torch.cuda.synchronize()
     assert torch.equal(a["I_dr"], b["I_dr"])
@@ -475,9 +476,9 @@ def test_large_batch_kernels_equal_tile_kernel(mode, cfg, monkeypatch):
     odd.wl, odd.dwl = sub.wl[:333], sub.dwl[:333]
     odd.lai_lib = np.ascontiguousarray(sub.lai_lib * np.linspace(1.0, 0.6, sub.n_z) ** 0.5)
     srel_o = srel[:150, :333]
-    monkeypatch.setenv("CRT1D_B200_2S_KERNEL", "tile")
+    tune(monkeypatch, "CRT1D_B200_2S_KERNEL", "tile")
     a = engine.solve(odd, "2s")
-    monkeypatch.setenv("CRT1D_B200_2S_KERNEL", mode)
+    tune(monkeypatch, "CRT1D_B200_2S_KERNEL", mode)
     b = engine.solve(odd, "2s")
     torch.cuda.synchronize()
     for k in ("I_df_d", "I_df_u", "F"):
@@ -538,10 +539,10 @@ def test_rows_kernel_other_schemes(scheme, monkeypatch):
     spec = sweep.synthetic_sweep_spec(seed=0)
     sub = spec.slice(255500, 255500 + 150)
     bw = np.stack([np.ones(spec.n_wl), np.linspace(0, 1, spec.n_wl)])
-    monkeypatch.setenv("CRT1D_B200_NO_ROWS", "1")
+    tune(monkeypatch, "CRT1D_B200_NO_ROWS", "1")
     a = engine.solve(sub, scheme, band_w=bw)
     torch.cuda.synchronize()
-    monkeypatch.delenv("CRT1D_B200_NO_ROWS")
+    tune(monkeypatch, "CRT1D_B200_NO_ROWS", None)
     b = engine.solve(sub, scheme, band_w=bw)
     torch.cuda.synchronize()
     # 4s: the 4x4 boundary solve amplifies FMA-contraction differences between instantiations (~1e-11 seen)
@@ -570,9 +571,9 @@ def test_rows_kernel_other_schemes(scheme, monkeypatch):
     for k in ("leaf_r_lib", "leaf_t_lib", "soil_r_lib", "I_dr0_lib", "I_df0_lib"):
         setattr(odd, k, np.ascontiguousarray(getattr(sub, k)[:, :401]))
     odd.wl, odd.dwl = sub.wl[:401], sub.dwl[:401]
-    monkeypatch.setenv("CRT1D_B200_NO_ROWS", "1")
+    tune(monkeypatch, "CRT1D_B200_NO_ROWS", "1")
     a = engine.solve(odd, scheme)
-    monkeypatch.delenv("CRT1D_B200_NO_ROWS")
+    tune(monkeypatch, "CRT1D_B200_NO_ROWS", None)
     b = engine.solve(odd, scheme)
     torch.cuda.synchronize()
     for k in a:
@@ -706,7 +707,9 @@ def test_float32_profile_storage(scheme, n_scen):
     b = engine.solve(db, scheme, band_w=bw, profile_dtype=torch.float32)
     torch.cuda.synchronize()
     for k in a:
-        if k in ("absorbed", "rho_c"):
+        if k == "status":
+            assert int(b[k].abs().sum()) == 0 and int(a[k].abs().sum()) == 0
+        elif k in ("absorbed", "rho_c"):
             assert b[k].dtype == torch.float64 and torch.equal(a[k], b[k]), k
         else:
             assert b[k].dtype == torch.float32 and b[k].shape == a[k].shape
@@ -739,7 +742,7 @@ def test_host_pointer_batch_entry_point(default_p):
     bw = np.stack([np.ones(b.n_wl), np.arange(b.n_wl) / b.n_wl])
     for scheme in FAST + ("4s",):
         pro = engine.host_prologue(b, scheme)
-        host = solve_batch_host(b, scheme, pro, band_w=bw)
+        host = solve_batch_host(b, scheme, pro, band_w=bw, status=True)
         dev = engine.solve(engine.DeviceBatch(b, scheme, prologue=pro), scheme, band_w=bw)
         torch.cuda.synchronize()
         assert set(host) == set(dev)
@@ -772,3 +775,232 @@ def test_smear_tuv_kernel_and_rebinned_batch(default_p):
     res = engine.solve(rb, "2s")
     ref = oracle.run("2s", rb.scenario_params(3))
     assert_close(res["F"][3].cpu().numpy(), ref["F"], RTOL, "2s on the rebinned batch")
+
+
+# ---------------------------------------------------------------------------------- 4s: omega -> 1, resonances
+def _rows_batch_of(q, n_scen, leaf_angle):
+    """`n_scen` copies of one reference-style case as a batch (>= 148 scenarios select the row-sweep kernels)."""
+    from crt1d_b200.scenarios import ScenarioBatch
+
+    return ScenarioBatch(
+        psi=np.full(n_scen, q["psi"]), lai_lib=q["lai"], leaf_r_lib=q["leaf_r"], leaf_t_lib=q["leaf_t"],
+        soil_r_lib=q["soil_r"], I_dr0_lib=q["I_dr0_all"], I_df0_lib=q["I_df0_all"], lai_idx=0, leaf_idx=0,
+        soil_idx=0, sky_idx=0, leaf_angle=leaf_angle, mla=57.0)
+
+
+def test_4s_edge_cases_match_reference(default_p):
+    """4s where a closed form needs care and the reference (an ODE integration, ref _solve_4s.py:48-97, 235-262) does
+    not: omega in {0.99 ... 1 - 1e-9}, omega* (the smaller eigenvalue^2 crosses zero; oscillatory mode beyond) and
+    kappa = lambda_k, for 3 zenith angles x 2 mu_s.  Plugin path (band-tile kernel) and a 160-scenario batch
+    (row-sweep kernel, split CTAs) vs reference-generated fixtures under the two-oracle rule."""
+    import torch
+
+    import crt1d_b200 as crt
+    from crt1d_b200 import engine
+    from util import assert_close_4s_shipped
+    from util import edge_4s_fixture_cases
+
+    for tag, mu_s, q, ship, tight in edge_4s_fixture_cases():
+        sol = crt.solvers.solve_4s(**_args("4s", q), mu_s=mu_s)
+        for k in tight:
+            assert np.all(np.isfinite(sol[k])), (tag, k)
+            assert_close_4s(sol[k], tight[k], f"plugin {tag} tight {k}")
+            assert_close_4s_shipped(sol[k], ship[k], f"plugin {tag} shipped {k}")
+        b = _rows_batch_of(q, 160, default_p["leaf_angle"])
+        pro = engine.host_prologue(b, "4s", mu_s=mu_s)
+        res = engine.solve(engine.DeviceBatch(b, "4s", prologue=pro, mu_s=mu_s), "4s", band_w=np.ones((1, b.n_wl)))
+        torch.cuda.synchronize()
+        assert int(res["status"].abs().sum()) == 0, tag
+        for i in (0, 77, 159):
+            for k in tight:
+                assert_close_4s(res[k][i].cpu().numpy(), tight[k], f"rows {tag}[{i}] tight {k}")
+        ends = (res["I_dr"][:, -1] - res["I_dr"][:, 0]) + (res["I_df_d"][:, -1] - res["I_df_d"][:, 0]) + (res["I_df_u"][:, 0] - res["I_df_u"][:, -1])
+        assert torch.allclose(ends.sum(1), res["absorbed"][:, 0], rtol=1e-11, atol=0), tag
+
+
+@pytest.mark.parametrize("n_scen", [1, 160])
+def test_4s_random_scenarios_match_reference(n_scen):
+    """Seeded random 4s scenarios (omega up to 1, zenith to 86 deg, thin / deep / irregular canopies) vs the
+    reference at tight tolerance (fixture ref_4s_random.npz), tile kernel (n_scen = 1 per scenario) and row-sweep
+    kernel (each scenario replicated to a 160-scenario batch)."""
+    import torch
+
+    from crt1d_b200 import engine
+    from util import EDGE_4S_MU_S
+    from util import random_4s_batch
+
+    g = golden("ref_4s_random.npz")
+    b = random_4s_batch()
+    for mu_s in EDGE_4S_MU_S:
+        for s in range(b.n_scen):
+            q = b.scenario_params(s)
+            bb = _rows_batch_of(q, n_scen, b.leaf_angle)
+            pro = engine.host_prologue(bb, "4s", mu_s=mu_s)
+            res = engine.solve(engine.DeviceBatch(bb, "4s", prologue=pro, mu_s=mu_s), "4s")
+            torch.cuda.synchronize()
+            for k in ("I_dr", "I_df_d", "I_df_u", "F"):
+                ref = g[f"mus{int(round(mu_s * 1000))}__s{s}__{k}"]
+                assert_close_4s(res[k][n_scen - 1].cpu().numpy(), ref, f"random 4s mu_s={mu_s} [{s}].{k}")
+
+
+# ---------------------------------------------------------------------------------- status words
+@pytest.mark.parametrize("n_scen", [6, 160])
+def test_nonfinite_status_flags(n_scen, default_p):
+    """A NaN in one leaf-spectrum row: exactly the scenarios that use the row are flagged (device path, tile and
+    row-sweep kernels, every scheme), and the host path returns CRT1D_NONFINITE (a RuntimeWarning in Python) with
+    the same status words; clean batches report 0."""
+    import torch
+
+    from crt1d_b200 import _abi
+    from crt1d_b200 import engine
+    from crt1d_b200.scenarios import ScenarioBatch
+    from crt1d_b200.solvers._plugin import solve_batch_host
+
+    nz = 12
+    r = np.stack([default_p["leaf_r"], default_p["leaf_r"]])
+    r[1, 40] = np.nan
+    idx = np.arange(n_scen) % 3 == 1
+    b = ScenarioBatch(
+        psi=np.radians(np.linspace(5, 70, n_scen)), lai_lib=np.linspace(1, 0, nz) * 3.0, leaf_r_lib=r,
+        leaf_t_lib=np.stack([default_p["leaf_t"]] * 2), soil_r_lib=default_p["soil_r"], I_dr0_lib=default_p["I_dr0_all"],
+        I_df0_lib=default_p["I_df0_all"], lai_idx=0, leaf_idx=idx.astype(np.int32), soil_idx=0, sky_idx=0,
+        leaf_angle=default_p["leaf_angle"], mla=57.0)
+    for scheme in FAST + ("4s",):
+        pro = engine.host_prologue(b, scheme, **({"tau_d_method": "9sky"} if scheme == "n79" else {}))
+        res = engine.solve(engine.DeviceBatch(b, scheme, prologue=pro), scheme)
+        torch.cuda.synchronize()
+        st = res["status"].cpu().numpy()
+        assert np.array_equal(st != 0, idx), (scheme, st)
+        assert np.all(st[idx] == _abi.STATUS_NONFINITE)
+        bad = ~torch.isfinite(res["F"]).reshape(n_scen, -1).all(dim=1)
+        assert np.array_equal(bad.cpu().numpy(), idx), scheme
+        if n_scen == 6:
+            with pytest.warns(RuntimeWarning, match="non-finite"):
+                host = solve_batch_host(b, scheme, pro, status=True)
+            assert np.array_equal(host["status"], st), scheme
+            clean = solve_batch_host(b.slice(0, 1), scheme, {k: (v[:1] if np.ndim(v) and len(v) == n_scen else v) for k, v in pro.items()}, status=True)
+            assert clean["status"][0] == 0
+
+
+# ---------------------------------------------------------------------------------- host path: chunks, pinned / pageable
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_path_chunked_pipeline(pinned):
+    """`crt1d_solve_host` on a batch whose profiles (1.0 GB) span several 128 MB device slots: every profile of every
+    scenario arrives, in pageable arrays (staging ring + copy threads) and in page-locked arrays (direct DMA), and
+    equals the device-pointer path bit for bit."""
+    import torch
+
+    from crt1d_b200 import engine
+    from crt1d_b200 import sweep
+    from crt1d_b200.solvers._plugin import solve_batch_host
+
+    spec = sweep.synthetic_sweep_spec(seed=0)
+    idx = np.arange(64) * 15625 + 77
+    sub = spec.slice(0, 64)
+    sub.psi = spec.psi[idx]
+    for k in ("lai_idx", "leaf_idx", "soil_idx", "sky_idx"):
+        setattr(sub, k, getattr(spec, k)[idx].copy())
+    bw = np.ones((2, spec.n_wl))
+    pro = engine.host_prologue(sub, "2s")
+    keep = []
+
+    def alloc(shape):
+        if not pinned:
+            return np.empty(shape)
+        t = torch.empty(shape, dtype=torch.float64).pin_memory()
+        keep.append(t)
+        return t.numpy()
+
+    host = solve_batch_host(sub, "2s", pro, band_w=bw, alloc=alloc, status=True)
+    dev = engine.solve(engine.DeviceBatch(sub, "2s", prologue=pro), "2s", band_w=bw)
+    torch.cuda.synchronize()
+    for k in host:
+        assert np.array_equal(host[k], dev[k].cpu().numpy()), k
+    # a second call reuses the workspace, streams and ring
+    host2 = solve_batch_host(sub, "2s", pro, band_w=bw, alloc=alloc)
+    assert np.array_equal(host2["F"], host["F"])
+
+
+# ---------------------------------------------------------------------------------- ADVICE r1: reload, input checks
+@pytest.mark.parametrize("scheme", ["n79", "zq", "zq_pa", "bl"])
+def test_reload_with_a_different_batch(scheme, default_p):
+    """`DeviceBatch.reload` with DIFFERENT LAI profiles: the prologue (tau_d per layer, tau_i, tau_psi) must follow the
+    tables that were uploaded, i.e. equal a fresh DeviceBatch of the new batch."""
+    import copy
+
+    import torch
+
+    from crt1d_b200 import engine
+    from crt1d_b200.scenarios import ScenarioBatch
+
+    nz = 20
+    b1 = ScenarioBatch(
+        psi=np.radians([20.0, 60.0]), lai_lib=np.stack([np.linspace(1, 0, nz) * 3.0, np.linspace(1, 0, nz) * 5.0]),
+        leaf_r_lib=default_p["leaf_r"], leaf_t_lib=default_p["leaf_t"], soil_r_lib=default_p["soil_r"],
+        I_dr0_lib=default_p["I_dr0_all"], I_df0_lib=default_p["I_df0_all"], lai_idx=[0, 1], leaf_idx=0, soil_idx=0,
+        sky_idx=0, leaf_angle=default_p["leaf_angle"], mla=57.0)
+    b2 = copy.copy(b1)
+    b2.lai_lib = np.stack([np.linspace(1, 0, nz) ** 1.7 * 1.5, np.linspace(1, 0, nz) * 7.0])
+    b2.psi = np.radians([35.0, 10.0])
+    db = engine.DeviceBatch(b1, scheme)
+    engine.solve(db, scheme)
+    db.reload(engine.pin_batch(b2), b2)
+    a = engine.solve(db, scheme)
+    fresh = engine.solve(engine.DeviceBatch(b2, scheme), scheme)
+    torch.cuda.synchronize()
+    for k in fresh:
+        assert torch.equal(a[k], fresh[k]), f"{scheme}.{k} after reload"
+    with pytest.raises(ValueError):
+        db.reload(engine.pin_batch(b2.slice(0, 1)), b2.slice(0, 1))
+
+
+def test_absorption_and_ebal_input_checks(default_p):
+    """float32-stored or non-contiguous profiles are converted (exactly) before the kernels read raw pointers; wrong
+    shapes / devices / dtypes raise instead of being reinterpreted."""
+    import torch
+
+    import crt1d_b200 as crt
+    from crt1d_b200 import engine
+
+    m = crt.Model("2s", nlayers=30)
+    db = engine.DeviceBatch(m.scenario_batch(), "2s")
+    a = engine.solve(db, "2s")
+    ref = engine.calc_absorption(db, a["I_dr"], a["I_df_d"], a["I_df_u"])
+    f32 = engine.solve(db, "2s", profile_dtype=torch.float32)
+    got = engine.calc_absorption(db, f32["I_dr"], f32["I_df_d"], f32["I_df_u"])
+    want = engine.calc_absorption(db, f32["I_dr"].double(), f32["I_df_d"].double(), f32["I_df_u"].double())
+    torch.cuda.synchronize()
+    assert torch.equal(got["aI"], want["aI"])
+    tr = {k: a[k].transpose(1, 2).contiguous().transpose(1, 2) for k in ("I_dr", "I_df_d", "I_df_u")}  # same values, strided
+    assert not tr["I_dr"].is_contiguous()
+    got = engine.calc_absorption(db, tr["I_dr"], tr["I_df_d"], tr["I_df_u"])
+    assert torch.equal(got["aI_sl"], ref["aI_sl"])
+    bw = np.ones((1, m.nwl))
+    e0 = engine.energy_balance(a["I_dr"], a["I_df_d"], a["I_df_u"], bw)
+    e1 = engine.energy_balance(tr["I_dr"], tr["I_df_d"], tr["I_df_u"], bw)
+    assert torch.equal(e0, e1)
+    with pytest.raises(ValueError):
+        engine.calc_absorption(db, a["I_dr"][:, :-1], a["I_df_d"], a["I_df_u"])
+    with pytest.raises(TypeError):
+        engine.calc_absorption(db, a["I_dr"].cpu().numpy(), a["I_df_d"], a["I_df_u"])
+    with pytest.raises(TypeError):
+        engine.calc_absorption(db, a["I_dr"].to(torch.int64), a["I_df_d"], a["I_df_u"])
+
+
+def test_model_leaf_angle_and_G_fn_stay_one_canopy():
+    """update_p(leaf_angle=...) also replaces G_fn (run() and run_batch() solve the same canopy); a G_fn that
+    contradicts leaf_angle drops the family with a warning."""
+    import crt1d_b200 as crt
+    from crt1d_b200.leaf_angle import LeafAngle
+
+    m = crt.Model("2s", nlayers=20)
+    la = LeafAngle("spherical")
+    m.update_p(leaf_angle=la)
+    assert m._p["G_fn"](0.7) == la.G_fn(0.7) == 0.5
+    one = m.run().out["F"]
+    batch = m.run_batch(m.scenario_batch())
+    assert_close(batch["F"][0], one, 1e-12, "run vs run_batch after update_p(leaf_angle)")
+    with pytest.warns(UserWarning, match="same canopy"):
+        m._p["G_fn"] = LeafAngle("horizontal").G_fn
+        m._check_inputs()
+    assert "leaf_angle" not in m._p

@@ -13,6 +13,9 @@ from util import RTOL_4S_TIGHT
 from util import VARIANTS
 from util import assert_close
 from util import assert_close_4s
+from util import assert_close_4s_shipped
+from util import edge_4s_case
+from util import edge_4s_fixture_cases
 from util import deep_case as _deep_case
 from util import golden
 from util import variant_case
@@ -218,3 +221,55 @@ def test_smear_tuv_device_function_matches_reference():
                             ("c_x", "c_y", "c_bins", "c_res")):
         got = hostcheck.smear_tuv(g[x], g[y], g[bins])
         assert np.array_equal(got, g[res]), bins
+
+
+@pytest.mark.parametrize("vec", (1, 2))
+def test_4s_edge_cases_vs_reference(vec):
+    """omega -> 1 (the smaller eigenvalue^2 of the four-stream operator vanishes at omega* = 0.99536 and is negative
+    beyond: oscillatory mode), omega* itself, and kappa = lambda_k resonances -- against reference-generated
+    fixtures (tests/golden/make_golden_4s_edge.py): the reference integrates the ODE (ref _solve_4s.py:48-97,
+    235-262) and is finite and smooth through all of them."""
+    for tag, mu_s, q, ship, tight in edge_4s_fixture_cases():
+        n = q["leaf_r"].size
+        if vec == 2 and n % 2:
+            q = {k: (v[:n - 1].copy() if isinstance(v, np.ndarray) and v.shape == (n,) else v) for k, v in q.items()}
+            ship = {k: v[:, :n - 1] for k, v in ship.items()}
+            tight = {k: v[:, :n - 1] for k, v in tight.items()}
+        sol = _solve(q, "4s", vec=vec, mu_s=mu_s)
+        for k in tight:
+            assert np.all(np.isfinite(sol[k])), (tag, k)
+            assert_close_4s(sol[k], tight[k], f"{tag} tight {k}")
+            assert_close_4s_shipped(sol[k], ship[k], f"{tag} shipped {k}")
+
+
+def test_4s_edge_inputs_match_fixture():
+    """The fixture's stored inputs are what util.edge_4s_case builds (root finding for omega* and the resonances)."""
+    for tag, mu_s, q, _, _ in edge_4s_fixture_cases():
+        psi_deg = float(tag.split("_")[0][3:])
+        q2 = edge_4s_case(psi_deg, mu_s)
+        for k in ("lai", "soil_r", "I_dr0_all", "I_df0_all"):
+            assert np.array_equal(q[k], q2[k]), (tag, k)
+        for k in ("leaf_r", "leaf_t"):
+            np.testing.assert_allclose(q[k], q2[k], rtol=1e-13, err_msg=f"{tag} {k}")
+
+
+def test_4s_thin_canopy_resonance_and_conservative_limit():
+    """The entire-basis variants no default-LAI case reaches: kappa = lambda_1 in a thin canopy (kappa LAI < 0.5:
+    series particular solution), omega = 1 exactly, and a sweep of omega across omega* -- vs the tight oracle."""
+    for lai_tot, sel in ((0.5, (5, 7, 9, 10, 11)), (0.05, (0, 5, 9))):
+        q = edge_4s_case(10.0, 0.501, lai_tot=lai_tot)
+        n = q["leaf_r"].size
+        q = {k: (v[list(sel)].copy() if isinstance(v, np.ndarray) and v.shape == (n,) else v) for k, v in q.items()}
+        ref = oracle.solve_4s_tight(**{k: q[k] for k in oracle.ARGS["4s"]})
+        sol = _solve(q, "4s", vec=1)
+        for k in ref:
+            assert_close_4s(sol[k], ref[k], f"thin {lai_tot} {k}")
+    q = edge_4s_case(45.0, 0.501)
+    n = q["leaf_r"].size
+    om = np.array([1.0, 0.9953, 0.99537])
+    q = {k: (v[:3].copy() if isinstance(v, np.ndarray) and v.shape == (n,) else v) for k, v in q.items()}
+    q["leaf_r"], q["leaf_t"] = 0.5 * om, 0.5 * om
+    ref = oracle.solve_4s_tight(**{k: q[k] for k in oracle.ARGS["4s"]})
+    sol = _solve(q, "4s", vec=1)
+    for k in ref:
+        assert_close_4s(sol[k], ref[k], f"omega=1 {k}")

@@ -137,3 +137,133 @@ def ragged_case(nz, kind="cluster", n_bands=8):
 
 
 RAGGED_NZ = (7, 8, 9, 10, 11, 16, 17, 20, 21, 30, 31, 99, 100, 101, 110)
+
+
+# ---- 4s edge cases: omega -> 1 (vanishing / negative eigenvalue^2 of the 4-stream operator) and
+# ---- kappa = lambda_k resonances (ref _solve_4s.py:48-97 integrates the ODE and is indifferent to both)
+EDGE_4S_PSI_DEG = (10.0, 45.0, 75.0)
+EDGE_4S_MU_S = (0.501, 0.33998)
+EDGE_4S_OMEGA = (0.99, 0.995, 0.9954, 0.997, 0.9999, 1.0 - 1e-9)
+
+
+def fourstream_N(omega, G1, G2, mu_s):
+    """The 2x2 matrix N = (P - Q)(P + Q) of s'' = N s + ... for s = D + U (sum of the downward and upward
+    radiance pairs of ref `eqns`, _solve_4s.py:80-95), index 0 <-> sector 2, index 1 <-> sector 1."""
+    m1, m2 = 0.5 * mu_s**2, 0.5 * (1 - mu_s**2)
+    al = 0.5 * omega * (1 - mu_s) * G2
+    be = 0.5 * omega * (1 - mu_s) * G1
+    ga = 0.5 * omega * mu_s * G1
+    q0, q1 = G2 / m2, G1 / m1
+    T = np.array([[(2 * al - G2) / m2, 2 * be / m2], [2 * be / m1, (2 * ga - G1) / m1]])
+    return -np.diag([q0, q1]) @ T
+
+
+def fourstream_l2(omega, G1, G2, mu_s):
+    """Eigenvalues lambda^2 of N, descending."""
+    return np.sort(np.linalg.eigvals(fourstream_N(omega, G1, G2, mu_s)).real)[::-1]
+
+
+def edge_4s_case(psi_deg, mu_s, n_z=20, lai_tot=4.0):
+    """Inputs of one `ref_4s_edge.npz` entry: the default canopy's leaf-angle function at `psi_deg`, `n_z`
+    equally spaced levels, and one band per entry of: EDGE_4S_OMEGA; omega* where the smaller eigenvalue^2
+    crosses zero (and omega* (1 +- 1e-7)); the omega at which kappa = K_b equals lambda_0 or lambda_1 when
+    such an omega exists in (0.02, 0.999) (and that omega (1 + 1e-9), (1 + 1e-5)).  r = 0.55 omega,
+    t = 0.45 omega."""
+    from scipy.optimize import brentq
+    import scipy.integrate as integ
+
+    from crt1d_b200 import cases
+
+    q = dict(cases.load_default_case(n_z))
+    G_fn = q["G_fn"]
+    G1 = integ.quad(lambda m: G_fn(np.arccos(m)), 0, mu_s)[0]
+    G2 = integ.quad(lambda m: G_fn(np.arccos(m)), mu_s, 1)[0]
+    psi = np.deg2rad(psi_deg)
+    kap = G_fn(psi) / np.cos(psi)
+    om = list(EDGE_4S_OMEGA)
+    f1 = lambda w: fourstream_l2(w, G1, G2, mu_s)[1]  # noqa: E731
+    if f1(0.9) * f1(1.0) < 0:
+        ws = brentq(f1, 0.9, 1.0, xtol=1e-15, rtol=1e-15)
+        om += [ws * (1 - 1e-7), ws, min(1.0, ws * (1 + 1e-7))]
+    for k in (0, 1):
+        fk = lambda w, k=k: fourstream_l2(w, G1, G2, mu_s)[k] - kap * kap  # noqa: E731
+        if fk(0.02) * fk(0.999) < 0:
+            wr = brentq(fk, 0.02, 0.999, xtol=1e-15, rtol=1e-15)
+            om += [wr, wr * (1 + 1e-9), wr * (1 + 1e-5)]
+    om = np.array(om)
+    n = om.size
+    q["psi"] = psi
+    q["lai"] = np.linspace(1, 0, n_z) * lai_tot
+    q["leaf_r"] = 0.55 * om
+    q["leaf_t"] = 0.45 * om
+    q["soil_r"] = np.linspace(0.05, 0.3, n)
+    q["I_dr0_all"] = np.linspace(80.0, 120.0, n)
+    q["I_df0_all"] = np.linspace(40.0, 20.0, n)
+    q["wl"] = np.linspace(0.4, 2.4, n)
+    q["dwl"] = np.full(n, 2.0 / max(n - 1, 1))
+    q["wl_leafsoil"] = q["wl"]
+    return with_callables(q)
+
+
+def edge_4s_fixture_cases():
+    """(tag, mu_s, params, shipped, tight) for every entry of ref_4s_edge.npz, inputs taken from the fixture itself
+    (the GPU box needs neither scipy.optimize nor the reference)."""
+    from crt1d_b200 import cases
+
+    g = golden("ref_4s_edge.npz")
+    base = cases.load_default_case(20)
+    out = []
+    for psi_deg in EDGE_4S_PSI_DEG:
+        for mu_s in EDGE_4S_MU_S:
+            tag = f"psi{int(psi_deg)}_mus{int(round(mu_s * 1000))}"
+            q = dict(base)
+            for k in ("psi", "lai", "leaf_r", "leaf_t", "soil_r", "I_dr0_all", "I_df0_all"):
+                q[k] = g[f"{tag}__in__{k}"]
+            q["psi"] = float(q["psi"])
+            n = q["leaf_r"].size
+            q["wl"] = np.linspace(0.4, 2.4, n)
+            q["dwl"] = np.full(n, 2.0 / max(n - 1, 1))
+            q["wl_leafsoil"] = q["wl"]
+            q = with_callables(q)
+            ship = {k: g[f"{tag}__shipped__{k}"] for k in ("I_dr", "I_df_d", "I_df_u", "F")}
+            tight = {k: g[f"{tag}__tight__{k}"] for k in ("I_dr", "I_df_d", "I_df_u", "F")}
+            out.append((tag, mu_s, q, ship, tight))
+    return out
+
+
+def assert_close_4s_shipped(x, ref, what=""):
+    """4s vs the reference as shipped (solve_bvp tol = 1e-6): 2e-4 relative or 1e-7 W m-2."""
+    assert_close(x, ref, RTOL_4S_SHIPPED, what, atol=ATOL_4S_SHIPPED)
+
+
+def tune(monkeypatch, name, value):
+    """Set (or, with None, delete) a CRT1D_B200_* kernel-selection variable for this test and make the library
+    re-read them: they are read once at load time, not on the launch path (conftest restores them afterwards)."""
+    from crt1d_b200 import _lib
+
+    if value is None:
+        monkeypatch.delenv(name, raising=False)
+    else:
+        monkeypatch.setenv(name, value)
+    _lib.load().crt1d_reload_tuning()
+
+
+def random_4s_batch(seed=7):
+    """Seeded random 4s scenarios for `ref_4s_random.npz`: zenith angles to 86 deg, omega = r + t up to 1 (a third of
+    the bands above 0.99), soil albedo to 0.5, one equally spaced and one irregular LAI profile, thin and deep."""
+    from crt1d_b200.leaf_angle import LeafAngle
+    from crt1d_b200.scenarios import ScenarioBatch
+
+    rng = np.random.default_rng(seed)
+    S, nw, nz = 5, 8, 17
+    om = np.concatenate([rng.uniform(0.02, 0.99, (3, nw - 3)), rng.uniform(0.99, 1.0, (3, 3))], axis=1)
+    frac = rng.uniform(0.3, 0.7, (3, nw))
+    steps = rng.uniform(0.2, 1.8, nz - 1)
+    irr = np.concatenate([np.cumsum(steps[::-1])[::-1], [0.0]])
+    lai_lib = np.stack([np.linspace(1, 0, nz) * 5.5, irr / irr[0] * 2.2, np.linspace(1, 0, nz) * 0.3])
+    return ScenarioBatch(
+        psi=np.radians([3.0, 30.0, 55.0, 72.0, 86.0]), lai_lib=lai_lib, leaf_r_lib=om * frac, leaf_t_lib=om * (1 - frac),
+        soil_r_lib=rng.uniform(0.02, 0.5, (2, nw)), I_dr0_lib=rng.uniform(0.0, 9.0, (2, nw)),
+        I_df0_lib=rng.uniform(0.1, 5.0, (2, nw)), lai_idx=[0, 1, 2, 0, 1], leaf_idx=[0, 1, 2, 2, 0],
+        soil_idx=[0, 1, 0, 1, 0], sky_idx=[0, 1, 1, 0, 0], leaf_angle=LeafAngle(), mla=57.0,
+    )
