@@ -14,6 +14,7 @@ from .leaf_angle import LeafAngle
 from .leaf_angle import mla_to_x_approx
 from .leaf_area import distribute_lai_beta
 from .leaf_area import distribute_lai_beta_bonan
+from .leaf_area import distribute_lai_from_cdd
 
 _LIB_PATH = os.path.join(os.path.dirname(__file__), "data", "spectra_lib.npz")
 _lib_cache = None
@@ -82,3 +83,34 @@ def load_bonan_sp1403_case():
         wl=wl, wl_leafsoil=wl, dwl=np.r_[0.3, 1.8], clump=1.0, G_fn=G_spherical,
         leaf_angle=LeafAngle("spherical", 0.0), mla=60.0, green=1.0, orient=1.0,
     )
+
+
+# The reference's default canopy description (Borden 1995 field study, late June: ref data/default_canopy_descrip.csv),
+# storeys listed uppermost first
+BORDEN95_CANOPY_DESCRIP = dict(
+    lai_tot=3.044, lai_frac=[0.608, 0.392], h_ref=34.2, h_canopy=22.0, h_max_lad=[15.4, 6.16], h_bot=[12.1, 1.375],
+    h_top=[22.0, 12.0], lad_h_top=[0.0, 0.065], mla=57.4, lat=44.31666, lon=80.93333, green=1.0, clump=[0.930, 0.930],
+)
+
+
+def load_canopy_descrip(fpath):
+    """Canopy-description CSV (`varname,value,...` rows; `;`-separated lists) -> dict  (ref cases.py:61-85)."""
+    import csv
+
+    d = {}
+    with open(fpath, newline="") as fh:
+        rows = csv.reader(fh)
+        next(rows)  # header
+        for row in rows:
+            if len(row) < 2 or not row[0].strip():
+                continue
+            name, val = row[0].strip(), row[1]
+            d[name] = [float(x) for x in val.split(";")] if ";" in val else float(val)
+    assert np.array(d["lai_frac"]).sum() == 1.0
+    return d
+
+
+def borden95_profile(nlayers, cdd=None):
+    """Equal-LAI-increment levels of the two-storey Borden canopy (`distribute_lai_from_cdd`).  The reference's
+    `load_Borden95_default_case` stops right after this step with NotImplementedError (ref cases.py:88-93)."""
+    return distribute_lai_from_cdd(dict(cdd or BORDEN95_CANOPY_DESCRIP), nlayers)

@@ -26,11 +26,14 @@ def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def solve_batch_host(batch, scheme, prologue, *, mu_s=0.501, band_w=None, device=None, alloc=np.empty, status=False):
+def solve_batch_host(batch, scheme, prologue, *, mu_s=0.501, band_w=None, device=None, alloc=np.empty, status=False,
+                     fields=None):
     """`crt1d_solve_host` on a ScenarioBatch with a host prologue dict; returns numpy arrays with a
     leading scenario axis.  `alloc(shape)` makes the float64 output arrays (default: fresh pageable numpy
     arrays like the reference's; a page-locked allocator lets the D2H copies run at PCIe speed).
-    `status=True` adds the per-scenario int32 status words (`_abi.STATUS_NONFINITE`) as `out["status"]`."""
+    `status=True` adds the per-scenario int32 status words (`_abi.STATUS_NONFINITE`) as `out["status"]`.
+    `fields`: names of the profiles to return (default all of the scheme's); the others are neither computed into
+    host memory nor copied (NULL pointers in `crt1d_out`)."""
     lib = _lib.load()
     S, nz, nw = batch.n_scen, batch.n_z, batch.n_wl
     keep = {}
@@ -48,18 +51,28 @@ def solve_batch_host(batch, scheme, prologue, *, mu_s=0.501, band_w=None, device
     cb.mla_deg = float(batch.mla)
     cb.mu_s = float(mu_s)
 
-    out = {k: alloc((S, nz, nw)) for k in ("I_dr", "I_df_d", "I_df_u", "F")}
+    main = ("I_dr", "I_df_d", "I_df_u", "F")
+    extra = EXTRA_NAMES.get(scheme, ())
+    if fields is not None:
+        unknown = set(fields) - set(main) - set(extra) - {"rho_c"}
+        if unknown:
+            raise KeyError(f"{scheme}: no such output field(s): {', '.join(sorted(unknown))}")
+    want = lambda k: fields is None or k in fields  # noqa: E731
+    out = {k: alloc((S, nz, nw)) for k in main if want(k)}
     rows = nz - 1 if scheme == "n79" else nz
-    for k in EXTRA_NAMES.get(scheme, ()):
-        out[k] = alloc((S, rows, nw))
-    if scheme == "bf":
+    for k in extra:
+        if want(k):
+            out[k] = alloc((S, rows, nw))
+    if scheme == "bf" and want("rho_c"):
         out["rho_c"] = np.empty((S, nw))
     co = _abi.Out()
-    for k in ("I_dr", "I_df_d", "I_df_u", "F"):
-        setattr(co, k, _ptr(out[k]))
-    for slot, k in zip(("x0", "x1", "x2"), EXTRA_NAMES.get(scheme, ())):
-        setattr(co, slot, _ptr(out[k]))
-    if scheme == "bf":
+    for k in main:
+        if k in out:
+            setattr(co, k, _ptr(out[k]))
+    for slot, k in zip(("x0", "x1", "x2"), extra):
+        if k in out:
+            setattr(co, slot, _ptr(out[k]))
+    if "rho_c" in out:
         co.rho_c = _ptr(out["rho_c"])
     if band_w is not None:
         keep["band_w"] = np.ascontiguousarray(np.atleast_2d(np.asarray(band_w, dtype=np.float64)))

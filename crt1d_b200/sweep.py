@@ -72,6 +72,37 @@ def synthetic_sweep_spec(seed=0, n_z=60, n_sza=N_SZA, n_lai=N_LAI, n_spec=N_SPEC
     )
 
 
+def nonuniform_lai_library(lai_tot, n_z, h_c=20.0):
+    """One cumulative-LAI profile per total in `lai_tot` from the generators whose axes are NOT equally spaced
+    (`leaf_area.distribute_lai_weibull_z` for pine / spruce / birch crowns, `distribute_lai_gamma`), cycling through
+    the four.  Rows obey the `ScenarioBatch` contract (`lai[0]` = total = max, `lai[-1] == 0`)."""
+    from . import leaf_area
+
+    z = np.linspace(0.0, h_c + 0.5, n_z)
+    rows = []
+    for i, tot in enumerate(np.asarray(lai_tot, dtype=np.float64)):
+        kind = i % 4
+        if kind == 3:
+            lai = leaf_area.distribute_lai_gamma(h_c, float(tot), n_z).lai
+        else:
+            lai = leaf_area.distribute_lai_weibull_z(z, float(tot), h_c, hb=0.5, species=("pine", "spruce", "birch")[kind]).lai
+        lai = np.array(lai, dtype=np.float64)
+        lai[-1] = 0.0  # weibull_z ends in -0.0
+        lai[0] = lai.max()
+        rows.append(lai)
+    return np.stack(rows)
+
+
+def nonuniform_lai_spec(spec):
+    """The same sweep as `spec` (indices, spectra, angles) with its LAI library replaced by non-uniform profiles of
+    the same totals -- the level-recurrence fast paths of the kernels do not apply to any level group of these."""
+    import copy
+
+    out = copy.copy(spec)
+    out.lai_lib = nonuniform_lai_library(spec.lai_lib[:, 0], spec.n_z)
+    return out
+
+
 class SweepRunner:
     """Chunked execution of a large `ScenarioBatch` on one GPU.
 
@@ -83,7 +114,7 @@ class SweepRunner:
     """
 
     def __init__(self, spec, scheme="2s", *, chunk=4096, device=None, n_buffers=2, bands=("PAR", "NIR"),
-                 profiles=True, n_quad=32, profile_dtype=None):
+                 profiles=True, n_quad=32, profile_dtype=None, n_diag_buffers=1):
         import warnings
 
         from . import engine
@@ -107,8 +138,19 @@ class SweepRunner:
         self.db = None
         self.pinned = None  # set by pin_host(): page-locked staging copies of the scenario tables
         self.ring = None
-        self.absorbed = None
+        # per-scenario diagnostics of the whole sweep stay resident; with n_diag_buffers = 2 consecutive steps
+        # alternate between two buffers, so a consumer on another stream (the NCCL all-gather of bench.py)
+        # can read step k's diagnostics while step k+1 is being computed
+        self.n_diag_buffers = int(n_diag_buffers)
+        self.absorbed_bufs = None
+        self._last = 0
+        self._next = 0
         self._calls = None
+
+    @property
+    def absorbed(self):
+        """Diagnostics `(S, n_bands)` of the most recent step."""
+        return None if self.absorbed_bufs is None else self.absorbed_bufs[self._last]
 
     @property
     def n_chunks(self):
@@ -148,24 +190,29 @@ class SweepRunner:
             ]
             if self.band_w is not None:
                 self.band_w_d = torch.as_tensor(self.band_w).to(dev)
-                self.absorbed = torch.empty((self.spec.n_scen, self.band_w.shape[0]), dtype=torch.float64, device=dev)
-        self._calls = []
-        for c in range(self.n_chunks):
-            lo, hi = c * self.chunk, min((c + 1) * self.chunk, self.spec.n_scen)
-            view = self.db.narrow(lo, hi)
-            co = self.ring[c % len(self.ring)].cout(hi - lo)
-            if self.band_w is not None:
-                co.band_w = self.band_w_d.data_ptr()
-                co.n_bw = self.band_w.shape[0]
-                co.absorbed = self.absorbed[lo:hi].data_ptr()
-            self._calls.append((view, co))
+        if self.band_w is not None and self.absorbed_bufs is None:
+            self.absorbed_bufs = [torch.empty((self.spec.n_scen, self.band_w.shape[0]), dtype=torch.float64, device=dev)
+                                  for _ in range(max(1, self.n_diag_buffers))]
+        self._calls = []  # [diagnostic buffer][chunk] -> (device view, crt1d_out)
+        views = [self.db.narrow(c * self.chunk, min((c + 1) * self.chunk, self.spec.n_scen)) for c in range(self.n_chunks)]
+        for b in range(len(self.absorbed_bufs) if self.absorbed_bufs else 1):
+            calls = []
+            for c, view in enumerate(views):
+                lo, hi = c * self.chunk, min((c + 1) * self.chunk, self.spec.n_scen)
+                co = self.ring[c % len(self.ring)].cout(hi - lo)
+                if self.band_w is not None:
+                    co.band_w = self.band_w_d.data_ptr()
+                    co.n_bw = self.band_w.shape[0]
+                    co.absorbed = self.absorbed_bufs[b][lo:hi].data_ptr()
+                calls.append((view, co))
+            self._calls.append(calls)
         self._sid = _abi.SCHEME_IDS[self.scheme]
         self._byref = ctypes.byref
         return self
 
     def step(self, events=None):
         """Enqueue one pass over all chunks on the current stream; returns the number of kernel launches.
-        `events`: optional list that receives a (start, end) CUDA-event pair per launch."""
+        `events`: optional list that receives a (start, end, n_scenarios) CUDA-event record per launch."""
         import ctypes
 
         import torch
@@ -175,7 +222,10 @@ class SweepRunner:
         lib = self.db.lib
         stream = torch.cuda.current_stream()
         sp = ctypes.c_void_p(stream.cuda_stream)
-        for view, co in self._calls:
+        calls = self._calls[self._next]
+        self._last = self._next
+        self._next = (self._next + 1) % len(self._calls)
+        for view, co in calls:
             if events is not None:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
@@ -185,8 +235,8 @@ class SweepRunner:
                 _lib.check(rc)
             if events is not None:
                 e1.record(stream)
-                events.append((e0, e1))
-        return len(self._calls)
+                events.append((e0, e1, view.batch.n_scen))
+        return len(calls)
 
     def algorithmic_bytes_per_unit(self):
         """bytes written per layer.band for this scheme + amortised input reads."""

@@ -24,10 +24,15 @@ def test_reference_arm_json_line():
     d = json.loads(lines[0])
     assert BASE_KEYS <= set(d) and d["impl"] == "reference"
     assert d["metric"] == "layer_band_solves_per_s" and d["unit"] == "layer*band solves/s" and d["higher_is_better"] is True
-    assert d["value"] > 1e6 and d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert d["value"] > 1e5 and d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "scenarios" in cb["sample"]
+    staged = os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "crt1d", "solvers", "_solve_2s.py"))
+    assert cb["kind"] == ("reference" if staged else "port")  # the unmodified reference when build() staged it
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "scenarios" in cb["sample"]
+    c1 = cb["cfg1_default_case"]  # BASELINE.json configs[0]: default case, 2s, one core, best of 5
+    assert c1["cores"] == 1 and c1["kind"] == cb["kind"] and abs(c1["checksum_F"] - 4.778896367937e4) < 1e-6
+    assert d["scaling"] == "strong" and "configs[2]" in d["config"]["workload"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
 

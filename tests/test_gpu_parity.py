@@ -1004,3 +1004,72 @@ def test_model_leaf_angle_and_G_fn_stay_one_canopy():
         m._p["G_fn"] = LeafAngle("horizontal").G_fn
         m._check_inputs()
     assert "leaf_angle" not in m._p
+
+
+# ---------------------------------------------------------------------------------- non-uniform LAI axes (8f rank 3)
+@pytest.mark.parametrize("tag", ["wz_birch60", "wz_pine20", "gamma60", "gamma10"])
+def test_nonuniform_lai_axes_match_reference_golden(tag):
+    """Every scheme through the plugin API on the cumulative-LAI axes of the reference's weibull_z / gamma generators
+    (unequal steps; weibull_z: zero-thickness layers, where the reference's n79 returns 0/0 and x/0 for the per-leaf-area
+    absorption and the CUDA path must return the same NaN / inf), vs reference-generated fixtures."""
+    import warnings
+
+    import crt1d_b200 as crt
+    from util import assert_close_same_nans
+    from util import nonuniform_case
+
+    g = golden("ref_leaf_area.npz")
+    q = nonuniform_case(tag)
+    for scheme in FAST + ("4s_tight",):
+        name = "4s" if scheme == "4s_tight" else scheme
+        keys = [k for k in g if k.startswith(f"sol__{tag}__{scheme}__")]
+        assert keys
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")  # the non-finite status warning of n79 on zero-thickness layers
+            sol = crt.solvers.AVAILABLE_SCHEMES[name]["solver"](**_args(name, q))
+        for full in keys:
+            k = full.split("__")[-1]
+            if scheme == "4s_tight":
+                assert_close_4s(sol[k], g[full], f"{tag} 4s.{k}")
+            else:
+                assert_close_same_nans(sol[k], g[full], RTOL, f"{tag} {scheme}.{k}")
+
+
+@pytest.mark.parametrize("scheme", ["2s", "4s", "bl", "bf", "g77", "zq", "zq_pa", "n79"])
+def test_nonuniform_lai_sweep_batched(scheme):
+    """160 scenarios of the sweep on the non-uniform LAI library (`sweep.nonuniform_lai_spec`: weibull_z pine / spruce /
+    birch and gamma profiles) through the device-prologue batch path -- row-sweep kernels for the closed forms, none of
+    whose level groups is equally spaced -- vs the oracle; every 7th band to keep the oracle fast."""
+    import warnings
+
+    import torch
+
+    from crt1d_b200 import engine
+    from crt1d_b200 import sweep
+    from util import assert_close_same_nans
+
+    spec = sweep.nonuniform_lai_spec(sweep.synthetic_sweep_spec(seed=0))
+    for k in ("leaf_r_lib", "leaf_t_lib", "soil_r_lib", "I_dr0_lib", "I_df0_lib"):
+        setattr(spec, k, np.ascontiguousarray(getattr(spec, k)[:, ::7]))
+    spec.wl, spec.dwl = spec.wl[::7], spec.dwl[::7]
+    lo = 350_000  # i_sza = 35; 160 consecutive scenarios cross two LAI rows (kinds 3 -> 0) and all spectra
+    sub = spec.slice(lo + 9_940, lo + 9_940 + 160)
+    assert len(set(sub.lai_idx.tolist())) == 2
+    res = engine.solve(sub, scheme)
+    torch.cuda.synchronize()
+    tight = scheme == "4s"
+    for i in (0, 59, 60, 159):
+        q = sub.scenario_params(i)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = oracle.solve_4s_tight(**{k: q[k] for k in oracle.ARGS["4s"]}) if tight else oracle.run(scheme, q)
+        for k in ref:
+            if k == "rho_c":
+                continue
+            got = res[k][i].cpu().numpy()
+            if tight:
+                assert_close_4s(got, ref[k], f"nonuniform 4s[{i}].{k}")
+            else:
+                # device Gauss-Legendre tau_d vs the oracle's quad(epsrel=1e-9) (1e-8, see test_batched_equals_plugin_path)
+                assert_close_same_nans(got, ref[k], 1e-8 if scheme in ("zq", "zq_pa", "n79", "bl") else RTOL,
+                                       f"nonuniform {scheme}[{i}].{k}", atol=1e-300)

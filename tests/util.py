@@ -267,3 +267,51 @@ def random_4s_batch(seed=7):
         I_df0_lib=rng.uniform(0.1, 5.0, (2, nw)), lai_idx=[0, 1, 2, 0, 1], leaf_idx=[0, 1, 2, 2, 0],
         soil_idx=[0, 1, 0, 1, 0], sky_idx=[0, 1, 1, 0, 0], leaf_angle=LeafAngle(), mla=57.0,
     )
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Non-beta LAI generators and the non-uniform cumulative-LAI axes they produce
+BORDEN95_CDD = dict(lai_tot=3.044, lai_frac=[0.608, 0.392], h_canopy=22.0, h_max_lad=[15.4, 6.16], h_bot=[12.1, 1.375],
+                    h_top=[22.0, 12.0], lad_h_top=[0, 0.065])
+LEAF_AREA_CASES = [
+    # (tag, generator name, positional args, keyword args); `z20` / `z60` grids are rebuilt by leaf_area_args()
+    ("wz_pine20", "distribute_lai_weibull_z", (np.linspace(0, 10.5, 20), 5, 10), dict(hb=2, species="pine")),
+    ("wz_spruce20", "distribute_lai_weibull_z", (np.linspace(0, 10.5, 20), 5, 10), dict(hb=2, species="spruce")),
+    ("wz_birch60", "distribute_lai_weibull_z", (np.linspace(0, 20.5, 60), 4, 20), dict(hb=0.5, species="birch")),
+    ("wz_bc60", "distribute_lai_weibull_z", (np.linspace(0, 20.5, 60), 6.5, 20), dict(hb=3.0, b=1.2, c=2.4)),
+    ("w_pine20", "distribute_lai_weibull", (10, 5, 20), dict(h_min=2, species="pine")),
+    ("w_spruce60", "distribute_lai_weibull", (20, 4, 60), dict(species="spruce")),
+    ("w_birch1000", "distribute_lai_weibull", (30, 6.5, 1000), dict(h_min=3, species="birch")),
+    ("gamma10", "distribute_lai_gamma", (20, 4, 10), {}),
+    ("gamma60", "distribute_lai_gamma", (20, 4, 60), {}),
+    ("gamma1000", "distribute_lai_gamma", (35, 7.5, 1000), {}),
+    ("cdd20", "distribute_lai_from_cdd", (BORDEN95_CDD, 20), {}),
+    ("cdd60", "distribute_lai_from_cdd", (BORDEN95_CDD, 60), {}),
+    ("cdd61", "distribute_lai_from_cdd", (BORDEN95_CDD, 61), {}),
+]
+NONUNIFORM_AXES = ("wz_birch60", "wz_pine20", "gamma60", "gamma10")
+
+
+def nonuniform_case(tag):
+    """Default case (every 9th band, SZA 35 deg) on the cumulative-LAI axis of LEAF_AREA_CASES[tag], generated by the
+    PRODUCT's leaf_area module (bit-identical to the reference's, see test_leaf_area_generators)."""
+    from crt1d_b200 import leaf_area
+
+    _, fn, args, kw = next(c for c in LEAF_AREA_CASES if c[0] == tag)
+    prof = getattr(leaf_area, fn)(*args, **kw)
+    q = variant_case(len(prof.lai), 35)
+    q["lai"], q["z"] = np.asarray(prof.lai, dtype=np.float64), np.asarray(prof.z, dtype=np.float64)
+    return with_callables(q)
+
+
+def assert_close_same_nans(x, ref, rtol, what="", atol=0.0):
+    """`assert_close` where the reference itself returns NaN / inf (n79 sunlit/shaded absorption per leaf area on
+    zero-thickness layers: 0/0 and x/0 in ref _solve_n79.py): the non-finite values must be the same ones at the same
+    places, everything else must agree."""
+    x, ref = np.asarray(x, dtype=float), np.asarray(ref, dtype=float)
+    assert x.shape == ref.shape, (what, x.shape, ref.shape)
+    assert np.array_equal(np.isnan(x), np.isnan(ref)), f"{what}: NaN pattern differs from the reference's"
+    inf = np.isinf(ref)
+    assert np.array_equal(np.isinf(x), inf) and np.array_equal(x[inf], ref[inf]), f"{what}: inf pattern differs"
+    m = np.isfinite(ref)
+    assert_close(x[m], ref[m], rtol, what, atol=atol)
