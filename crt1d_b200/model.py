@@ -21,6 +21,7 @@ from .solvers import RET_KEYS_ALL_SCHEMES
 from .spectra import BAND_DEFNS_UM
 from .spectra import x_frac_in_bounds
 from .variables import VMD
+from .variables import da_attrs
 
 __all__ = ("Model", "run_sensitivity")
 
@@ -228,45 +229,52 @@ class Model:
 
     # ------------------------------------------------------------------ export
     def to_xr(self, *, info=""):
-        """Pack inputs/outputs into an `xarray.Dataset` with dims z, zm, wl, wle (ref model.py:338-447).
+        """Pack inputs/outputs into an `xarray.Dataset` laid out exactly as the reference's (ref model.py:338-447):
+        coords z, wl, zm, wle; data variables I_dr, I_df_d, I_df_u, F, I_d, dwl, lai, dlai, the post-processed
+        absorption set, the scheme's own `aI*_scheme` arrays, and the scalars psi, sza, G, K_b; attrs info / scheme
+        names / version -- so the reference's `diagnostics.band` / `compare_ebal` accept it unchanged.
         xarray is imported here, not at module import: it is not part of this image."""
         try:
             import xarray as xr
         except ImportError as e:
             raise ImportError("Model.to_xr needs xarray, which is not installed") from e
+        return xr.Dataset(**self.dataset_description(info=info))
+
+    def dataset_description(self, *, info=""):
+        """The keyword arguments of `xarray.Dataset` for this run (`coords`, `data_vars`, `attrs`)."""
         if self._run_count == 0:
-            raise Exception("Must run the model first.")
+            raise Exception("Must run the model before creating the dataset.")
+        from . import __version__
+
         p = self._p
-
-        def tup(name, data, dims):
-            m = VMD[name] if name in VMD else None
-            attrs = {"units": m.units, "long_name": m.long_name} if m else {}
-            return (dims, data, attrs)
-
-        coords = {
-            "z": tup("z", p["z"], "z"), "zm": tup("zm", p["zm"], "zm"),
-            "wl": tup("wl", p["wl"], "wl"), "wle": tup("wle", p["wle"], "wle"),
+        out = self.out_all
+        tup = VMD.dv_tuple
+        dv = {
+            "I_dr": tup("I_dr", out["I_dr"]), "I_df_d": tup("I_df_d", out["I_df_d"]), "I_df_u": tup("I_df_u", out["I_df_u"]),
+            "F": tup("F", out["F"]), "I_d": tup("I_d", out["I_dr"] + out["I_df_d"]),
+            "dwl": tup("dwl", p["dwl"]), "lai": tup("lai", p["lai"]), "dlai": tup("dlai", p["dlai"]),
         }
-        dv = {k: tup(k, v, ("z", "wl")) for k, v in self.out.items()}
-        dv["lai"] = tup("lai", p["lai"], "z")
-        dv["dlai"] = tup("dlai", p["dlai"], "zm")
-        dv["dwl"] = tup("dwl", p["dwl"], "wl")
-        for k, v in self.out_extra.items():
-            base = k[: -len("_scheme")]
-            if base.startswith("aI"):
-                if base not in VMD:
-                    raise KeyError(f"scheme extra {base!r} has no variable metadata")
-                dims = ("z", "wl") if v.shape[0] == self.nlev else ("zm", "wl")
-                dv[k] = tup(base, v, dims)
         if self.absorption is not None:
-            for k, v in self.absorption.items():
-                dv[k] = tup(k, v, ("zm", "wl") if v.ndim == 2 else "zm")
-        attrs = {
-            "info": info, "scheme_name": self.scheme["name"], "scheme_long_name": self.scheme["long_name"],
-            "scheme_short_name": self.scheme["short_name"], "sza": np.rad2deg(p["psi"]), "psi": p["psi"],
-            "mu": p["mu"], "G": p["G"], "K_b": p["K_b"],
-        }
-        return xr.Dataset(coords=coords, data_vars=dv, attrs=attrs)
+            dv.update({k: tup(k, v) for k, v in self.absorption.items()})
+        for k, v in self.out_extra.items():
+            if k[:2] != "aI":
+                continue
+            if v.shape[0] == p["z"].size:  # some schemes provide absorption on interface levels
+                dims = ("z", "wl")
+            elif v.shape[0] == p["zm"].size:
+                dims = ("zm", "wl")
+            else:
+                raise ValueError("Scheme absorption output has too many or too few levels.")
+            base = k[: -len("_scheme")]
+            if base not in VMD:
+                raise Exception(f"Scheme absorbance variable {base} not found in vmd.")
+            dv[k] = (dims, v, da_attrs(VMD[base]))
+        dv.update({"psi": tup("psi", p["psi"]), "sza": tup("sza", np.rad2deg(p["psi"])), "G": tup("G", p["G"]),
+                   "K_b": tup("K_b", p["K_b"])})
+        coords = {"z": tup("z", p["z"]), "wl": tup("wl", p["wl"]), "zm": tup("zm", p["zm"]), "wle": tup("wle", p["wle"])}
+        attrs = {"info": info, "scheme_name": self.scheme["name"], "scheme_long_name": self.scheme["long_name"],
+                 "scheme_short_name": self.scheme["short_name"], "crt1d_version": __version__}
+        return {"coords": coords, "data_vars": dv, "attrs": attrs}
 
 
 def _calc_absorption(m):
@@ -362,7 +370,7 @@ def sensitivity_dataset(res, m0, p_sets, *, bands=("PAR", "NIR")):
 
     def tup(name, data, dims):
         m = VMD[name] if name in VMD else None
-        return (tuple(dims), data, {"units": m.units, "long_name": m.long_name} if m else {})
+        return (tuple(dims), data, da_attrs(m) if m else {})
 
     coords = {"z": tup("z", p["z"], ["z"]), "zm": tup("zm", p["zm"], ["zm"]), "wl": tup("wl", p["wl"], ["wl"])}
     sw_dims = []

@@ -188,8 +188,8 @@ class SweepRunner:
                                   extras=self.profiles, profile_dtype=self.profile_dtype)
                 for _ in range(self.n_buffers if self.profiles else 1)
             ]
-            if self.band_w is not None:
-                self.band_w_d = torch.as_tensor(self.band_w).to(dev)
+        if self.band_w is not None and getattr(self, "band_w_d", None) is None:
+            self.band_w_d = torch.as_tensor(self.band_w).to(dev)
         if self.band_w is not None and self.absorbed_bufs is None:
             self.absorbed_bufs = [torch.empty((self.spec.n_scen, self.band_w.shape[0]), dtype=torch.float64, device=dev)
                                   for _ in range(max(1, self.n_diag_buffers))]

@@ -1055,21 +1055,38 @@ def test_nonuniform_lai_sweep_batched(scheme):
     lo = 350_000  # i_sza = 35; 160 consecutive scenarios cross two LAI rows (kinds 3 -> 0) and all spectra
     sub = spec.slice(lo + 9_940, lo + 9_940 + 160)
     assert len(set(sub.lai_idx.tolist())) == 2
-    res = engine.solve(sub, scheme)
+    quad_scheme = scheme in ("zq", "zq_pa", "n79", "bl")  # prologue holds tau_d integrals (scipy quad in the reference)
+    if quad_scheme:
+        # host prologue = the oracle's own quad calls -> the 1e-10 bar applies; the device prologue (Gauss-Legendre)
+        # is then compared with it at quad's own accuracy (default epsabs = epsrel = 1.5e-8 on tau_d)
+        res = engine.solve(engine.DeviceBatch(sub, scheme, prologue=engine.host_prologue(sub, scheme)), scheme)
+        dev = engine.solve(sub, scheme)
+        torch.cuda.synchronize()
+        for k in ("I_dr", "I_df_d", "I_df_u", "F"):
+            a, b = dev[k].cpu().numpy(), res[k].cpu().numpy()
+            assert np.max(np.abs(a - b)) <= 2e-7 * np.max(np.abs(b)), (scheme, k)
+    else:
+        res = engine.solve(sub, scheme)
     torch.cuda.synchronize()
     tight = scheme == "4s"
+    sel = [0, 50, 120, 208, 209, 210, 211, 299]  # 4s: the BVP oracle on a few bands (210 = the weakest field of the set)
     for i in (0, 59, 60, 159):
         q = sub.scenario_params(i)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            ref = oracle.solve_4s_tight(**{k: q[k] for k in oracle.ARGS["4s"]}) if tight else oracle.run(scheme, q)
+            if tight:
+                # solve_bvp at tol = 1e-13: at the two-oracle rule's 1e-11 the collocation solution itself is off by
+                # 1.4e-12 absolute in band 210 (value 5e-5), at 1e-13 it converges onto the closed form (2e-15)
+                kw = {k: (q[k][sel] if k in ("leaf_r", "leaf_t", "soil_r", "I_dr0_all", "I_df0_all") else q[k])
+                      for k in oracle.ARGS["4s"]}
+                ref = oracle.solve_4s(tol=1e-13, max_nodes=400000, exact_jacobian=True, **kw)
+            else:
+                ref = oracle.run(scheme, q)
         for k in ref:
             if k == "rho_c":
                 continue
             got = res[k][i].cpu().numpy()
             if tight:
-                assert_close_4s(got, ref[k], f"nonuniform 4s[{i}].{k}")
+                assert_close(got[:, sel], ref[k], 1e-10, f"nonuniform 4s[{i}].{k}", atol=1e-14 * float(np.max(np.abs(ref[k]))))
             else:
-                # device Gauss-Legendre tau_d vs the oracle's quad(epsrel=1e-9) (1e-8, see test_batched_equals_plugin_path)
-                assert_close_same_nans(got, ref[k], 1e-8 if scheme in ("zq", "zq_pa", "n79", "bl") else RTOL,
-                                       f"nonuniform {scheme}[{i}].{k}", atol=1e-300)
+                assert_close_same_nans(got, ref[k], RTOL, f"nonuniform {scheme}[{i}].{k}", atol=1e-300)
