@@ -1271,18 +1271,35 @@ CRT_HD void solve4(double (&A)[4][4], double (&b)[4]) {
     }
 }
 
+// Where the ordinary (real, well separated eigenvalue) closed form hands over to coef_4s_general.  The general branch
+// costs direct exp / series evaluations at every level AND makes its whole warp take that path, so the windows are as
+// narrow as the ordinary form's accuracy allows (measured against the general form, tests/test_hostmath.py):
+//   (lambda_1 LAI)^2 < CRT_4S_ENTIRE_BELOW : the two lambda_1 modes e^{-lam x}, e^{-lam (LAI-x)} approach linear
+//       dependence like 1/(lam LAI); at 1e-3 the boundary solve still leaves ~1e-13
+//   |kappa^2 - lambda_k^2| <= CRT_4S_RESONANCE_WIDTH kappa^2 : the particular solution's 1/(kappa^2 - lambda_k^2)
+//       cancels against the homogeneous part: measured error of the ordinary form 2e-14 / width (2e-11 at 1e-3).
+//       Resonant columns: 0.09 % of the sweep's.
+#ifndef CRT_4S_ENTIRE_BELOW
+#define CRT_4S_ENTIRE_BELOW 1e-3
+#endif
+#ifndef CRT_4S_RESONANCE_WIDTH
+#define CRT_4S_RESONANCE_WIDTH 1e-3
+#endif
 // Folded per-band coefficients: I_dn(x) = sum_k dnP[k] e^{-lam_k (LAI-x)} + dnM[k] e^{-lam_k x} + dnK e^{-kappa x}
 struct Coef4s {
     // I_dn(x) = sum_k dnP[k] p_k + dnM[k] m_k + dnK X,  m_k = e^{-lam_k x},  p_k = e^{-lam_k (LAI - x)},  X = e^{-kappa x}.
     // Fast form (lam[0] > 0): dnP/upP are pre-multiplied by g_k = e^{-lam_k LAI}, so p_k's factor is just e^{+lam_k x},
     // the other half of the exp_pm that yields m_k.
+    // The two lowest mantissa bits of a positive lam[0] say whether X is e^{-kappa x} (0) or the resonance-safe
+    // R_k(x) = (e^{-kappa x} - e^{-lam_k x})/(kappa^2 - lam_k^2) of mode k = bits - 1 (|kappa^2 - lam_k^2| <=
+    // CRT_4S_RESONANCE_WIDTH kappa^2: coefficients from coef_4s_general); every fast-form lam[0] is stored that way.
     // Slow form (lam[0] < 0, direct evaluation of every basis function, unscaled coefficients): lam[0] holds
     // -lambda_0 with a 3-bit mode word in its lowest mantissa bits (a relative perturbation of lambda_0 below
     // 2^-49; e^{-lam x} moves by at most that / e in absolute terms):
     //   mode & 1        mode 1 uses the entire basis: lam[1] = lambda_1^2 (any sign), m_1 = c(x), p_1 = sh(x)
     //   (mode >> 1) & 3 resonant mode + 1 (0 = none): X = R_k(x) instead of e^{-kappa x}
-    // Reasons for the slow form: lam_0 LAI >= 600 (the scaled product could overflow), lambda_1^2 LAI^2 < 1/4,
-    // |kappa^2 - lambda_k^2| <= 0.05 kappa^2.
+    // Reasons for the slow form: lam_0 LAI >= 600 (the scaled product could overflow), lambda_1^2 LAI^2 <
+    // CRT_4S_ENTIRE_BELOW, |kappa^2 - lambda_k^2| <= CRT_4S_RESONANCE_WIDTH kappa^2.
     double lam[2], dnP[2], dnM[2], upP[2], upM[2], dnK, upK, Idr0;
 };
 
@@ -1296,6 +1313,28 @@ CRT_HD double pack_mode_4s(double lam0, int mode) {  // -(lam0 with its three lo
     double r;
     memcpy(&r, &b, 8);
     return -r;
+#endif
+}
+// fast form: lam0 (> 0) with its two lowest mantissa bits = res (a relative change of lam0 below 2^-50)
+CRT_HD double tag_res_4s(double lam0, int res) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((__double_as_longlong(lam0) & ~3LL) | (long long)res);
+#else
+    int64_t b;
+    memcpy(&b, &lam0, 8);
+    b = (b & ~(int64_t)3) | (int64_t)res;
+    double r;
+    memcpy(&r, &b, 8);
+    return r;
+#endif
+}
+CRT_HD int fast_res_4s(double lam0_stored) {
+#if defined(__CUDA_ARCH__)
+    return (int)(__double_as_longlong(lam0_stored) & 3LL);
+#else
+    int64_t b;
+    memcpy(&b, &lam0_stored, 8);
+    return (int)(b & 3);
 #endif
 }
 CRT_HD int unpack_mode_4s(double lam0_stored) {
@@ -1357,7 +1396,7 @@ CRT_HD double res_series_4s(double kappa, double l2, double x) {
 //   F = e^{-kappa x}/(kappa^2 - l2), or the resonance-safe R (R' = -kappa R - A/(kappa + lam); entire pair: R' = -kappa R + B).
 // In the resonant case e^{-kappa x} = A_k [- kappa B_k] + (kappa^2 - l2_k) R_k is eliminated from the other mode's
 // particular term, so the level stage still sums five products (X := R_k takes the e^{-kappa x} slot).
-CRT_HD_NOINLINE void coef_4s_general(const Scen4s& s, double r, double t, double rho, double Idr0, double Idf0,
+CRT_HD void coef_4s_general(const Scen4s& s, double r, double t, double rho, double Idr0, double Idf0,
                                      const double (&N)[2][2], const double (&l2)[2], const double (&phi)[2][2],
                                      Coef4s& k) {
     const double omega = r + t;
@@ -1374,10 +1413,10 @@ CRT_HD_NOINLINE void coef_4s_general(const Scen4s& s, double r, double t, double
     c[0] = (r0 * phi[1][1] - r1 * phi[1][0]) / dphi;
     c[1] = (phi[0][0] * r1 - phi[0][1] * r0) / dphi;
 
-    const bool entire1 = !(l2[1] * L * L >= 0.25);
+    const bool entire1 = !(l2[1] * L * L >= CRT_4S_ENTIRE_BELOW);
     int res = 0;
-    if (fabs(k2 - l2[0]) <= 0.05 * k2) res = 1;
-    else if (fabs(k2 - l2[1]) <= 0.05 * k2) res = 2;
+    if (fabs(k2 - l2[0]) <= CRT_4S_RESONANCE_WIDTH * k2) res = 1;
+    else if (fabs(k2 - l2[1]) <= CRT_4S_RESONANCE_WIDTH * k2) res = 2;
 
     double chi[2][2], mphi[2], mchi[2], lam[2];
 #pragma unroll
@@ -1502,59 +1541,123 @@ CRT_HD_NOINLINE void coef_4s_general(const Scen4s& s, double r, double t, double
     k.lam[1] = entire1 ? l2[1] : lam[1];
 }
 
+// Eigen-system of the 4-stream operator for one band: N (s'' = N s + ...), its eigenvalues l2 (descending) and the
+// eigenvectors phi, normalised to unit max-norm.  One function for the ordinary and the rare path: same numbers.
+struct Eig4s {
+    double N00, N01, N10, N11, l2[2], phi[2][2];
+};
+// N and its eigenvalues.  The rarity test (ordinary_4s) is evaluated on l2 by TWO kernels -- the sweep kernel, which
+// skips a rare column, and fixup_4s_kernel, which redoes it -- and they must agree on every column, so this part is
+// written with explicitly rounded operations: no context-dependent FMA contraction, the same bits everywhere.
+#if defined(__CUDA_ARCH__)
+#define CRT_MUL(a, b) __dmul_rn((a), (b))
+#define CRT_ADD(a, b) __dadd_rn((a), (b))
+#define CRT_SUB(a, b) __dsub_rn((a), (b))
+#else
+#define CRT_MUL(a, b) ((a) * (b))
+#define CRT_ADD(a, b) ((a) + (b))
+#define CRT_SUB(a, b) ((a) - (b))
+#endif
+CRT_HD void l2_4s(const Scen4s& s, double omega, Eig4s& E, double& dif, double& disc) {
+    const double h = CRT_MUL(0.5, omega);
+    const double al = CRT_MUL(CRT_MUL(h, CRT_SUB(1.0, s.mu_s)), s.G2);   // alpha_p = alpha_m (ref :190-191), P = 1
+    const double be = CRT_MUL(CRT_MUL(h, CRT_SUB(1.0, s.mu_s)), s.G1);   // beta  (ref :192-193)
+    const double ga = CRT_MUL(CRT_MUL(h, s.mu_s), s.G1);                 // gamma (ref :194-195)
+    // index 0 <-> sector 2 (|mu| in [mu_s, 1]), index 1 <-> sector 1;  q = -(P - Q) diagonal
+    const double T00 = CRT_MUL(CRT_SUB(CRT_MUL(2.0, al), s.G2), s.inv_m2), T01 = CRT_MUL(CRT_MUL(2.0, be), s.inv_m2);
+    const double T10 = CRT_MUL(CRT_MUL(2.0, be), s.inv_m1), T11 = CRT_MUL(CRT_SUB(CRT_MUL(2.0, ga), s.G1), s.inv_m1);
+    E.N00 = -CRT_MUL(s.q0, T00); E.N01 = -CRT_MUL(s.q0, T01); E.N10 = -CRT_MUL(s.q1, T10); E.N11 = -CRT_MUL(s.q1, T11);
+    // eigenvalues of N (real: N01 N10 >= 0)
+    const double tr = CRT_ADD(E.N00, E.N11);
+    dif = CRT_SUB(E.N00, E.N11);
+    disc = sqrt(CRT_ADD(CRT_MUL(dif, dif), CRT_MUL(4.0, CRT_MUL(E.N01, E.N10))));
+    const double det = CRT_SUB(CRT_MUL(E.N00, E.N11), CRT_MUL(E.N01, E.N10));
+    E.l2[0] = CRT_MUL(0.5, CRT_ADD(tr, disc));
+    E.l2[1] = det / E.l2[0];
+}
+CRT_HD void eig_4s(const Scen4s& s, double omega, Eig4s& E) {
+    double dif, disc;
+    l2_4s(s, omega, E, dif, disc);
+    const double N00 = E.N00, N01 = E.N01, N10 = E.N10, N11 = E.N11;
+    if (dif >= 0.0) {
+        E.phi[0][0] = E.l2[0] - N11; E.phi[0][1] = N10;
+        E.phi[1][0] = N01;           E.phi[1][1] = 0.5 * (-dif - disc);   // l2[1] - N00 without cancellation
+    } else {
+        E.phi[0][0] = N01;           E.phi[0][1] = 0.5 * (-dif + disc);   // l2[0] - N00
+        E.phi[1][0] = 0.5 * (dif - disc); E.phi[1][1] = N10;              // l2[1] - N11
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double nrm = rcp_nr(fmax(fabs(E.phi[i][0]), fabs(E.phi[i][1])));
+        E.phi[i][0] *= nrm;
+        E.phi[i][1] *= nrm;
+    }
+}
+// rare columns: vanishing / negative lambda_1^2, kappa near lambda_k  (also catches NaN inputs)
+CRT_HD bool ordinary_4s(const Scen4s& s, const double (&l2)[2]) {
+    const double k2g = CRT_MUL(s.kappa, s.kappa);
+    const double w = CRT_MUL(CRT_4S_RESONANCE_WIDTH, k2g);
+    return CRT_MUL(CRT_MUL(l2[1], s.L_T), s.L_T) >= CRT_4S_ENTIRE_BELOW && fabs(CRT_SUB(k2g, l2[0])) > w && fabs(CRT_SUB(k2g, l2[1])) > w;
+}
+
+// The rare columns, OUT OF LINE and self-contained (scalars in, coefficients out through memory; it rebuilds the
+// eigen-system itself): nothing of the ordinary path is live across this call or passed to it by reference, so the
+// ordinary path's coefficients stay in registers.  (With the general form called on coef_4s's own l2 / phi / k the
+// coefficient stage of every column carried a 960-byte stack frame: 4s 0.83 -> 0.56 of HBM peak.)
+CRT_HD_NOINLINE void coef_4s_rare(const Scen4s* sp, double r, double t, double rho, double Idr0, double Idf0, Coef4s* out) {
+    const Scen4s& s = *sp;
+    Eig4s E;
+    eig_4s(s, r + t, E);
+    const double Nm[2][2] = {{E.N00, E.N01}, {E.N10, E.N11}};
+    Coef4s kg;
+    coef_4s_general(s, r, t, rho, Idr0, Idf0, Nm, E.l2, E.phi, kg);
+    // Resonance only (both modes exponential, nothing can overflow): keep the column on the fast level path --
+    // scaled growing modes, exponentials by recurrence -- with X = R_k(x) flagged in lam[0]'s low bits.
+    const int mode = unpack_mode_4s(kg.lam[0]);
+    const double l0 = sqrt(E.l2[0]);
+    if ((mode & 1) == 0 && (mode >> 1) != 0 && l0 * s.L_T < 600.0) {
+        kg.lam[0] = tag_res_4s(l0, mode >> 1);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double gi = exp_neg(kg.lam[i] * s.L_T);
+            kg.dnP[i] *= gi;
+            kg.upP[i] *= gi;
+        }
+    }
+    *out = kg;
+}
+
+// Ordinary columns only.  For a rare column it returns lam[0] = NaN and the CALLER invokes coef_4s_rare -- from a
+// place where little is live (the call sitting inside this function cost every column ~200 bytes of spills).
+CRT_HD bool coef_4s_is_rare(const Coef4s& k) { return k.lam[0] != k.lam[0]; }
 CRT_HD Coef4s coef_4s(const Scen4s& s, double r, double t, double rho, double Idr0, double Idf0) {
     const double omega = r + t;                                   // ref :180
     const double R_dr0 = Idr0 * s.inv_pi_mu0;                     // I / (pi mu): irradiance -> radiance (ref :169)
     const double R_df0 = Idf0 * (1.0 / CRT_PI);                   // ref :170
-    const double al = 0.5 * omega * (1.0 - s.mu_s) * s.G2;        // alpha_p = alpha_m (ref :190-191), P = 1
-    const double be = 0.5 * omega * (1.0 - s.mu_s) * s.G1;        // beta  (ref :192-193)
-    const double ga = 0.5 * omega * s.mu_s * s.G1;                // gamma (ref :194-195)
     const double e1 = 0.25 * omega * R_dr0 * s.mu_s;              // eps_1 (ref :196-197)
     const double e2 = 0.25 * omega * R_dr0 * (1.0 - s.mu_s);      // eps_2 (ref :198-199)
     const double m1 = s.m1, m2 = s.m2;
-    // index 0 <-> sector 2 (|mu| in [mu_s, 1]), index 1 <-> sector 1
     const double q0 = s.q0, q1 = s.q1;                            // -(P - Q) diagonal
-    const double T00 = (2.0 * al - s.G2) * s.inv_m2, T01 = 2.0 * be * s.inv_m2;
-    const double T10 = 2.0 * be * s.inv_m1, T11 = (2.0 * ga - s.G1) * s.inv_m1;
-    const double N00 = -q0 * T00, N01 = -q0 * T01, N10 = -q1 * T10, N11 = -q1 * T11;
     const double G = s.kappa * s.mu0;
     const double vD0 = G * e2 * s.inv_m2, vD1 = G * e1 * s.inv_m1;  // forcing of rows 1, 2 (ref :80-87)
-
-    // eigenpairs of N (real: N01 N10 >= 0)
-    const double tr = N00 + N11, dif = N00 - N11;
-    const double disc = sqrt(dif * dif + 4.0 * N01 * N10);
-    const double det = N00 * N11 - N01 * N10;
-    double l2[2];
-    l2[0] = 0.5 * (tr + disc);
-    l2[1] = det * rcp_nr(l2[0]);
-    double phi[2][2];
-    if (dif >= 0.0) {
-        phi[0][0] = l2[0] - N11; phi[0][1] = N10;
-        phi[1][0] = N01;         phi[1][1] = 0.5 * (-dif - disc);   // l2[1] - N00 without cancellation
-    } else {
-        phi[0][0] = N01;         phi[0][1] = 0.5 * (-dif + disc);   // l2[0] - N00
-        phi[1][0] = 0.5 * (dif - disc); phi[1][1] = N10;            // l2[1] - N11
+    Eig4s E;
+    eig_4s(s, omega, E);
+    if (!ordinary_4s(s, E.l2)) {  // the caller redoes this column with coef_4s_rare (see coef_4s_is_rare)
+        Coef4s kr;
+        kr.lam[0] = kr.lam[1] = kr.dnK = kr.upK = nan("");
+        kr.Idr0 = Idr0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) kr.dnP[i] = kr.dnM[i] = kr.upP[i] = kr.upM[i] = 0.0;
+        return kr;
     }
+    const double N00 = E.N00, N01 = E.N01, N10 = E.N10, N11 = E.N11;
+    const double (&l2)[2] = E.l2;
+    const double (&phi)[2][2] = E.phi;
     Coef4s k;
     double psi_[2][2], g[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        const double nrm = rcp_nr(fmax(fabs(phi[i][0]), fabs(phi[i][1])));
-        phi[i][0] *= nrm;
-        phi[i][1] *= nrm;
-    }
-    {   // rare columns: vanishing / negative lambda_1^2, kappa near lambda_k  (also catches NaN inputs)
-        const double k2g = s.kappa * s.kappa;
-        const bool ordinary = l2[1] * s.L_T * s.L_T >= 0.25 && fabs(k2g - l2[0]) > 0.05 * k2g && fabs(k2g - l2[1]) > 0.05 * k2g;
-        if (!ordinary) {
-            const double Nm[2][2] = {{N00, N01}, {N10, N11}};
-            coef_4s_general(s, r, t, rho, Idr0, Idf0, Nm, l2, phi, k);
-            return k;
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        k.lam[i] = sqrt(l2[i]);
+        k.lam[i] = i == 0 ? tag_res_4s(sqrt(l2[0]), 0) : sqrt(l2[i]);
         psi_[i][0] = -k.lam[i] * phi[i][0] * s.inv_q0;   // (P-Q)^{-1} phi lambda
         psi_[i][1] = -k.lam[i] * phi[i][1] * s.inv_q1;
         g[i] = exp_neg(k.lam[i] * s.L_T);
@@ -1628,21 +1731,23 @@ CRT_HD void level_4s_e(const Scen4s& s, const Coef4s& k, double eK, double m0, d
     level_4s_x(s, k, eK, eK, m0, p0, m1, p1, Idr, dn, up, F);
 }
 
-// Slow form: every basis function of level x evaluated directly (mode word: see Coef4s).
-CRT_HD_NOINLINE void basis_4s_slow(const Scen4s& s, const Coef4s& k, double x, double eK, double* b5) {
-    const int mode = unpack_mode_4s(k.lam[0]);
-    const double l0 = -k.lam[0], xr = s.L_T - x;
+// Slow form: every basis function of level x evaluated directly (mode word: see Coef4s).  Out of line, scalars by
+// value: the scenario / coefficient structs of the caller must not have their address taken (they would live in
+// local memory for the whole kernel).
+CRT_HD_NOINLINE void basis_4s_slow(double L_T, double kappa, double lam0_stored, double lam1, double x, double eK, double* b5) {
+    const int mode = unpack_mode_4s(lam0_stored);
+    const double l0 = -lam0_stored, xr = L_T - x;
     double X = eK, m1, p1;
     const double m0 = exp(-l0 * x), p0 = exp(-l0 * xr);
     if (mode & 1) {
-        csh_entire(k.lam[1], x, m1, p1);
+        csh_entire(lam1, x, m1, p1);
     } else {
-        m1 = exp(-k.lam[1] * x);
-        p1 = exp(-k.lam[1] * xr);
+        m1 = exp(-lam1 * x);
+        p1 = exp(-lam1 * xr);
     }
     const int res = mode >> 1;
-    if (res == 1) X = res_exp_4s(s.kappa, l0, x, eK);
-    else if (res == 2) X = (mode & 1) ? res_series_4s(s.kappa, k.lam[1], x) : res_exp_4s(s.kappa, k.lam[1], x, eK);
+    if (res == 1) X = res_exp_4s(kappa, l0, x, eK);
+    else if (res == 2) X = (mode & 1) ? res_series_4s(kappa, lam1, x) : res_exp_4s(kappa, lam1, x, eK);
     b5[0] = X; b5[1] = m0; b5[2] = p0; b5[3] = m1; b5[4] = p1;
 }
 
@@ -1653,12 +1758,32 @@ CRT_HD void level_4s(const Scen4s& s, const Coef4s& k, double x, double eK, doub
     if (k.lam[0] > 0.0) {
         exp_pm(k.lam[0] * x, m0, p0);
         exp_pm(k.lam[1] * x, m1, p1);
-        level_4s_e(s, k, eK, m0, p0, m1, p1, Idr, dn, up, F);
+        const int res = fast_res_4s(k.lam[0]);
+        const double X = res ? res_exp_4s(s.kappa, k.lam[res - 1], x, eK) : eK;
+        level_4s_x(s, k, eK, X, m0, p0, m1, p1, Idr, dn, up, F);
     } else {
         double b5[5];
-        basis_4s_slow(s, k, x, eK, b5);
+        basis_4s_slow(s.L_T, s.kappa, k.lam[0], k.lam[1], x, eK, b5);
         level_4s_x(s, k, eK, b5[0], b5[1], b5[2], b5[3], b5[4], Idr, dn, up, F);
     }
+}
+
+// One level of an ORDINARY 4s column (real, well separated eigenvalues; not resonant): what the row-sweep kernel
+// evaluates -- its rare columns are redone by fixup_4s_kernel, so none of the general machinery is compiled into it.
+CRT_HD void level_4s_plain(const Scen4s& s, const Coef4s& k, double x, double eK, double& Idr, double& dn, double& up,
+                           double& F) {
+    double m0, p0, m1, p1;
+    if (k.lam[0] > 0.0) {
+        exp_pm(k.lam[0] * x, m0, p0);
+        exp_pm(k.lam[1] * x, m1, p1);
+    } else {  // lam_0 LAI >= 600: unscaled coefficients, direct exponentials
+        const double l0 = -k.lam[0], xr = s.L_T - x;
+        m0 = exp(-l0 * x);
+        p0 = exp(-l0 * xr);
+        m1 = exp(-k.lam[1] * x);
+        p1 = exp(-k.lam[1] * xr);
+    }
+    level_4s_e(s, k, eK, m0, p0, m1, p1, Idr, dn, up, F);
 }
 
 // L[j], eK[j] = exp(-kappa L[j]) level tables.
@@ -1673,6 +1798,15 @@ CRT_HD void column_4s(const Scen4s& s, const double* L, const double* eK, int n_
     Coef4s k[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) k[v] = coef_4s(s, in.leaf_r[v], in.leaf_t[v], in.soil_r[v], in.Idr0[v], in.Idf0[v]);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        if (coef_4s_is_rare(k[v])) {
+            Coef4s kg;  // through copies: neither k[] nor s may have their address taken on the common path
+            const Scen4s sg = s;
+            coef_4s_rare(&sg, in.leaf_r[v], in.leaf_t[v], in.soil_r[v], in.Idr0[v], in.Idf0[v], &kg);
+            k[v] = kg;
+        }
+    }
     double gnd[VEC][3];
     const double tol = 8.0 * 2.220446049250313e-16 * s.L_T;
     for (int j0 = 0; j0 < n_z; j0 += LV4) {
@@ -1697,7 +1831,9 @@ CRT_HD void column_4s(const Scen4s& s, const double* L, const double* eK, int n_
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 if (rec[v]) {
-                    level_4s_e(s, k[v], eK[j], m0[v], p0[v], m1[v], p1[v], Idr[v], dn[v], up[v], F[v]);
+                    const int res = fast_res_4s(k[v].lam[0]);
+                    const double X = res ? res_exp_4s(s.kappa, k[v].lam[res - 1], L[j], eK[j]) : eK[j];
+                    level_4s_x(s, k[v], eK[j], X, m0[v], p0[v], m1[v], p1[v], Idr[v], dn[v], up[v], F[v]);
                     m0[v] *= qi0[v];
                     p0[v] *= qd0[v];
                     m1[v] *= qi1[v];

@@ -861,7 +861,7 @@ struct RowsTraits<CRT1D_SCHEME_4S> {
     static __device__ __forceinline__ double rho_c(const Coef&) { return 0.0; }
     static __device__ __forceinline__ void level(const Scen& sc, const Coef& k, const double* tab, int n_z, int j,
                                                  double (&f)[NF]) {
-        level_4s(sc, k, tab[j], tab[n_z + j], f[0], f[1], f[2], f[3]);
+        level_4s_plain(sc, k, tab[j], tab[n_z + j], f[0], f[1], f[2], f[3]);
     }
 };
 
@@ -942,6 +942,17 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_rows_kernel(const crt1d_batc
                 b1.Idr0[0] = b.Idr0[v];
                 b1.Idf0[0] = b.Idf0[v];
                 k[v] = TR::coef(sc, b1);
+                bool redone_later = false;
+                if constexpr (SCHEME == CRT1D_SCHEME_4S) {
+                    // rare column (vanishing / negative eigenvalue, kappa ~ lambda_k): fixup_4s_kernel, launched right after
+                    // this kernel, recomputes it in full and adds its share of the absorbed sums; here it sweeps harmless
+                    // finite numbers (zero coefficients) and contributes nothing
+                    redone_later = coef_4s_is_rare(k[v]);
+                    if (redone_later) {
+                        k[v].lam[0] = k[v].lam[1] = 1.0;
+                        k[v].dnK = k[v].upK = 0.0;
+                    }
+                }
                 double a[NC];
                 TR::pack(k[v], a);
                 if constexpr (!DIAG) {  // reduced-diagnostic instantiation: coefficients are never stored
@@ -953,7 +964,7 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_rows_kernel(const crt1d_batc
                     double gnd[NF], top[NF];
                     TR::level(sc, k[v], sm, n_z, 0, gnd);
                     TR::level(sc, k[v], sm, n_z, n_z - 1, top);
-                    const double ab = absorbed_from_ends(top[0], gnd[0], top[1], gnd[1], top[2], gnd[2]);
+                    const double ab = redone_later ? 0.0 : absorbed_from_ends(top[0], gnd[0], top[1], gnd[1], top[2], gnd[2]);
                     if (out.status && !isfinite(ab)) atomicOr(out.status + s, CRT1D_STATUS_NONFINITE);
                     for (int q = 0; q < (out.absorbed ? out.n_bw : 0); ++q) a4[q] += out.band_w[(int64_t)q * n_wl + c0 + v] * ab;
                 }
@@ -1136,6 +1147,126 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_rows_kernel(const crt1d_batc
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 4s, row-sweep path: the RARE columns.  coef_4s hands a column over when its smaller eigenvalue^2 is (nearly) zero or
+// negative (omega -> 1) or kappa sits within CRT_4S_RESONANCE_WIDTH of an eigenvalue (~0.2 % of a sweep's columns).
+// Their general closed form (coef_4s_general: entire basis, resonance-safe particular solution, direct evaluation of
+// every basis function) is 10x the code and registers of the ordinary one; compiled into solve_rows_kernel it cost
+// EVERY column (0.84 -> 0.56 of HBM peak: spilled recurrence factors re-read in the level loop).  So the sweep kernel
+// treats a rare column as all-zero coefficients, and this kernel -- launched on the same stream right after it --
+// redoes them: one warp per scenario re-evaluates the (cheap, deterministic) rarity test of every band, and for the
+// rare bands solves the general form and writes all their levels and their share of the absorbed sums (added in band
+// order: deterministic).
+// ---------------------------------------------------------------------------------------------
+#ifndef CRT_FIXUP_MINB
+#define CRT_FIXUP_MINB 20
+#endif
+// One WARP per scenario (a 32-thread CTA: the work is latency-bound serial arithmetic, so what counts is how many
+// scenarios are resident -- 20+ per SM, i.e. a whole launch of ~4000 scenarios in about one wave).  The warp tests 32
+// consecutive bands per step (one per lane) and collects the rare ones, in band order, into a pending list; a flush
+// then (i) lets lane i solve the general coefficients of pending column i -- different columns on different lanes, in
+// parallel -- into shared memory, (ii) shares the (column, level) evaluations out over all 32 lanes, (iii) adds the
+// columns' absorbed-sum terms in list (= band) order.
+struct FixupSlot {
+    double c[13];  // Coef4s, field order of RowsTraits<4S>::pack + Idr0
+};
+__global__ void __launch_bounds__(32, CRT_FIXUP_MINB) fixup_4s_kernel(const crt1d_batch in, const crt1d_out out) {
+    extern __shared__ double tab[];  // L[j], exp(-K_b L[j]), then 32 coefficient slots
+    __shared__ int pend[32];
+    const int64_t s = blockIdx.x;
+    const int n_z = in.n_z, n_wl = in.n_wl;
+    const int lane = threadIdx.x;
+    FixupSlot* const slot = reinterpret_cast<FixupSlot*>(tab + 2 * n_z);
+    for (int j = lane; j < n_z; j += 32) fill_level_tables<CRT1D_SCHEME_4S>(in, s, j, tab);
+    __syncwarp();
+    const double mu_s = in.mu_s > 0.0 ? in.mu_s : 0.501;
+    const Scen4s sc = scen_4s(in.psi[s], in.K_b[s], in.G_int[2 * s], in.G_int[2 * s + 1], mu_s, tab[0]);
+    const bool f32 = out.profile_f32 != 0;
+    const int64_t prof = (int64_t)n_z * n_wl;
+    void* const pf[4] = {prof_base(out.I_dr, f32, s * prof), prof_base(out.I_df_d, f32, s * prof),
+                         prof_base(out.I_df_u, f32, s * prof), prof_base(out.F, f32, s * prof)};
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    int n = 0, total = 0;
+
+    auto load_slot = [&](int i) {
+        Coef4s k;
+        const double* c = slot[i].c;
+        k.lam[0] = c[0]; k.lam[1] = c[1]; k.dnP[0] = c[2]; k.dnP[1] = c[3]; k.dnM[0] = c[4]; k.dnM[1] = c[5];
+        k.upP[0] = c[6]; k.upP[1] = c[7]; k.upM[0] = c[8]; k.upM[1] = c[9]; k.dnK = c[10]; k.upK = c[11]; k.Idr0 = c[12];
+        return k;
+    };
+    auto flush = [&]() {
+        double ab = 0.0;
+        if (lane < n) {  // (i) coefficients, one pending column per lane
+            const int cc = pend[lane];
+            const BandIn<1> b = load_bands<1>(in, s, cc);
+            Coef4s k;
+            coef_4s_rare(&sc, b.leaf_r[0], b.leaf_t[0], b.soil_r[0], b.Idr0[0], b.Idf0[0], &k);
+            double* c = slot[lane].c;
+            c[0] = k.lam[0]; c[1] = k.lam[1]; c[2] = k.dnP[0]; c[3] = k.dnP[1]; c[4] = k.dnM[0]; c[5] = k.dnM[1];
+            c[6] = k.upP[0]; c[7] = k.upP[1]; c[8] = k.upM[0]; c[9] = k.upM[1]; c[10] = k.dnK; c[11] = k.upK; c[12] = k.Idr0;
+            double g[4], t[4];  // its ground and top levels: the absorbed-sum term
+            level_4s(sc, k, tab[0], tab[n_z], g[0], g[1], g[2], g[3]);
+            level_4s(sc, k, tab[n_z - 1], tab[2 * n_z - 1], t[0], t[1], t[2], t[3]);
+            ab = absorbed_from_ends(t[0], g[0], t[1], g[1], t[2], g[2]);
+            if (out.status && !isfinite(ab)) atomicOr(out.status + s, CRT1D_STATUS_NONFINITE);
+        }
+        __syncwarp();
+        const int items = n * n_z;  // (ii) every level of every pending column
+        for (int it = lane; it < items; it += 32) {
+            const int col = it / n_z, j = it - col * n_z;
+            const Coef4s k = load_slot(col);
+            double f[4][1];
+            level_4s(sc, k, tab[j], tab[n_z + j], f[0][0], f[1][0], f[2][0], f[3][0]);
+            const int64_t off = (int64_t)j * n_wl + pend[col];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) st_prof<1>(pf[q], f32, off, f[q]);
+        }
+        if (out.absorbed) {  // (iii) in list order, the same sum on every lane
+            for (int col = 0; col < n; ++col) {
+                const double a = __shfl_sync(0xffffffffu, ab, col);
+                const int cc = pend[col];
+                for (int q = 0; q < out.n_bw; ++q) acc[q] += out.band_w[(int64_t)q * n_wl + cc] * a;
+            }
+        }
+        __syncwarp();
+        total += n;
+        n = 0;
+    };
+
+    for (int base = 0; base < n_wl; base += 32) {
+        const int c = base + lane;
+        bool rare = false;
+        if (c < n_wl) {  // the same test, on the same bits, as coef_4s made in the sweep kernel (l2_4s: explicit roundings)
+            const int64_t lo = (int64_t)in.leaf_idx[s] * n_wl + c;
+            Eig4s E;
+            double dif, disc;
+            l2_4s(sc, __ldg(in.leaf_r_lib + lo) + __ldg(in.leaf_t_lib + lo), E, dif, disc);
+            rare = !ordinary_4s(sc, E.l2);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, rare);
+        if (mask == 0) continue;
+        const int add = __popc(mask);
+        if (n + add > 32) flush();
+        if (rare) pend[n + __popc(mask & ((1u << lane) - 1u))] = c;
+        n += add;
+        __syncwarp();
+    }
+    if (n > 0) flush();
+    if (out.absorbed && total > 0 && lane < out.n_bw) {
+        double v = 0.0;  // lane q keeps acc[q]; static indexing only
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v = lane == q ? acc[q] : v;
+        out.absorbed[s * out.n_bw + lane] += v;  // after the sweep kernel's own sum: stream order
+    }
+}
+static cudaError_t launch_fixup_4s(const crt1d_batch& in, const crt1d_out& out, cudaStream_t stream) {
+    const size_t smem = (size_t)2 * in.n_z * sizeof(double) + 32 * sizeof(FixupSlot);
+    if (cudaError_t e = ensure_smem(fixup_4s_kernel, smem); e != cudaSuccess) return e;
+    fixup_4s_kernel<<<(unsigned)in.n_scen, 32, smem, stream>>>(in, out);
+    return cudaGetLastError();
+}
+
 template <int SCHEME>
 static size_t rows_shared_bytes(int n_z, int n_wl, int split = 1, int vec = 2) {
     int ld = (n_wl + 1) & ~1;
@@ -1162,7 +1293,9 @@ static cudaError_t launch_rows_t(const crt1d_batch& in, const crt1d_out& out, in
         auto kd = solve_rows_kernel<SCHEME, VEC, 10, 256, false, FUSED, DM, true>;  // LV, F32 play no part
         if (cudaError_t e = ensure_smem(kd, smem_d); e != cudaSuccess) return e;
         kd<<<(unsigned)in.n_scen, diag_threads(SCHEME == CRT1D_SCHEME_4S ? 64 : 128), smem_d, stream>>>(in, out, 1);
-        return cudaGetLastError();
+        if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) return e;
+        if constexpr (SCHEME == CRT1D_SCHEME_4S) return launch_fixup_4s(in, out, stream);
+        return cudaSuccess;
     }
     if constexpr (SCHEME == CRT1D_SCHEME_4S) {
         // Two CTAs per SM, each on half of the scenario's band chunks (half the coefficient array: 2 x ~106 KB):
@@ -1178,13 +1311,16 @@ static cudaError_t launch_rows_t(const crt1d_batch& in, const crt1d_out& out, in
                 if (e != cudaSuccess) return e;
             }
             kern2<<<(unsigned)(in.n_scen * 2), min(th, MAXT / 2), smem2, stream>>>(in, out, 2);
-            return cudaGetLastError();
+            if (e = cudaGetLastError(); e != cudaSuccess) return e;
+            return launch_fixup_4s(in, out, stream);
         }
     }
     auto kern = solve_rows_kernel<SCHEME, VEC, LV, MAXT, F32, FUSED, 1>;
     if (cudaError_t e = ensure_smem(kern, smem); e != cudaSuccess) return e;
     kern<<<(unsigned)in.n_scen, th, smem, stream>>>(in, out, 1);
-    return cudaGetLastError();
+    if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) return e;
+    if constexpr (SCHEME == CRT1D_SCHEME_4S) return launch_fixup_4s(in, out, stream);
+    return cudaSuccess;
 }
 
 // 4s level groups: 10 levels per work item.  Measured (two CTAs per SM): 15 levels 0.80, 30 levels 0.81 vs 0.77 --

@@ -74,7 +74,13 @@ CRT_HD void fill_level_tables(const crt1d_batch& in, int64_t s, int j, double* t
         }
         if (j < n_z - 1) {
             const double dl = Lj - lai[j + 1];                                    // :41
-            const double tdj = in.tau_d_lev[(int64_t)in.lai_idx[s] * n_z + j];    // :53 (prologue quadrature / 9sky)
+            // :53 (prologue quadrature / 9sky).  A zero-thickness layer has tau_d = 1 and is the identity; the layer
+            // algebra (:85-88, divisions by (1 - td) rho) reaches that limit smoothly -- any td in [1 - 1e-15, 1)
+            // gives the same fluxes to 1e-14 -- but not AT td == 1 (0 * inf).  The reference's own quad returns
+            // 1 - 2^-53 for L = 0, an exact prologue (the device Gauss-Legendre rule) returns 1: use the former.
+            // (Only the exact value is replaced: the "9sky" rule legitimately returns td > 1 for thin layers.)
+            const double td_in = in.tau_d_lev[(int64_t)in.lai_idx[s] * n_z + j];
+            const double tdj = td_in == 1.0 ? 1.0 - 0x1p-53 : td_in;
             const double fs = exp(-K_b * ((Lj + lai[j + 1]) / 2.0));              // fracsun, :57-58
             tab[2 * n_z + j] = tdj;
             tab[3 * n_z + j] = 1.0 - tdj;

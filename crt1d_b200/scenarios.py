@@ -109,6 +109,20 @@ class ScenarioBatch:
             setattr(out, k, getattr(self, k)[lo:hi])
         return out
 
+    def permuted(self, order):
+        """The same scenarios in another order (`order[i]` = index of the scenario that comes i-th) over the same
+        libraries -- a batch is index arrays, so this costs 20 bytes per scenario."""
+        import copy
+
+        order = np.asarray(order, dtype=np.int64)
+        if order.shape != (self.n_scen,) or not np.array_equal(np.sort(order), np.arange(self.n_scen)):
+            raise ValueError("order must be a permutation of range(n_scen)")
+        out = copy.copy(self)
+        out.psi = np.ascontiguousarray(self.psi[order])
+        for k in ("lai_idx", "leaf_idx", "soil_idx", "sky_idx"):
+            setattr(out, k, np.ascontiguousarray(getattr(self, k)[order]))
+        return out
+
     @classmethod
     def from_params(cls, p, leaf_angle=None):
         """A one-scenario batch from a reference-style parameter dict."""

@@ -114,7 +114,7 @@ class SweepRunner:
     """
 
     def __init__(self, spec, scheme="2s", *, chunk=4096, device=None, n_buffers=2, bands=("PAR", "NIR"),
-                 profiles=True, n_quad=32, profile_dtype=None, n_diag_buffers=1):
+                 profiles=True, n_quad=32, profile_dtype=None, n_diag_buffers=1, order=None):
         import warnings
 
         from . import engine
@@ -122,6 +122,12 @@ class SweepRunner:
         from .spectra import x_frac_in_bounds
 
         self.engine = engine
+        # execution order: None = as given, or an explicit permutation (`ScenarioBatch.permuted`).  Profiles and
+        # `absorbed` come out in EXECUTION order; `absorbed_in_spec_order()` undoes it.
+        self.order = None
+        if order is not None:
+            self.order = np.asarray(order)
+            spec = spec.permuted(self.order)
         self.spec, self.scheme = spec, scheme
         self.chunk = int(min(chunk, spec.n_scen))
         self.n_buffers = int(n_buffers)
@@ -151,6 +157,16 @@ class SweepRunner:
     def absorbed(self):
         """Diagnostics `(S, n_bands)` of the most recent step."""
         return None if self.absorbed_bufs is None else self.absorbed_bufs[self._last]
+
+    def absorbed_in_spec_order(self):
+        """`absorbed` re-ordered to the scenario order of the batch this runner was built from."""
+        if self.order is None:
+            return self.absorbed
+        import torch
+
+        out = torch.empty_like(self.absorbed)
+        out[torch.as_tensor(self.order, device=self.absorbed.device)] = self.absorbed
+        return out
 
     @property
     def n_chunks(self):

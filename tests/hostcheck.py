@@ -26,6 +26,37 @@ def build(force=False):
     return LIB
 
 
+def build_variant(name, defines):
+    """A second copy of the checker compiled with `-D` overrides (e.g. the 4s branch windows), for tests that compare
+    two evaluation forms of the same kernel source."""
+    path = os.path.join(HERE, "_hostcheck", f"libhostcheck_{name}.so")
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("crt_core.cuh", "crt_scheme.cuh", "crt_leafangle.cuh", "crt_spectra.cuh")]
+    if not os.path.exists(path) or any(os.path.getmtime(d) > os.path.getmtime(path) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", "-ffp-contract=off"]
+                              + [f"-D{d}" for d in defines] + ["-o", path, SRC])
+    L = C.CDLL(path)
+    L.hostcheck_solve.restype = C.c_int
+    L.hostcheck_solve.argtypes = [C.c_int, C.POINTER(_abi.Batch), C.POINTER(_abi.Out), C.c_int]
+    return L
+
+
+class use_lib:
+    """Context manager: route `solve()` through another build of the checker."""
+
+    def __init__(self, L):
+        self.L = L
+
+    def __enter__(self):
+        global _lib
+        lib()
+        self.saved, _lib = _lib, self.L
+        return self
+
+    def __exit__(self, *exc):
+        global _lib
+        _lib = self.saved
+
+
 def lib():
     global _lib
     if _lib is None:

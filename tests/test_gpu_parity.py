@@ -1090,3 +1090,4 @@ def test_nonuniform_lai_sweep_batched(scheme):
                 assert_close(got[:, sel], ref[k], 1e-10, f"nonuniform 4s[{i}].{k}", atol=1e-14 * float(np.max(np.abs(ref[k]))))
             else:
                 assert_close_same_nans(got, ref[k], RTOL, f"nonuniform {scheme}[{i}].{k}", atol=1e-300)
+

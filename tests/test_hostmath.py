@@ -273,3 +273,51 @@ def test_4s_thin_canopy_resonance_and_conservative_limit():
     sol = _solve(q, "4s", vec=1)
     for k in ref:
         assert_close_4s(sol[k], ref[k], f"omega=1 {k}")
+
+
+def test_4s_resonance_window_accuracy():
+    """How wide the kappa ~ lambda_k window of coef_4s must be.  Bands whose omega brings lambda_0^2 (then lambda_1^2)
+    to within delta = |kappa^2 - lambda_k^2| / kappa^2 of kappa^2, delta from 1e-1 down to 1e-9 on both sides, through
+    three builds of the same kernel source: a wide window (0.05: the resonance-safe form wherever the ordinary one loses
+    more than 4e-13), the ordinary form everywhere (window = 0), and the default.  The ordinary form loses ~2e-14 / delta;
+    the default must stay within 5e-11 of the wide build for every delta (it switches at CRT_4S_RESONANCE_WIDTH = 1e-3)."""
+    from scipy.optimize import brentq
+
+    from crt1d_b200.leaf_angle import LeafAngle
+    from crt1d_b200.solvers import common
+    from util import fourstream_l2
+
+    safe = hostcheck.build_variant("4s_wide", ["CRT_4S_ENTIRE_BELOW=-1.0", "CRT_4S_RESONANCE_WIDTH=0.05"])
+    plain = hostcheck.build_variant("4s_plain", ["CRT_4S_ENTIRE_BELOW=-1.0", "CRT_4S_RESONANCE_WIDTH=-1.0"])
+    la = LeafAngle.from_mla(57)
+    mu_s = 0.501
+    G1, G2 = common.G_sector_integrals(la.G_fn, mu_s)
+    worst_default, worst_plain_outside = 0.0, 0.0
+    for target, which in ((3.0, 0), (0.3, 1)):
+        psi = brentq(lambda p: la.K_b_fn(p) ** 2 - target, 0.01, 1.55)
+        k2 = la.K_b_fn(psi) ** 2
+        om0 = brentq(lambda o: fourstream_l2(o, G1, G2, mu_s)[which] - k2, 0.01, 0.99)
+        d = np.logspace(-1, -9, 120)
+        om = np.r_[om0 - d * om0, om0 + d * (1 - om0) * 0.5]
+        om = om[(om > 0.01) & (om < 0.99)]
+        delta = np.array([abs(k2 - fourstream_l2(o, G1, G2, mu_s)[which]) / k2 for o in om])
+        nw = om.size
+        for lai_tot in (0.5, 3.0, 8.0):
+            b = ScenarioBatch(psi=[psi], lai_lib=np.linspace(1, 0, 30) * lai_tot, leaf_r_lib=0.55 * om, leaf_t_lib=0.45 * om,
+                              soil_r_lib=np.full(nw, 0.2), I_dr0_lib=np.full(nw, 1.0), I_df0_lib=np.full(nw, 0.3),
+                              lai_idx=[0], leaf_idx=0, soil_idx=0, sky_idx=0, leaf_angle=la)
+            pro = host_prologue(b, "4s")
+            dflt = hostcheck.solve(b, "4s", pro, vec=1)
+            with hostcheck.use_lib(safe):
+                ref = hostcheck.solve(b, "4s", pro, vec=1)
+            with hostcheck.use_lib(plain):
+                ordn = hostcheck.solve(b, "4s", pro, vec=1)
+            for k in ("I_df_d", "I_df_u"):
+                scale = np.max(np.abs(ref[k][0]), axis=0)
+                e_d = np.max(np.abs(dflt[k][0] - ref[k][0]), axis=0) / scale
+                e_o = np.max(np.abs(ordn[k][0] - ref[k][0]), axis=0) / scale
+                worst_default = max(worst_default, float(e_d.max()))
+                worst_plain_outside = max(worst_plain_outside, float(e_o[delta > 1e-3].max()))
+                assert e_o[delta < 1e-6].max() > 1e-9  # the ordinary form really does fail close to the resonance
+    assert worst_default < 5e-11, worst_default
+    assert worst_plain_outside < 5e-11, worst_plain_outside

@@ -1,0 +1,6 @@
+#!/bin/bash
+O=$PWD/gpurun_out/r2; mkdir -p $O
+for lib in b200 fx8 fx12 fx32; do
+CRT1D_B200_LIB=$PWD/crt1d_b200/libcrt1d_$lib.so timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 24 --csv --log-file $O/l_$lib.csv python bench.py --scheme 4s --scenarios 16576 --steps 1 --warmup 2 --no-cpu-baseline --no-e2e --no-legs > /dev/null 2>&1
+echo "== $lib"; grep -i "fixup" $O/l_$lib.csv | awk -F'","' '{print substr($5,1,40), $NF}' | tail -3
+done
