@@ -1091,3 +1091,4 @@ def test_nonuniform_lai_sweep_batched(scheme):
             else:
                 assert_close_same_nans(got, ref[k], RTOL, f"nonuniform {scheme}[{i}].{k}", atol=1e-300)
 
+

@@ -189,7 +189,6 @@ int main(int argc, char** argv) {
     COLC(7, 544, 200 * 1024, 2, 0) COLC(7, 544, 200 * 1024, 2, 1) COLC(7, 544, 200 * 1024, 2, 5)
     COLC(7, 352, 200 * 1024, 3, 0) COLC(7, 352, 200 * 1024, 3, 1) COLC(7, 352, 200 * 1024, 3, 5) COLC(7, 352, 110 * 1024, 3, 1) COLC(7, 352, 110 * 1024, 3, 5)
     COLC(4, 256, 86 * 1024, 5, 1) COLC(4, 256, 86 * 1024, 5, 5) COLC(4, 352, 200 * 1024, 3, 1) COLC(4, 352, 110 * 1024, 3, 1)
-    COLC(7, 128, 50 * 1024, 9, 1)
 #define ITEMS(K, NAME, NF, BLK, LVV, SMEM) { double gb = NF * per * 8.0 / 1e9; \
         CK(cudaFuncSetAttribute(K<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
         float ms = time_ms([&] { K<NF><<<S, BLK, SMEM>>>(F, n_z, n_wl, LVV); }, reps); \
