@@ -668,11 +668,15 @@ CRT_HD void column_n79(const ScenN79& s, const double* tab, int n_z, const BandI
 #pragma unroll
             for (int v = 0; v < VEC; ++v) { e0[v] = e_prev[v]; f0[v] = f_prev[v]; }
         } else if (sg > 0) {
-            out.ld_tmp(F_F, base - 1, e0);
-            out.ld_tmp(F_DN, base - 1, f0);
+            out.ld_pf(F_F, base - 1, 0, e0);
+            out.ld_pf(F_DN, base - 1, 1, f0);
         } else {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) e0[v] = f0[v] = 0.0;
+        }
+        if (sg >= 2) {  // start fetching the next segment's checkpoint now (consumed after this segment's two passes)
+            out.pf_tmp(F_F, base - CK - 1, 0);
+            out.pf_tmp(F_DN, base - CK - 1, 1);
         }
         {
             double eu[VEC], fu[VEC];
@@ -837,11 +841,15 @@ CRT_HD void column_zq(const ScenZq& s, const double* eK, int n_z, const BandIn<V
 #pragma unroll
             for (int v = 0; v < VEC; ++v) { e0[v] = e_prev[v]; f0[v] = f_prev[v]; }
         } else if (g > 0) {
-            out.ld_tmp(F_F, base - 1, e0);
-            out.ld_tmp(F_DN, base - 1, f0);
+            out.ld_pf(F_F, base - 1, 0, e0);
+            out.ld_pf(F_DN, base - 1, 1, f0);
         } else {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) { e0[v] = 0.0; f0[v] = x0[v]; }
+        }
+        if (g >= 2) {  // start fetching the next segment's checkpoint now (consumed after this segment's two passes)
+            out.pf_tmp(F_F, base - CK - 1, 0);
+            out.pf_tmp(F_DN, base - CK - 1, 1);
         }
         {
             double e[VEC], f[VEC];

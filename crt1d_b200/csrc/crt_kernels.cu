@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <mutex>
 #include <type_traits>
 
@@ -39,6 +40,8 @@ struct Tuning {
     bool force_vec1 = false;     // CRT1D_B200_FORCE_VEC1
     bool tile_2s = false;        // CRT1D_B200_2S_KERNEL=tile
     bool no_rows = false;        // CRT1D_B200_NO_ROWS
+    int fixup_parts = 0;         // CRT1D_B200_FIXUP_PARTS (0 = by level count)
+    bool no_flat = false;        // CRT1D_B200_NO_FLAT: tridiagonal schemes keep the (scenario, band tile) mapping
 };
 static Tuning read_tuning() {
     Tuning t;
@@ -51,6 +54,8 @@ static Tuning read_tuning() {
     t.force_vec1 = getenv("CRT1D_B200_FORCE_VEC1") != nullptr;
     if (const char* e = getenv("CRT1D_B200_2S_KERNEL")) t.tile_2s = e[0] != 'r';
     t.no_rows = getenv("CRT1D_B200_NO_ROWS") != nullptr;
+    t.no_flat = getenv("CRT1D_B200_NO_FLAT") != nullptr;
+    if (const char* e = getenv("CRT1D_B200_FIXUP_PARTS")) t.fixup_parts = atoi(e);
     return t;
 }
 static Tuning g_tuning = read_tuning();
@@ -93,7 +98,7 @@ __host__ __device__ constexpr bool uses_segments(int scheme) {
 }
 // slots (levels) of the segment store: the segment itself, plus zq_pa's checkpoints (its M-grid is not the output grid)
 __host__ __device__ inline int seg_slots(int scheme, int n_z) {
-    if (scheme != CRT1D_SCHEME_ZQ_PA) return SEG_CK;
+    if (scheme != CRT1D_SCHEME_ZQ_PA) return SEG_CK + 1;  // + the prefetch slot of the next checkpoint (pf_tmp / ld_pf)
     const int M = n_z < ZQPA_MAX_M ? n_z : ZQPA_MAX_M;
     return SEG_CK + 1 + (M - 1) / SEG_CK + 1;  // segment slots 0..CK (slot 0 = the pair below the segment) + checkpoints
 }
@@ -190,6 +195,23 @@ struct GlobalOut {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) x[v] = __ldcs(q + v);
         }
+    }
+    // Checkpoint prefetch: the back sweep needs the parked pair of the NEXT segment ~1000 cycles after it starts the
+    // current one, and an L2 round trip at that point is exposed latency in a latency-bound kernel (ncu: 21 % of the
+    // stall cycles were long-scoreboard).  pf_tmp starts the copy into this thread's slot SEG_CK of the segment store
+    // (cp.async: no registers held while it is in flight); ld_pf waits for it and reads the slot.
+    __device__ __forceinline__ void pf_tmp(int f, int j, int k) const {
+        const double* q = base[f] + at(f, j);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(seg + (SEG_CK * 2 + k) * VEC);
+        if constexpr (VEC == 2) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(q) : "memory");
+        } else {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(q) : "memory");
+        }
+    }
+    __device__ __forceinline__ void ld_pf(int f, int j, int k, double (&x)[VEC]) const {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        seg_ld(SEG_CK, k, x);
     }
     // segment store of the checkpointed Thomas sweeps: `slots` levels x 2 values x VEC columns per thread in
     // shared memory, thread-major with one pad element: thread stride (2 slots + 1) * VEC doubles is an odd
@@ -368,6 +390,122 @@ __global__ void __launch_bounds__(BLK, MINB) solve_kernel(const crt1d_batch in, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Flat column mapping for the tridiagonal schemes (zq, n79, zq_pa): the batch's column groups (VEC adjacent bands of
+// one scenario) are numbered through, scenario after scenario, and CTA c takes groups [c nthr, (c+1) nthr) -- so
+// every CTA is full.  With the (scenario, band tile) mapping of solve_kernel the last tile of a scenario is mostly
+// empty (2100 bands / 512 columns per tile: 26 of 256 threads in the fifth tile), and these kernels are bound by
+// the latency of their per-column recurrences at 16 warps per SM: the early-exiting warps are latency-hiding
+// capacity lost for a whole CTA lifetime (18 % of the warp slots at 2100 bands).  A CTA spans at most two scenarios
+// (launcher: nthr <= groups per scenario) and keeps both scenarios' level tables.
+// Canopy-absorbed sums: each CTA reduces its columns per spanned scenario in a fixed order into
+// partial[c][which][band group]; absorbed_flat_finish_kernel adds a scenario's partials in CTA order (deterministic).
+// ---------------------------------------------------------------------------------------------
+template <int SCHEME, int VEC, int BLK, int MINB, bool FAST>
+__global__ void __launch_bounds__(BLK, MINB) solve_flat_kernel(const crt1d_batch in, const crt1d_out out, int gps,
+                                                               double* __restrict__ partial) {
+    extern __shared__ double tab[];
+    __shared__ double red[BLK / 32][8];
+
+    const int nthr = blockDim.x;
+    const int n_z = in.n_z, n_wl = in.n_wl;
+    const int64_t g0 = (int64_t)blockIdx.x * nthr;
+    const int64_t total = in.n_scen * gps;
+    const int64_t g1 = min(total, g0 + nthr);  // this CTA's groups: [g0, g1)
+    const int64_t s_first = g0 / gps, s_last = (g1 - 1) / gps;
+    const size_t td = tab_doubles(SCHEME, n_z);
+
+    for (int j = threadIdx.x; j < n_z; j += nthr) {
+        fill_level_tables<SCHEME>(in, s_first, j, tab);
+        if (s_last != s_first) fill_level_tables<SCHEME>(in, s_last, j, tab + td);
+    }
+    __syncthreads();
+    if constexpr (SCHEME == CRT1D_SCHEME_ZQ_PA) {
+        for (int j = threadIdx.x; j < n_z; j += nthr) {
+            fill_level_tables_2<SCHEME>(in, s_first, j, tab);
+            if (s_last != s_first) fill_level_tables_2<SCHEME>(in, s_last, j, tab + td);
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < n_z; j += nthr) {
+            fill_level_tables_3<SCHEME>(in, s_first, j, tab);
+            if (s_last != s_first) fill_level_tables_3<SCHEME>(in, s_last, j, tab + td);
+        }
+        __syncthreads();
+    }
+
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    int which = 0;
+    const int64_t gid = g0 + threadIdx.x;
+    if (gid < g1) {
+        const int64_t s = gid / gps;
+        const int b0 = (int)(gid - s * gps) * VEC;
+        which = s != s_first;
+        const int64_t prof = (int64_t)n_z * n_wl;                       // doubles per scenario in a profile
+        const int64_t xprof = (int64_t)extra_rows(SCHEME, n_z) * n_wl;  // ... in an extra-output slot
+        const BandIn<VEC> b = load_bands<VEC>(in, s, b0);
+        GlobalOut<VEC, FAST> o;
+        o.stride = n_wl;
+        o.f32 = out.profile_f32 != 0;
+        o.seg = tab + 2 * td + (size_t)threadIdx.x * seg_thread_doubles<VEC>(SCHEME, n_z);
+        o.off = s * prof + b0;
+        o.xoff = s * xprof + b0;
+        o.base[F_IDR] = out.I_dr;
+        o.base[F_DN] = out.I_df_d;
+        o.base[F_UP] = out.I_df_u;
+        o.base[F_F] = out.F;
+        o.base[F_X0] = out.x0;
+        o.base[F_X1] = out.x1;
+        o.base[F_X2] = out.x2;
+        double rho_c[VEC], ab[VEC];
+        solve_column_group<SCHEME, VEC>(in, s, tab + which * td, b, o, rho_c, ab);
+        if (partial) {
+            for (int k = 0; k < out.n_bw; ++k) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[k] += out.band_w[(int64_t)k * n_wl + b0 + v] * ab[v];
+            }
+        }
+        if (out.status) {
+            bool bad = false;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) bad = bad || !isfinite(ab[v]);
+            if (bad) atomicOr(out.status + s, CRT1D_STATUS_NONFINITE);
+        }
+    }
+
+    if (partial) {  // fixed-order reduction: lanes by shuffle tree, warps in warp order
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            double v = (q >> 2) == which ? acc[q & 3] : 0.0;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            if (lane == 0) red[warp][q] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            double v = 0.0;
+            for (int w = 0; w < nthr / 32; ++w) v += red[w][threadIdx.x];
+            partial[(int64_t)blockIdx.x * 8 + threadIdx.x] = v;
+        }
+    }
+}
+
+// absorbed[s][k] = sum over the CTAs of solve_flat_kernel that hold columns of scenario s, in CTA order.
+__global__ void __launch_bounds__(256) absorbed_flat_finish_kernel(const double* __restrict__ partial, int64_t n_scen, int gps,
+                                                                   int nthr, int n_bw, double* __restrict__ absorbed) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_scen * n_bw) return;
+    const int64_t s = i / n_bw;
+    const int k = (int)(i - s * n_bw);
+    const int64_t c_lo = (s * gps) / nthr, c_hi = ((s + 1) * gps - 1) / nthr;
+    double v = 0.0;
+    for (int64_t c = c_lo; c <= c_hi; ++c) {
+        const int which = (c * nthr) / gps != s;  // slot 0 = the CTA's first scenario
+        v += partial[c * 8 + which * 4 + k];
+    }
+    absorbed[i] = v;
+}
+
 // Number of output fields a scheme writes (4 profiles + its extra slots).
 __host__ __device__ constexpr int n_out_fields(int scheme) {
     return scheme == CRT1D_SCHEME_ZQ ? 7 : scheme == CRT1D_SCHEME_N79 ? 6 : (scheme == CRT1D_SCHEME_BF || scheme == CRT1D_SCHEME_G77) ? 7 : 4;
@@ -391,9 +529,79 @@ static int tile_threads(int cfg, int blk) {
     return cfg;
 }
 
+// Stream-ordered scratch for the flat kernels' per-CTA absorbed partials (pool memory is kept across calls).
+static cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t stream) {
+    static std::once_flag once[64];
+    int dev = 0;
+    if (cudaError_t e = cudaGetDevice(&dev); e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) {
+        std::call_once(once[dev], [dev] {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t keep = UINT64_MAX;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+        });
+    }
+    return cudaMallocAsync(p, bytes, stream);
+}
+
+// Flat mapping (solve_flat_kernel) when a CTA cannot span more than two scenarios and two sets of level tables leave
+// the shared memory for the same number of resident CTAs.
+template <int SCHEME, int VEC, int BLK, int MINB>
+static bool flat_eligible(const crt1d_batch& in, int nthr, size_t& smem) {
+    if constexpr (!uses_segments(SCHEME)) return false;
+    // zq_pa keeps the (scenario, band tile) mapping: its three-pass scenario prologue (M-grid, interpolation tables,
+    // emission order) is paid per CTA, and the flat mapping has 16 CTAs per scenario where the fused-absorbed tile
+    // mapping has one: measured 0.490 (flat) vs 0.515 (tile) of HBM peak; zq 0.755 -> 0.860, n79 0.743 -> 0.797.
+    if constexpr (SCHEME == CRT1D_SCHEME_ZQ_PA) return false;
+    if (tuning().no_flat) return false;
+    const int gps = in.n_wl / VEC;
+    if (gps * VEC != in.n_wl || nthr > gps) return false;
+    smem = (2 * tab_doubles(SCHEME, in.n_z) + (size_t)nthr * seg_thread_doubles<VEC>(SCHEME, in.n_z)) * sizeof(double);
+    const size_t old_smem = (tab_doubles(SCHEME, in.n_z) + (size_t)nthr * seg_thread_doubles<VEC>(SCHEME, in.n_z)) * sizeof(double);
+    const size_t per_sm = 228u * 1024u, per_cta = 1024u + sizeof(double) * (BLK / 32) * 8;
+    if (smem > 227u * 1024u) return false;
+    // resident CTAs the (scenario, band tile) mapping gets: the register bound (MINB CTAs of BLK threads) or its shared memory
+    const size_t want = std::min<size_t>((size_t)MINB * (BLK / nthr), per_sm / (old_smem + per_cta));
+    return per_sm / (smem + per_cta) >= want;
+}
+
+template <int SCHEME, int VEC, int BLK, int MINB>
+static cudaError_t launch_flat(const crt1d_batch& in, const crt1d_out& out, int nthr, size_t smem, cudaStream_t stream) {
+    const int gps = in.n_wl / VEC;
+    const int64_t grid = (in.n_scen * gps + nthr - 1) / nthr;
+    if (grid <= 0 || grid > 2147483647LL) return cudaErrorInvalidConfiguration;
+    auto kern = solve_flat_kernel<SCHEME, VEC, BLK, MINB, false>;
+    double* const f[7] = {out.I_dr, out.I_df_d, out.I_df_u, out.F, out.x0, out.x1, out.x2};
+    bool all = out.profile_f32 == 0;
+    for (int q = 0; q < n_out_fields(SCHEME); ++q) all = all && f[q] != nullptr;
+    if (all) kern = solve_flat_kernel<SCHEME, VEC, BLK, MINB, true>;
+    if (cudaError_t e = ensure_smem(kern, smem); e != cudaSuccess) return e;
+    double* partial = nullptr;
+    if (out.absorbed) {
+        if (cudaError_t e = scratch_alloc(reinterpret_cast<void**>(&partial), (size_t)grid * 8 * sizeof(double), stream); e != cudaSuccess) return e;
+    }
+    kern<<<(unsigned)grid, nthr, smem, stream>>>(in, out, gps, partial);
+    cudaError_t e = cudaGetLastError();
+    if (partial) {
+        if (e == cudaSuccess) {
+            const int64_t n = in.n_scen * out.n_bw;
+            absorbed_flat_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(partial, in.n_scen, gps, nthr, out.n_bw, out.absorbed);
+            e = cudaGetLastError();
+        }
+        cudaFreeAsync(partial, stream);
+    }
+    return e;
+}
+
 template <int SCHEME, int VEC, int BLK, int MINB>
 static cudaError_t launch_one(const crt1d_batch& in, const crt1d_out& out, cudaStream_t stream) {
     const int nthr = tile_threads(SCHEME == CRT1D_SCHEME_ZQ_PA ? ZQPA_THREADS : BLK, BLK);
+    if constexpr (uses_segments(SCHEME)) {
+        size_t smem_flat = 0;
+        if (flat_eligible<SCHEME, VEC, BLK, MINB>(in, nthr, smem_flat)) return launch_flat<SCHEME, VEC, BLK, MINB>(in, out, nthr, smem_flat, stream);
+    }
     const int cols = nthr * VEC;
     const int tiles_per_scen = (in.n_wl + cols - 1) / cols;
     const int tiles_per_cta = out.absorbed ? tiles_per_scen : 1;
@@ -866,7 +1074,8 @@ struct RowsTraits<CRT1D_SCHEME_4S> {
 };
 
 template <int SCHEME, int VEC, int LV, int MAXT, bool F32, bool FUSED, int MINB, bool DIAG = false>
-__global__ void __launch_bounds__(MAXT, MINB) solve_rows_kernel(const crt1d_batch in, const crt1d_out out, int split) {
+__global__ void __launch_bounds__(MAXT, MINB) solve_rows_kernel(const crt1d_batch in, const crt1d_out out, int split,
+                                                                unsigned* __restrict__ rare_mask) {
     using TR = RowsTraits<SCHEME>;
     constexpr int NC = TR::NC, NF = TR::NF;
     extern __shared__ double sm[];  // [level tables][coefficients NC x ld][partial sums chunks x 4][ready flags chunks]
@@ -951,6 +1160,8 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_rows_kernel(const crt1d_batc
                     if (redone_later) {
                         k[v].lam[0] = k[v].lam[1] = 1.0;
                         k[v].dnK = k[v].upK = 0.0;
+                        // bit (scenario, band) of the rare-column mask: what fixup_4s_kernel works from
+                        atomicOr(rare_mask + s * ((n_wl + 31) >> 5) + ((c0 + v) >> 5), 1u << ((c0 + v) & 31));
                     }
                 }
                 double a[NC];
@@ -1140,8 +1351,10 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_rows_kernel(const crt1d_batc
             for (int q = 0; q < n_chunks; ++q) v += partial[q][threadIdx.x];
             if (split == 1) {
                 out.absorbed[s * out.n_bw + threadIdx.x] = v;
-            } else {  // two parts into a zeroed sum: 0 + a + b = 0 + b + a exactly, so still deterministic
+            } else if (split == 2) {  // two parts into a zeroed sum: 0 + a + b = 0 + b + a exactly, so still deterministic
                 atomicAdd(&out.absorbed[s * out.n_bw + threadIdx.x], v);
+            } else {  // three or more parts: the launcher passed a scratch array [scenario][part][band group]; parts_sum_kernel adds them in part order
+                out.absorbed[(s * split + part) * out.n_bw + threadIdx.x] = v;
             }
         }
     }
@@ -1161,23 +1374,37 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_rows_kernel(const crt1d_batc
 #ifndef CRT_FIXUP_MINB
 #define CRT_FIXUP_MINB 20
 #endif
-// One WARP per scenario (a 32-thread CTA: the work is latency-bound serial arithmetic, so what counts is how many
-// scenarios are resident -- 20+ per SM, i.e. a whole launch of ~4000 scenarios in about one wave).  The warp tests 32
-// consecutive bands per step (one per lane) and collects the rare ones, in band order, into a pending list; a flush
-// then (i) lets lane i solve the general coefficients of pending column i -- different columns on different lanes, in
-// parallel -- into shared memory, (ii) shares the (column, level) evaluations out over all 32 lanes, (iii) adds the
-// columns' absorbed-sum terms in list (= band) order.
+// One WARP per (scenario, level part) (a 32-thread CTA: the work is latency-bound serial arithmetic, so what counts is
+// how many warps are resident -- 20+ per SM, i.e. a whole launch of ~4000 scenarios in about one wave).  The rare columns
+// come from the bit mask the sweep kernel set in its coefficient stage (one bit per (scenario, band); the first version
+// re-ran the rarity test over all 2100 bands here: 66 dependent load + eigenvalue rounds per warp, 2/3 of this kernel's
+// time).  A warp with an empty mask exits at once.  Otherwise it walks the set bits in band order into a pending list; a
+// flush then (i) lets lane i solve the general coefficients of pending column i -- different columns on different
+// lanes, in parallel -- into shared memory, (ii) shares the (column, level) evaluations of ITS levels out over all 32
+// lanes, (iii) part 0 adds the columns' absorbed-sum terms in list (= band) order.  Deep canopies use several parts per
+// scenario (n_parts ~ n_z / 64: at n_z = 1000 one warp per scenario was 21 % of the 4s step).
 struct FixupSlot {
     double c[13];  // Coef4s, field order of RowsTraits<4S>::pack + Idr0
 };
-__global__ void __launch_bounds__(32, CRT_FIXUP_MINB) fixup_4s_kernel(const crt1d_batch in, const crt1d_out out) {
+__global__ void __launch_bounds__(32, CRT_FIXUP_MINB) fixup_4s_kernel(const crt1d_batch in, const crt1d_out out,
+                                                                      const unsigned* __restrict__ rare_mask, int n_parts) {
     extern __shared__ double tab[];  // L[j], exp(-K_b L[j]), then 32 coefficient slots
     __shared__ int pend[32];
-    const int64_t s = blockIdx.x;
+    const int64_t s = blockIdx.x / n_parts;
+    const int part = blockIdx.x - (int)s * n_parts;
     const int n_z = in.n_z, n_wl = in.n_wl;
     const int lane = threadIdx.x;
+    const int n_words = (n_wl + 31) >> 5;
+    const unsigned* const mask = rare_mask + s * n_words;
+    bool any = false;
+    for (int w = lane; w < n_words; w += 32) any = any || mask[w] != 0u;
+    if (!__any_sync(0xffffffffu, any)) return;
+
+    const int j_lo = (int)((int64_t)n_z * part / n_parts), j_hi = (int)((int64_t)n_z * (part + 1) / n_parts);  // this warp's levels
     FixupSlot* const slot = reinterpret_cast<FixupSlot*>(tab + 2 * n_z);
-    for (int j = lane; j < n_z; j += 32) fill_level_tables<CRT1D_SCHEME_4S>(in, s, j, tab);
+    for (int j = j_lo + lane; j < j_hi; j += 32) fill_level_tables<CRT1D_SCHEME_4S>(in, s, j, tab);
+    if (lane == 0 && j_lo > 0) fill_level_tables<CRT1D_SCHEME_4S>(in, s, 0, tab);
+    if (lane == 1 && j_hi < n_z) fill_level_tables<CRT1D_SCHEME_4S>(in, s, n_z - 1, tab);
     __syncwarp();
     const double mu_s = in.mu_s > 0.0 ? in.mu_s : 0.501;
     const Scen4s sc = scen_4s(in.psi[s], in.K_b[s], in.G_int[2 * s], in.G_int[2 * s + 1], mu_s, tab[0]);
@@ -1186,7 +1413,7 @@ __global__ void __launch_bounds__(32, CRT_FIXUP_MINB) fixup_4s_kernel(const crt1
     void* const pf[4] = {prof_base(out.I_dr, f32, s * prof), prof_base(out.I_df_d, f32, s * prof),
                          prof_base(out.I_df_u, f32, s * prof), prof_base(out.F, f32, s * prof)};
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    int n = 0, total = 0;
+    int n = 0;
 
     auto load_slot = [&](int i) {
         Coef4s k;
@@ -1205,16 +1432,19 @@ __global__ void __launch_bounds__(32, CRT_FIXUP_MINB) fixup_4s_kernel(const crt1
             double* c = slot[lane].c;
             c[0] = k.lam[0]; c[1] = k.lam[1]; c[2] = k.dnP[0]; c[3] = k.dnP[1]; c[4] = k.dnM[0]; c[5] = k.dnM[1];
             c[6] = k.upP[0]; c[7] = k.upP[1]; c[8] = k.upM[0]; c[9] = k.upM[1]; c[10] = k.dnK; c[11] = k.upK; c[12] = k.Idr0;
-            double g[4], t[4];  // its ground and top levels: the absorbed-sum term
-            level_4s(sc, k, tab[0], tab[n_z], g[0], g[1], g[2], g[3]);
-            level_4s(sc, k, tab[n_z - 1], tab[2 * n_z - 1], t[0], t[1], t[2], t[3]);
-            ab = absorbed_from_ends(t[0], g[0], t[1], g[1], t[2], g[2]);
-            if (out.status && !isfinite(ab)) atomicOr(out.status + s, CRT1D_STATUS_NONFINITE);
+            if (part == 0) {
+                double g[4], t[4];  // its ground and top levels: the absorbed-sum term
+                level_4s(sc, k, tab[0], tab[n_z], g[0], g[1], g[2], g[3]);
+                level_4s(sc, k, tab[n_z - 1], tab[2 * n_z - 1], t[0], t[1], t[2], t[3]);
+                ab = absorbed_from_ends(t[0], g[0], t[1], g[1], t[2], g[2]);
+                if (out.status && !isfinite(ab)) atomicOr(out.status + s, CRT1D_STATUS_NONFINITE);
+            }
         }
         __syncwarp();
-        const int items = n * n_z;  // (ii) every level of every pending column
+        const int n_lev = j_hi - j_lo;
+        const int items = n * n_lev;  // (ii) this warp's levels of every pending column
         for (int it = lane; it < items; it += 32) {
-            const int col = it / n_z, j = it - col * n_z;
+            const int col = it / n_lev, j = j_lo + (it - col * n_lev);
             const Coef4s k = load_slot(col);
             double f[4][1];
             level_4s(sc, k, tab[j], tab[n_z + j], f[0][0], f[1][0], f[2][0], f[3][0]);
@@ -1222,7 +1452,7 @@ __global__ void __launch_bounds__(32, CRT_FIXUP_MINB) fixup_4s_kernel(const crt1
 #pragma unroll
             for (int q = 0; q < 4; ++q) st_prof<1>(pf[q], f32, off, f[q]);
         }
-        if (out.absorbed) {  // (iii) in list order, the same sum on every lane
+        if (out.absorbed && part == 0) {  // (iii) in list order, the same sum on every lane
             for (int col = 0; col < n; ++col) {
                 const double a = __shfl_sync(0xffffffffu, ab, col);
                 const int cc = pend[col];
@@ -1230,41 +1460,60 @@ __global__ void __launch_bounds__(32, CRT_FIXUP_MINB) fixup_4s_kernel(const crt1
             }
         }
         __syncwarp();
-        total += n;
         n = 0;
     };
 
-    for (int base = 0; base < n_wl; base += 32) {
-        const int c = base + lane;
-        bool rare = false;
-        if (c < n_wl) {  // the same test, on the same bits, as coef_4s made in the sweep kernel (l2_4s: explicit roundings)
-            const int64_t lo = (int64_t)in.leaf_idx[s] * n_wl + c;
-            Eig4s E;
-            double dif, disc;
-            l2_4s(sc, __ldg(in.leaf_r_lib + lo) + __ldg(in.leaf_t_lib + lo), E, dif, disc);
-            rare = !ordinary_4s(sc, E.l2);
+    for (int w0 = 0; w0 < n_words; w0 += 32) {  // set bits in band order; control flow is warp-uniform
+        const unsigned m = (w0 + lane < n_words) ? mask[w0 + lane] : 0u;
+        unsigned lanes = __ballot_sync(0xffffffffu, m != 0u);
+        while (lanes) {
+            const int src = __ffs(lanes) - 1;
+            lanes &= lanes - 1;
+            unsigned word = __shfl_sync(0xffffffffu, m, src);
+            while (word) {
+                const int bit = __ffs(word) - 1;
+                word &= word - 1;
+                if (lane == 0) pend[n] = (w0 + src) * 32 + bit;
+                ++n;
+                __syncwarp();
+                if (n == 32) flush();
+            }
         }
-        const unsigned mask = __ballot_sync(0xffffffffu, rare);
-        if (mask == 0) continue;
-        const int add = __popc(mask);
-        if (n + add > 32) flush();
-        if (rare) pend[n + __popc(mask & ((1u << lane) - 1u))] = c;
-        n += add;
-        __syncwarp();
     }
     if (n > 0) flush();
-    if (out.absorbed && total > 0 && lane < out.n_bw) {
+    if (out.absorbed && part == 0 && lane < out.n_bw) {
         double v = 0.0;  // lane q keeps acc[q]; static indexing only
 #pragma unroll
         for (int q = 0; q < 4; ++q) v = lane == q ? acc[q] : v;
         out.absorbed[s * out.n_bw + lane] += v;  // after the sweep kernel's own sum: stream order
     }
 }
-static cudaError_t launch_fixup_4s(const crt1d_batch& in, const crt1d_out& out, cudaStream_t stream) {
+static cudaError_t launch_fixup_4s(const crt1d_batch& in, const crt1d_out& out, const unsigned* rare_mask, cudaStream_t stream) {
     const size_t smem = (size_t)2 * in.n_z * sizeof(double) + 32 * sizeof(FixupSlot);
     if (cudaError_t e = ensure_smem(fixup_4s_kernel, smem); e != cudaSuccess) return e;
-    fixup_4s_kernel<<<(unsigned)in.n_scen, 32, smem, stream>>>(in, out);
+    int n_parts = std::max(1, std::min(32, in.n_z / 64));
+    if (tuning().fixup_parts > 0) n_parts = std::min(tuning().fixup_parts, in.n_z);
+    if (!grid_ok(in.n_scen * n_parts)) return cudaErrorInvalidConfiguration;
+    fixup_4s_kernel<<<(unsigned)(in.n_scen * n_parts), 32, smem, stream>>>(in, out, rare_mask, n_parts);
     return cudaGetLastError();
+}
+// the sweep kernel's rare-column bit mask: stream-ordered scratch, zeroed
+static cudaError_t rare_mask_alloc(const crt1d_batch& in, unsigned** mask, cudaStream_t stream) {
+    const size_t bytes = (size_t)in.n_scen * ((in.n_wl + 31) / 32) * sizeof(unsigned);
+    if (cudaError_t e = scratch_alloc(reinterpret_cast<void**>(mask), bytes, stream); e != cudaSuccess) return e;
+    return cudaMemsetAsync(*mask, 0, bytes, stream);
+}
+
+// absorbed[s][k] = sum of the `split` parts of scenario s, in part order (deterministic)
+__global__ void __launch_bounds__(256) parts_sum_kernel(const double* __restrict__ parts, int64_t n_scen, int split, int n_bw,
+                                                        double* __restrict__ absorbed) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_scen * n_bw) return;
+    const int64_t s = i / n_bw;
+    const int k = (int)(i - s * n_bw);
+    double v = 0.0;
+    for (int p = 0; p < split; ++p) v += parts[(s * split + p) * n_bw + k];
+    absorbed[i] = v;
 }
 
 template <int SCHEME>
@@ -1284,43 +1533,72 @@ static cudaError_t launch_rows_t(const crt1d_batch& in, const crt1d_out& out, in
     // 4s: its coefficient stage (eigen-system + 4x4 solve, 168 registers) is better kept as a separate phase
     // (0.82 vs 0.77 of HBM peak when fused into the first item); bl/bf/g77 fuse it (no store-free phase).
     constexpr bool FUSED = SCHEME != CRT1D_SCHEME_4S;
+    constexpr bool IS4S = SCHEME == CRT1D_SCHEME_4S;
     if (!grid_ok(in.n_scen)) return cudaErrorInvalidConfiguration;
+    unsigned* rare = nullptr;  // 4s: (scenario, band) bits of the columns fixup_4s_kernel redoes
+    if constexpr (IS4S) {
+        if (cudaError_t e = rare_mask_alloc(in, &rare, stream); e != cudaSuccess) return e;
+    }
+    // every path ends here: 4s runs its fix-up kernel behind the sweep and returns the mask to the pool
+    auto finish = [&](cudaError_t e) {
+        if constexpr (IS4S) {
+            if (e == cudaSuccess) e = launch_fixup_4s(in, out, rare, stream);
+            cudaFreeAsync(rare, stream);
+        }
+        return e;
+    };
     if (no_profile_requested(out)) {  // reduced-diagnostic mode: small CTAs, several per SM, level tables only
         const int n_tab = n_level_tables(SCHEME) * in.n_z;
         const int chunks = (in.n_wl / VEC + 31) / 32;
         const size_t smem_d = (size_t)(n_tab + (n_tab & 1)) * sizeof(double) + (size_t)chunks * (4 * sizeof(double) + sizeof(int));
-        constexpr int DM = SCHEME == CRT1D_SCHEME_4S ? CRT_DIAG_MINB_4S : CRT_DIAG_MINB;
+        constexpr int DM = IS4S ? CRT_DIAG_MINB_4S : CRT_DIAG_MINB;
         auto kd = solve_rows_kernel<SCHEME, VEC, 10, 256, false, FUSED, DM, true>;  // LV, F32 play no part
-        if (cudaError_t e = ensure_smem(kd, smem_d); e != cudaSuccess) return e;
-        kd<<<(unsigned)in.n_scen, diag_threads(SCHEME == CRT1D_SCHEME_4S ? 64 : 128), smem_d, stream>>>(in, out, 1);
-        if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) return e;
-        if constexpr (SCHEME == CRT1D_SCHEME_4S) return launch_fixup_4s(in, out, stream);
-        return cudaSuccess;
+        if (cudaError_t e = ensure_smem(kd, smem_d); e != cudaSuccess) return finish(e);
+        kd<<<(unsigned)in.n_scen, diag_threads(IS4S ? 64 : 128), smem_d, stream>>>(in, out, 1, rare);
+        return finish(cudaGetLastError());
     }
-    if constexpr (SCHEME == CRT1D_SCHEME_4S) {
+    if constexpr (IS4S) {
         // Two CTAs per SM, each on half of the scenario's band chunks (half the coefficient array: 2 x ~106 KB):
         // one CTA's store-free coefficient phase (~20 % of its life) overlaps the other's level sweeps.
-        const int split = tuning().split_4s;
-        const size_t smem2 = rows_shared_bytes<SCHEME>(in.n_z, in.n_wl, 2, VEC);
-        if (split == 2 && in.n_scen * 2 <= 2147483647LL && 2 * (smem2 + 3 * 1024) <= 228u * 1024u) {
+        // Deep canopies (n_z = 1000: 16 KB of level tables on top of the coefficients): the band chunks are split three
+        // or four ways instead, so that two CTAs still fit.
+        int split = tuning().split_4s;
+        size_t smem2 = rows_shared_bytes<SCHEME>(in.n_z, in.n_wl, split, VEC);
+        while (split >= 2 && split < 4 && 2 * (smem2 + 3 * 1024) > 228u * 1024u) {
+            ++split;
+            smem2 = rows_shared_bytes<SCHEME>(in.n_z, in.n_wl, split, VEC);
+        }
+        if (split >= 2 && in.n_scen * split <= 2147483647LL && 2 * (smem2 + 3 * 1024) <= 228u * 1024u) {
             auto kern2 = solve_rows_kernel<SCHEME, VEC, LV, MAXT / 2, F32, FUSED, 2>;
             cudaError_t e = ensure_smem(kern2, smem2);
-            if (e != cudaSuccess) return e;
-            if (out.absorbed) {
+            if (e != cudaSuccess) return finish(e);
+            crt1d_out o2 = out;
+            double* parts = nullptr;
+            if (out.absorbed && split == 2) {
                 e = cudaMemsetAsync(out.absorbed, 0, (size_t)in.n_scen * out.n_bw * sizeof(double), stream);
-                if (e != cudaSuccess) return e;
+                if (e != cudaSuccess) return finish(e);
+            } else if (out.absorbed) {
+                e = scratch_alloc(reinterpret_cast<void**>(&parts), (size_t)in.n_scen * split * out.n_bw * sizeof(double), stream);
+                if (e != cudaSuccess) return finish(e);
+                o2.absorbed = parts;
             }
-            kern2<<<(unsigned)(in.n_scen * 2), min(th, MAXT / 2), smem2, stream>>>(in, out, 2);
-            if (e = cudaGetLastError(); e != cudaSuccess) return e;
-            return launch_fixup_4s(in, out, stream);
+            kern2<<<(unsigned)(in.n_scen * split), min(th, MAXT / 2), smem2, stream>>>(in, o2, split, rare);
+            e = cudaGetLastError();
+            if (parts) {
+                if (e == cudaSuccess) {
+                    const int64_t n = in.n_scen * out.n_bw;
+                    parts_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(parts, in.n_scen, split, out.n_bw, out.absorbed);
+                    e = cudaGetLastError();
+                }
+                cudaFreeAsync(parts, stream);
+            }
+            return finish(e);
         }
     }
     auto kern = solve_rows_kernel<SCHEME, VEC, LV, MAXT, F32, FUSED, 1>;
-    if (cudaError_t e = ensure_smem(kern, smem); e != cudaSuccess) return e;
-    kern<<<(unsigned)in.n_scen, th, smem, stream>>>(in, out, 1);
-    if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) return e;
-    if constexpr (SCHEME == CRT1D_SCHEME_4S) return launch_fixup_4s(in, out, stream);
-    return cudaSuccess;
+    if (cudaError_t e = ensure_smem(kern, smem); e != cudaSuccess) return finish(e);
+    kern<<<(unsigned)in.n_scen, th, smem, stream>>>(in, out, 1, rare);
+    return finish(cudaGetLastError());
 }
 
 // 4s level groups: 10 levels per work item.  Measured (two CTAs per SM): 15 levels 0.80, 30 levels 0.81 vs 0.77 --

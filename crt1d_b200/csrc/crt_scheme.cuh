@@ -48,14 +48,11 @@ CRT_HD void fill_level_tables(const crt1d_batch& in, int64_t s, int j, double* t
             const int M = n_z < ZQPA_MAX_M ? n_z : ZQPA_MAX_M;
             const double dl = lai[0] / M;
             double* cum = tab + 2 * n_z;
-            double* eC = cum + (M + 1);
             double c = 0.0;
             cum[0] = 0.0;
-            eC[0] = 1.0;
-            for (int i = 1; i <= M; ++i) {
-                c += dl;
-                cum[i] = c;
-                eC[i] = exp(-K_b * c);
+            for (int i = 1; i <= M; ++i) {  // serial by definition; the exponentials of cum[] are taken in the second pass,
+                c += dl;                    // one per thread (100 dependent exp calls here were ~30 000 cycles of a
+                cum[i] = c;                 // one-thread prologue in every CTA)
             }
         }
     } else if constexpr (SCHEME == CRT1D_SCHEME_N79) {
@@ -102,6 +99,12 @@ CRT_HD void fill_level_tables_2(const crt1d_batch& in, int64_t s, int j, double*
         const int n_z = in.n_z;
         const int M = n_z < ZQPA_MAX_M ? n_z : ZQPA_MAX_M;
         const double* cum = tab + 2 * n_z;
+        {  // exp(-Kb cum[i]), i = 0..M (M <= n_z: the thread of the last level takes the extra entry when M = n_z)
+            const double K_b = in.K_b[s];
+            double* eC = tab + 2 * n_z + (M + 1);
+            if (j <= M) eC[j] = j == 0 ? 1.0 : exp(-K_b * cum[j]);
+            if (j == n_z - 1 && M == n_z) eC[M] = exp(-K_b * cum[M]);
+        }
         int k;
         double t, w;
         interp_np_prepare(tab[j], cum, M + 1, tab[0] / M, k, t, w);

@@ -42,6 +42,8 @@ struct HostOut {
     void ld_tmp(int f, int j, double (&x)[VEC]) const {
         for (int v = 0; v < VEC; ++v) x[v] = p[f][(int64_t)j * stride + v];
     }
+    void pf_tmp(int, int, int) const {}  // checkpoint prefetch: a cp.async on the device, nothing to do here
+    void ld_pf(int f, int j, int, double (&x)[VEC]) const { ld_tmp(f, j, x); }
 };
 
 template <int SCHEME, int VEC>

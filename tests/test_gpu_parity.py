@@ -1092,3 +1092,74 @@ def test_nonuniform_lai_sweep_batched(scheme):
                 assert_close_same_nans(got, ref[k], RTOL, f"nonuniform {scheme}[{i}].{k}", atol=1e-300)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("scheme", ["zq", "n79", "zq_pa"])
+def test_flat_column_mapping_equals_tile_mapping(scheme, monkeypatch):
+    """Tridiagonal schemes on wide batches use the flat column mapping (solve_flat_kernel: every CTA full, a CTA may
+    span two scenarios, checkpoint prefetch, per-CTA absorbed partials added in CTA order); narrow band axes keep the
+    (scenario, band tile) mapping.  Same per-column arithmetic -> identical profiles; the absorbed sums differ only in
+    summation order.  Also: a batch whose last CTA is partly empty, one scenario alone, an odd band count (VEC = 1)."""
+    import copy
+
+    import torch
+
+    from crt1d_b200 import engine
+    from crt1d_b200 import sweep
+
+    spec = sweep.synthetic_sweep_spec(seed=0)
+    bw = np.stack([np.ones(spec.n_wl), np.linspace(0, 1, spec.n_wl)])
+    for lo, n in ((612345, 7), (255500, 1), (40, 150)):
+        sub = spec.slice(lo, lo + n)
+        tune(monkeypatch, "CRT1D_B200_NO_FLAT", "1")
+        a = engine.solve(sub, scheme, band_w=bw)
+        torch.cuda.synchronize()
+        tune(monkeypatch, "CRT1D_B200_NO_FLAT", None)
+        b = engine.solve(sub, scheme, band_w=bw)
+        torch.cuda.synchronize()
+        for k in a:
+            if k == "absorbed":
+                assert_close(b[k].cpu().numpy(), a[k].cpu().numpy(), 1e-12, f"flat vs tile {scheme}.absorbed n={n}")
+            else:
+                assert torch.equal(a[k], b[k]), f"flat vs tile {scheme}.{k} n={n}"
+        for i in {0, n - 1}:  # vs the oracle (device Gauss-Legendre tau_d vs host quad: 1e-8, see test_batched_equals_plugin_path)
+            ref = oracle.run(scheme, sub.scenario_params(i))
+            for k in ("I_dr", "I_df_d", "I_df_u", "F"):
+                assert_close(b[k][i].cpu().numpy(), ref[k], 1e-8, f"flat {scheme}[{i}].{k}", atol=1e-300)
+    odd = copy.copy(spec.slice(40, 40 + 9))
+    for k in ("leaf_r_lib", "leaf_t_lib", "soil_r_lib", "I_dr0_lib", "I_df0_lib"):
+        setattr(odd, k, np.ascontiguousarray(getattr(odd, k)[:, :401]))
+    odd.wl, odd.dwl = odd.wl[:401], odd.dwl[:401]
+    tune(monkeypatch, "CRT1D_B200_NO_FLAT", "1")
+    a = engine.solve(odd, scheme)
+    tune(monkeypatch, "CRT1D_B200_NO_FLAT", None)
+    b = engine.solve(odd, scheme)
+    torch.cuda.synchronize()
+    for k in a:
+        assert torch.equal(a[k], b[k]), f"flat vs tile odd {scheme}.{k}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("split", ["1", "3", "4"])
+def test_4s_rows_kernel_band_splits(split, monkeypatch):
+    """4s row-sweep kernel: `split` CTAs share a scenario's band chunks (2 by default; 3 or 4 on deep canopies, where
+    two half-scenario CTAs no longer fit in shared memory; their absorbed parts go through a scratch array and are added
+    in part order).  Every split runs the same per-column arithmetic."""
+    import torch
+
+    from crt1d_b200 import engine
+    from crt1d_b200 import sweep
+
+    spec = sweep.synthetic_sweep_spec(seed=0)
+    sub = spec.slice(255500, 255500 + 150)
+    bw = np.stack([np.ones(spec.n_wl), np.linspace(0, 1, spec.n_wl)])
+    a = engine.solve(sub, "4s", band_w=bw)
+    torch.cuda.synchronize()
+    tune(monkeypatch, "CRT1D_B200_4S_SPLIT", split)
+    b = engine.solve(sub, "4s", band_w=bw)
+    torch.cuda.synchronize()
+    tune(monkeypatch, "CRT1D_B200_4S_SPLIT", None)
+    for k in a:
+        if k == "absorbed":
+            assert_close(b[k].cpu().numpy(), a[k].cpu().numpy(), 1e-12, f"4s split {split} absorbed")
+        else:
+            assert torch.equal(a[k], b[k]), f"4s split {split} {k}"
