@@ -6,7 +6,7 @@ interface level of one wavelength band of one scenario.  Workload at N = 1: BASE
 the batched 2s sweep of 10^6 scenarios (100 SZA x 100 LAI x 100 leaf/soil/sky spectra) x 2100 one-nm
 bands x 60 levels, synthetic; one STEP = one full pass over the sweep
 (1.26e11 units, 4.03 TB of fp64 profiles written to HBM in chunks + per-scenario absorbed PAR/NIR).
-N > 1 (torchrun, one rank per GPU): BASELINE.json configs[3] -- the SAME 10^6-scenario sweep block-partitioned
+N > 1 (torchrun, one rank per GPU): BASELINE.json configs[3] -- the SAME 10^6-scenario sweep partitioned (units of 148 scenarios dealt round-robin)
 over the ranks (strong scaling; no data-path collective); the per-scenario diagnostics are all-gathered over NCCL
 on a side stream inside the timed region (double-buffered, so step k's gather overlaps step k+1's kernels), with the
 collective and every rank's kernel time event-timed.  `--scaling weak` = every rank its own sweep (seed = rank).
@@ -48,6 +48,9 @@ def parse():
                          "(BASELINE.json configs[3]; at N = 1 that is configs[2]); weak: every rank runs its own "
                          "--scenarios sweep (seed = rank).  Under auto/strong at N > 1 a short weak-scaling leg is "
                          "added to the line under `weak_scaling`")
+    ap.add_argument("--partition", default="deal", choices=["deal", "block"],
+                    help="strong scaling at N > 1: 'deal' = units of 148 scenarios round-robin over the ranks (default: "
+                         "balanced when scenario cost depends on its parameters, as for 4s); 'block' = contiguous blocks")
     ap.add_argument("--profile-dtype", default="f64", choices=["f64", "f32"],
                     help="storage type of the profiles in HBM (arithmetic is always float64); f32 = the optional "
                          "reduced-precision path of BASELINE.json, NOT the headline configuration")
@@ -147,7 +150,7 @@ def scaling_of(args):
 def workload_name(args, world=None):
     world = world or args.gpus
     cfg = 4 if args.nz != 60 else (2 if world == 1 else 3)
-    how = ("per GPU" if scaling_of(args) == "weak" else ("on 1 GPU" if world == 1 else f"block-partitioned over {world} GPUs"))
+    how = ("per GPU" if scaling_of(args) == "weak" else ("on 1 GPU" if world == 1 else f"partitioned over {world} GPUs"))
     return (f"batched {args.scheme} sweep: {args.scenarios} scenarios (SZA x LAI x PROSPECT-style spectra) x 2100 "
             f"1-nm bands x {args.nz} levels {how} (BASELINE.json configs[{cfg}])")
 
@@ -261,9 +264,14 @@ def main():
         torch.cuda.synchronize()
 
     strong = scaling_of(args) == "strong"
-    if strong:  # one sweep, contiguous scenario blocks per rank (distributed.shard_batch)
+    dealt = False
+    if strong:  # one sweep, partitioned over the ranks
         full_spec = make_spec(0, args.scenarios, args.nz)
-        spec, _ = cdist.shard_batch(full_spec, world, rank)
+        dealt = world > 1 and args.partition == "deal"
+        if dealt:  # units of 148 scenarios dealt round-robin: every rank gets the same mix of cheap and dear scenarios
+            spec, _ = cdist.deal_batch(full_spec, world, rank)
+        else:      # contiguous scenario blocks (distributed.shard_batch)
+            spec, _ = cdist.shard_batch(full_spec, world, rank)
         S_total = full_spec.n_scen
     else:  # weak scaling: every rank owns a full sweep (seed = rank)
         spec = make_spec(rank, args.scenarios, args.nz)
@@ -280,8 +288,9 @@ def main():
     # scenario), all-gathered over NCCL on a SIDE stream: step k's gather reads diagnostics buffer k % 2 while step
     # k + 1's kernels fill the other; step k + 2 waits for gather k before it overwrites the buffer.
     side = torch.cuda.Stream(device=dev) if world > 1 else None
-    equal = S_total % world == 0
-    gbuf = [torch.empty((S_total, n_bw), dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 and equal else None
+    equal = S_total % world == 0 and not dealt
+    gbuf = [torch.empty((S_total, n_bw), dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 and (equal or dealt) else None
+    dealt_gather = cdist.DealtGather(S_total, n_bw, world, dev) if dealt else None
     gather_done = [None, None]
     coll_events = []
     gathered = None
@@ -300,7 +309,9 @@ def main():
                 if time_collective:
                     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     c0.record(side)
-                if equal:
+                if dealt:  # all-gather + scatter to global scenario order
+                    gathered = dealt_gather(runner.absorbed_bufs[slot], gbuf[slot])
+                elif equal:
                     dist.all_gather_into_tensor(gbuf[slot], runner.absorbed_bufs[slot])
                     gathered = gbuf[slot]
                 else:
@@ -449,7 +460,7 @@ def main():
                 "profile_storage": args.profile_dtype,
                 "l2": "no flush needed: each launch writes a %.1f GB profile chunk (>> 126 MB L2), 2-buffer ring" % (
                     runner.chunk * spec.n_z * spec.n_wl * bpu / 1e9),
-                "parallelism": (f"one sweep block-partitioned over {world} rank(s)" if strong else f"one sweep per rank x{world}")
+                "parallelism": (f"one sweep over {world} rank(s), " + ("units of 148 scenarios dealt round-robin" if dealt else "contiguous blocks") if strong else f"one sweep per rank x{world}")
                                + ", no data-path collective; NCCL all-gather of absorbed[S,2] on a side stream",
             },
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "e2e_host_profiles": e2e_host, "gpu_launches": launches,

@@ -89,7 +89,7 @@ def host_prologue(batch: ScenarioBatch, scheme, *, K_b_fn=None, G_fn=None, mu_s=
         td = np.array([_common.tau_df_fn(K_b_fn, row[0] / M) for row in batch.lai_lib])
         pro["tau_i"] = td[batch.lai_idx]
     elif scheme == "bl":
-        pro["tau_d_lev"] = np.array([[_common.tau_df_fn(K_b_fn, L) for L in row] for row in batch.lai_lib])
+        pro["tau_d_lev"] = np.array([_common.tau_df_fn(K_b_fn, row) for row in batch.lai_lib])  # ref _solve_bl.py:35-37
     elif scheme == "n79":
         td = np.zeros_like(batch.lai_lib)
         for i, row in enumerate(batch.lai_lib):

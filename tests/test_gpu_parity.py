@@ -500,10 +500,10 @@ def test_deep_canopy_nz1000():
         ref = oracle.run(scheme, q, **kw)
         sol = crt.solvers.AVAILABLE_SCHEMES[scheme]["solver"](**_args(scheme, q), **kw)
         for k in ref:
-            assert_close(sol[k], ref[k], 1e-9 if scheme in ("zq", "n79", "zq_pa") else RTOL, f"deep {scheme}.{k}")
-    q2 = {k: (v[:2].copy() if isinstance(v, np.ndarray) and v.shape == (6,) else v) for k, v in q.items()}
-    ref = oracle.solve_4s_tight(**{k: q2[k] for k in oracle.ARGS["4s"]})
-    sol = crt.solvers.solve_4s(**_args("4s", q2))
+            # same bar as everywhere (the kernels' arithmetic is 3e-13 off the oracle at n_z = 1000: tests/test_hostmath.py)
+            assert_close(sol[k], ref[k], RTOL, f"deep {scheme}.{k}")
+    ref = oracle.solve_4s_tight(**{k: q[k] for k in oracle.ARGS["4s"]})  # all six bands (2.6 s of solve_bvp at tol = 1e-11)
+    sol = crt.solvers.solve_4s(**_args("4s", q))
     for k in ref:
         assert_close_4s(sol[k], ref[k], f"deep 4s.{k}")
 

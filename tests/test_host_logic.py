@@ -186,3 +186,40 @@ def test_host_prologue_uses_reference_quadratures(default_p):
     assert np.array_equal(td[:-1], oracle.tau_df_fn(K, lai[:-1] - lai[1:], method="9sky")) and td[-1] == 0
     with pytest.raises(ValueError):
         host_prologue(b, "n79", K_b_fn=K, tau_d_method="nope")
+
+
+def test_vectorised_gauss_legendre_tau_d(default_p):
+    """`tau_df_fn(method="gl")` / `use_gl_for_quad()`: the opt-in extension that replaces the ~100 QUADPACK integrand
+    calls per level of a bl / n79 plugin prologue by one pass over 384 Gauss-Legendre nodes.  It must agree with the
+    reference's `quad(epsrel=1e-9)` within that call's own error bound -- QUADPACK stops at its default epsabs = 1.49e-8
+    (observed: 7e-9 off a tight integral at L = 1.69 where this rule is exact to 1e-16) -- for every leaf-angle family and
+    for thin layers, accept scalar-only callables, and leave the default (`quad`, bit-identical to the reference)
+    untouched when off."""
+    import math
+
+    from crt1d_b200 import leaf_angle as la
+    from crt1d_b200.engine import host_prologue
+    from crt1d_b200.solvers import common
+
+    L = np.array([0.0, 1e-6, 1e-3, 0.05, 0.1, 0.5, 1.0, 3.0, 6.0, 10.0])
+    for G in (la.G_spherical, la.G_horizontal, la.G_vertical, lambda p: la.G_ellipsoidal(p, 1.5), lambda p: la.G_ellipsoidal(p, 0.6)):
+        K = lambda p, G=G: G(p) / np.cos(p)  # noqa: E731
+        q, g = common.tau_df_fn(K, L), common.tau_df_fn(K, L, method="gl")
+        assert np.all(np.abs(g - q) <= 1.5e-8), np.abs(g - q).max()
+        assert g[0] == pytest.approx(1.0, abs=1e-15)
+    Ks = lambda p: 0.5 / math.cos(p)  # noqa: E731  scalar-only callable (math.cos rejects arrays)
+    assert common.tau_df_fn(Ks, 1.3, method="gl") == pytest.approx(common.tau_df_fn(Ks, 1.3), abs=1.5e-8)
+    assert isinstance(common.tau_df_fn(Ks, 1.3, method="gl"), float)
+    b = ScenarioBatch.from_params(default_p)
+    K = default_p["K_b_fn"]
+    ref = host_prologue(b, "bl", K_b_fn=K)["tau_d_lev"]
+    common.use_gl_for_quad(True)
+    try:
+        fast = host_prologue(b, "bl", K_b_fn=K)["tau_d_lev"]
+        fast_n79 = host_prologue(b, "n79", K_b_fn=K)["tau_d_lev"]
+    finally:
+        common.use_gl_for_quad(False)
+    assert not np.array_equal(fast, ref) and np.all(np.abs(fast - ref) <= 1.5e-8)
+    assert np.array_equal(host_prologue(b, "bl", K_b_fn=K)["tau_d_lev"], ref)  # off again: the reference's quad, bit for bit
+    ref_n79 = host_prologue(b, "n79", K_b_fn=K)["tau_d_lev"]
+    assert np.all(np.abs(fast_n79 - ref_n79) <= 1.5e-8)

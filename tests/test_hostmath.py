@@ -160,11 +160,11 @@ def test_kernel_math_deep_canopy_nz1000():
         ref = oracle.run(scheme, q, **kw)
         sol = _solve(q, scheme, **kw)
         for k in ref:
-            # 2 x 1000 unknowns per tridiagonal column: rounding accumulates over the sweep
-            assert_close(sol[k], ref[k], 1e-9 if scheme in ("zq", "n79", "zq_pa") else RTOL, f"deep {scheme}.{k}")
-    q2 = {k: (v[:2].copy() if isinstance(v, np.ndarray) and v.shape == (6,) else v) for k, v in q.items()}
-    ref = oracle.solve_4s_tight(**{k: q2[k] for k in oracle.ARGS["4s"]})
-    sol = _solve(q2, "4s")
+            # 2 x 1000 unknowns per tridiagonal column: measured 3e-13 (n79), 2e-13 (zq), 2e-14 (zq_pa) against the
+            # oracle; the oracle itself moves by up to 3e-12 (n79 aI_lsh) when `lai` is perturbed by one ulp
+            assert_close(sol[k], ref[k], RTOL, f"deep {scheme}.{k}")
+    ref = oracle.solve_4s_tight(**{k: q[k] for k in oracle.ARGS["4s"]})  # all six bands (2.6 s of solve_bvp at tol = 1e-11)
+    sol = _solve(q, "4s")
     for k in ref:
         assert_close_4s(sol[k], ref[k], f"deep 4s.{k}")
 

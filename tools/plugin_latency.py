@@ -45,6 +45,13 @@ def main():
             t_cpu_big = best(lambda: oracle.run(scheme, q), 3)
         rows.append(dict(scheme=scheme, gpu_ms_60x107=t_gpu, cpu_port_ms_60x107=t_cpu, gpu_ms_60x2100=t_gpu_big,
                          cpu_port_ms_60x2100=t_cpu_big))
+        if scheme in ("bl", "n79", "zq", "zq_pa"):  # host prologue with the vectorised Gauss-Legendre tau_d (opt-in extension)
+            from crt1d_b200.solvers import common
+
+            common.use_gl_for_quad(True)
+            rows[-1]["gpu_ms_60x107_gl_prologue"] = best(lambda: m.scheme["solver"](**args), 10)
+            rows[-1]["gpu_ms_60x2100_gl_prologue"] = best(lambda: m.scheme["solver"](**args_big), 5)
+            common.use_gl_for_quad(False)
         print(rows[-1])
     json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "plugin_latency.json"), "w"), indent=1)
 
