@@ -96,6 +96,7 @@ PROTOTYPES = {
     "crt1d_solve_host": (C.c_int, [C.c_int, C.POINTER(Batch), C.POINTER(Out), C.c_int]),
     "crt1d_release_workspace": (C.c_int, []),
     "crt1d_reload_tuning": (C.c_int, []),
+    "crt1d_preferred_batch": (C.c_int64, [C.c_int, C.c_int32, C.c_int32, C.c_int64, C.c_int]),
     "crt1d_calc_absorption": (
         C.c_int, [C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AbsorptionOut), C.c_void_p]),
     "crt1d_energy_balance": (

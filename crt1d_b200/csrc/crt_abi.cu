@@ -427,6 +427,18 @@ int crt1d_release_workspace(void) {
     return CRT1D_OK;
 }
 
+int64_t crt1d_preferred_batch(int scheme, int32_t n_z, int32_t n_wl, int64_t max_scen, int device) {
+    if (scheme < 0 || scheme >= CRT1D_N_SCHEMES || n_z < 1 || n_wl < 1 || max_scen < 1) {
+        fail(CRT1D_ERR_INVALID_ARG, "crt1d_preferred_batch: bad scheme id or size");
+        return CRT1D_ERR_INVALID_ARG;
+    }
+    int n_sm = 0;
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return fail(CRT1D_ERR_NO_DEVICE, "crt1d_preferred_batch: no CUDA device");
+    cudaError_t e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return cuda_fail(e, "crt1d_preferred_batch: cudaDeviceGetAttribute");
+    return crt::preferred_batch(scheme, n_z, n_wl, max_scen, n_sm);
+}
+
 int crt1d_reload_tuning(void) {
     crt::reload_tuning();
     return CRT1D_OK;

@@ -9,6 +9,7 @@
 namespace crt {
 
 size_t solve_shared_bytes(int scheme, int n_z);
+int64_t preferred_batch(int scheme, int n_z, int n_wl, int64_t max_scen, int n_sm);
 void reload_tuning();  // re-read the CRT1D_B200_* tuning variables (read once at load otherwise)
 cudaError_t launch_solve(int scheme, const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream);
 cudaError_t launch_absorption(const crt1d_batch& in, const double* I_dr, const double* I_df_d, const double* I_df_u,

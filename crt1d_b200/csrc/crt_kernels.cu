@@ -561,10 +561,12 @@ static bool flat_eligible(const crt1d_batch& in, int nthr, size_t& smem) {
     smem = (2 * tab_doubles(SCHEME, in.n_z) + (size_t)nthr * seg_thread_doubles<VEC>(SCHEME, in.n_z)) * sizeof(double);
     const size_t old_smem = (tab_doubles(SCHEME, in.n_z) + (size_t)nthr * seg_thread_doubles<VEC>(SCHEME, in.n_z)) * sizeof(double);
     const size_t per_sm = 228u * 1024u, per_cta = 1024u + sizeof(double) * (BLK / 32) * 8;
-    if (smem > 227u * 1024u) return false;
     // resident CTAs the (scenario, band tile) mapping gets: the register bound (MINB CTAs of BLK threads) or its shared memory
+    // (n79 at n_z = 1000 keeps ONE resident CTA either way: 64 B of tables per level.  Moving the tables to global memory
+    // (read through L1) so that two CTAs fit was measured and dropped: 0.61 -> 0.53-0.57 of HBM peak -- twice the resident
+    // columns double the parked-checkpoint working set (242 MB at two CTAs per SM against 126 MB of L2).)
     const size_t want = std::min<size_t>((size_t)MINB * (BLK / nthr), per_sm / (old_smem + per_cta));
-    return per_sm / (smem + per_cta) >= want;
+    return smem <= 227u * 1024u && per_sm / (smem + per_cta) >= want;
 }
 
 template <int SCHEME, int VEC, int BLK, int MINB>
@@ -641,9 +643,18 @@ template <> struct TileCfg<CRT1D_SCHEME_G77> { static constexpr int BLK = 256, M
 //   zq    (128,4) 0.706 | (128,3) 0.729 | (256,2) 0.748 | (128,5) 0.627 | one column per thread 0.645
 //   n79   (128,4) 0.632 | (128,3) 0.609 | (256,2) 0.625 | (128,5) 0.555 | one column per thread 0.498
 //   zq_pa (128,4) one column per thread 0.476 | (128,3) two columns 0.461 | (128,4) two columns 0.350 | (128,2) 0.383
-template <> struct TileCfg<CRT1D_SCHEME_ZQ_PA> { static constexpr int BLK = 256, MINB = 2; };
-template <> struct TileCfg<CRT1D_SCHEME_ZQ> { static constexpr int BLK = 256, MINB = 2; };
-template <> struct TileCfg<CRT1D_SCHEME_N79> { static constexpr int BLK = 256, MINB = 2; };
+#ifndef CRT_ZQPA_MINB
+#define CRT_ZQPA_MINB 2
+#endif
+template <> struct TileCfg<CRT1D_SCHEME_ZQ_PA> { static constexpr int BLK = 256, MINB = CRT_ZQPA_MINB; };
+#ifndef CRT_ZQ_MINB
+#define CRT_ZQ_MINB 2
+#endif
+#ifndef CRT_N79_MINB
+#define CRT_N79_MINB 2
+#endif
+template <> struct TileCfg<CRT1D_SCHEME_ZQ> { static constexpr int BLK = 256, MINB = CRT_ZQ_MINB; };
+template <> struct TileCfg<CRT1D_SCHEME_N79> { static constexpr int BLK = 256, MINB = CRT_N79_MINB; };
 
 template <int SCHEME>
 static cudaError_t launch_vec(const crt1d_batch& in, const crt1d_out& out, bool vec2, cudaStream_t stream) {
@@ -1528,6 +1539,18 @@ static size_t rows_shared_bytes(int n_z, int n_wl, int split = 1, int vec = 2) {
     return (size_t)(n_tab + (n_tab & 1) + RowsTraits<SCHEME>::NC * ld) * sizeof(double) + (size_t)chunks_per_part * (4 * sizeof(double) + sizeof(int));
 }
 
+// 4s band split of a launch: the configured split (2), widened to 3 or 4 when two CTAs would not fit (deep canopies);
+// 1 = no split possible.  `smem2` = dynamic shared memory of one CTA at that split.
+static int split_4s_for(int n_z, int n_wl, int vec, size_t& smem2) {
+    int split = tuning().split_4s;
+    smem2 = rows_shared_bytes<CRT1D_SCHEME_4S>(n_z, n_wl, split, vec);
+    while (split >= 2 && split < 4 && 2 * (smem2 + 3 * 1024) > 228u * 1024u) {
+        ++split;
+        smem2 = rows_shared_bytes<CRT1D_SCHEME_4S>(n_z, n_wl, split, vec);
+    }
+    return (split >= 2 && 2 * (smem2 + 3 * 1024) <= 228u * 1024u) ? split : 1;
+}
+
 template <int SCHEME, int VEC, int LV, int MAXT, bool F32>
 static cudaError_t launch_rows_t(const crt1d_batch& in, const crt1d_out& out, int th, size_t smem, cudaStream_t stream) {
     // 4s: its coefficient stage (eigen-system + 4x4 solve, 168 registers) is better kept as a separate phase
@@ -1562,13 +1585,9 @@ static cudaError_t launch_rows_t(const crt1d_batch& in, const crt1d_out& out, in
         // one CTA's store-free coefficient phase (~20 % of its life) overlaps the other's level sweeps.
         // Deep canopies (n_z = 1000: 16 KB of level tables on top of the coefficients): the band chunks are split three
         // or four ways instead, so that two CTAs still fit.
-        int split = tuning().split_4s;
-        size_t smem2 = rows_shared_bytes<SCHEME>(in.n_z, in.n_wl, split, VEC);
-        while (split >= 2 && split < 4 && 2 * (smem2 + 3 * 1024) > 228u * 1024u) {
-            ++split;
-            smem2 = rows_shared_bytes<SCHEME>(in.n_z, in.n_wl, split, VEC);
-        }
-        if (split >= 2 && in.n_scen * split <= 2147483647LL && 2 * (smem2 + 3 * 1024) <= 228u * 1024u) {
+        size_t smem2 = 0;
+        const int split = split_4s_for(in.n_z, in.n_wl, VEC, smem2);
+        if (split >= 2 && in.n_scen * split <= 2147483647LL) {
             auto kern2 = solve_rows_kernel<SCHEME, VEC, LV, MAXT / 2, F32, FUSED, 2>;
             cudaError_t e = ensure_smem(kern2, smem2);
             if (e != cudaSuccess) return finish(e);
@@ -1677,6 +1696,41 @@ tile:
         case CRT1D_SCHEME_ZQ_PA: return launch_vec<CRT1D_SCHEME_ZQ_PA>(in, out, vec2 && ZQPA_VEC == 2, stream);
         default: return cudaErrorInvalidValue;
     }
+}
+
+// Scenarios per launch, at most `max_scen`, that fill WHOLE waves of resident CTAs for the kernel launch_solve picks.
+// A kernel whose CTAs all take about the same time T runs ceil(grid / resident) * T: 4.1 waves cost 5 (the deep-canopy
+// zq launch of 296 scenarios: 1215 CTAs on 296 slots).  Row-sweep kernels: one CTA per scenario and SM (4s: `split`
+// CTAs per scenario, two resident); flat tridiagonal kernels: grid = ceil(n gps / nthr) on n_SM x resident slots.
+int64_t preferred_batch(int scheme, int n_z, int n_wl, int64_t max_scen, int n_sm) {
+    if (max_scen < scen_kernel_min_batch() || n_sm <= 0) return max_scen;
+    const bool vec2 = n_wl % 2 == 0 && !tuning().force_vec1;
+    int64_t num = 1, den = 1;  // scenarios per wave = n_sm * num / den
+    if (scheme == CRT1D_SCHEME_ZQ || scheme == CRT1D_SCHEME_N79) {
+        crt1d_batch in{};
+        in.n_z = n_z;
+        in.n_wl = n_wl;
+        constexpr int B = TileCfg<CRT1D_SCHEME_ZQ>::BLK, M = TileCfg<CRT1D_SCHEME_ZQ>::MINB;
+        const int nthr = tile_threads(B, B);
+        size_t smem = 0;
+        bool flat;
+        if (scheme == CRT1D_SCHEME_ZQ)
+            flat = vec2 ? flat_eligible<CRT1D_SCHEME_ZQ, 2, B, M>(in, nthr, smem) : flat_eligible<CRT1D_SCHEME_ZQ, 1, B, M>(in, nthr, smem);
+        else
+            flat = vec2 ? flat_eligible<CRT1D_SCHEME_N79, 2, B, M>(in, nthr, smem) : flat_eligible<CRT1D_SCHEME_N79, 1, B, M>(in, nthr, smem);
+        if (!flat) return max_scen;
+        const size_t per_cta = 1024u + sizeof(double) * (B / 32) * 8;
+        const int64_t resident = std::min<int64_t>((int64_t)M * (B / nthr), (int64_t)((228u * 1024u) / (smem + per_cta)));
+        num = resident * nthr;
+        den = n_wl / (vec2 ? 2 : 1);
+    } else if (scheme == CRT1D_SCHEME_4S) {
+        size_t smem2 = 0;
+        const int split = split_4s_for(n_z, n_wl, vec2 ? 2 : 1, smem2);
+        if (split >= 2) { num = 2; den = split; }
+    }
+    const int64_t waves = max_scen * den / (n_sm * num);
+    if (waves <= 0) return max_scen;
+    return waves * n_sm * num / den;
 }
 
 // ---------------------------------------------------------------------------------------------

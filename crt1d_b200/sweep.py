@@ -111,6 +111,9 @@ class SweepRunner:
     buffers (each far larger than the 126 MB L2, so nothing is served from cache between chunks),
     while the fused per-scenario diagnostics (canopy-integrated absorbed PAR / NIR) of ALL scenarios
     stay resident and are what leaves the GPU.  One kernel launch per chunk; chunks are independent.
+
+    `chunk` = scenarios per launch; a negative value means "at most |chunk|, rounded down to whole waves of resident
+    CTAs for this scheme's kernel" (`crt1d_preferred_batch`).
     """
 
     def __init__(self, spec, scheme="2s", *, chunk=4096, device=None, n_buffers=2, bands=("PAR", "NIR"),
@@ -129,7 +132,17 @@ class SweepRunner:
             self.order = np.asarray(order)
             spec = spec.permuted(self.order)
         self.spec, self.scheme = spec, scheme
-        self.chunk = int(min(chunk, spec.n_scen))
+        self.chunk = int(min(abs(chunk), spec.n_scen))
+        if chunk < 0:  # "at most |chunk| scenarios per launch, whole waves of resident CTAs": the library knows its kernels
+            from . import _abi
+            from . import _lib
+
+            idx = device if isinstance(device, int) else getattr(device, "index", None)
+            idx = -1 if idx is None else int(idx)
+            n = _lib.load().crt1d_preferred_batch(_abi.SCHEME_IDS[scheme], spec.n_z, spec.n_wl, self.chunk, idx)
+            if n < 0:
+                _lib.check(int(n))
+            self.chunk = int(n)
         self.n_buffers = int(n_buffers)
         self.profiles = profiles
         self.profile_dtype = profile_dtype  # None / torch.float64, or torch.float32 storage (closed-form schemes)

@@ -181,6 +181,11 @@ CRT1D_API int crt1d_solve_zq_pa(const crt1d_batch* in, const crt1d_out* out, voi
  * of its library. */
 CRT1D_API int crt1d_solve_host(int scheme, const crt1d_batch* in_host, const crt1d_out* out_host, int device);
 CRT1D_API int crt1d_release_workspace(void); /* frees the calling thread's cached device workspace, streams and staging ring */
+/* Scenarios per `crt1d_solve` launch, at most `max_scen`, that fill whole waves of resident CTAs for the kernel the
+ * library picks for (scheme, n_z, n_wl) on `device` (-1 = the current one): a caller that cuts a sweep into chunks
+ * (the reference would loop `Model.run`, crt1d/model.py:298-320) should cut it into chunks of this size -- a launch
+ * of 4.1 waves costs 5.  Returns the size (> 0) or a negative error code. */
+CRT1D_API int64_t crt1d_preferred_batch(int scheme, int32_t n_z, int32_t n_wl, int64_t max_scen, int device);
 /* test / tuning hook: re-read the CRT1D_B200_* kernel-selection environment variables (they are read once, when
  * the library is loaded; no getenv on the launch path). */
 CRT1D_API int crt1d_reload_tuning(void);

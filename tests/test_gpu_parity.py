@@ -1139,6 +1139,36 @@ def test_flat_column_mapping_equals_tile_mapping(scheme, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_preferred_batch_fills_whole_waves():
+    """crt1d_preferred_batch: scenarios per launch that fill whole waves of resident CTAs for the kernel the library
+    picks (row-sweep: one CTA per scenario and SM; flat tridiagonal kernels: ceil(n gps / 256) CTAs on 2 n_SM slots;
+    deep 4s: three CTAs per scenario, two resident).  SweepRunner(chunk=-N) uses it."""
+    import torch
+
+    from crt1d_b200 import _abi
+    from crt1d_b200 import _lib
+    from crt1d_b200 import sweep
+
+    lib = _lib.load()
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    ids = _abi.SCHEME_IDS
+    pb = lambda sch, nz, mx: int(lib.crt1d_preferred_batch(ids[sch], nz, 2100, mx, 0))
+    assert pb("2s", 60, 4144) == (4144 // n_sm) * n_sm
+    assert pb("2s", 60, 100) == 100  # below the row-sweep threshold: nothing to round
+    for sch, nz, mx in (("zq", 1000, 296), ("n79", 1000, 296), ("zq", 60, 4144), ("n79", 60, 4144)):
+        n = pb(sch, nz, mx)
+        assert 0 < n <= mx
+        ctas = -(-n * 1050 // 256)
+        waves = ctas / (2 * n_sm)
+        assert waves <= round(waves) + 1e-9 and round(waves) - waves < 0.02, (sch, nz, n, waves)
+    if n_sm == 148:
+        assert pb("zq", 1000, 296) == 288 and pb("zq", 60, 4144) == 4113 and pb("4s", 1000, 296) == 296 and pb("4s", 60, 4144) == 4144
+    assert lib.crt1d_preferred_batch(99, 60, 2100, 100, 0) < 0
+    spec = sweep.synthetic_sweep_spec(seed=0).slice(0, 5000)
+    assert sweep.SweepRunner(spec, "zq", chunk=-4144, device=torch.device("cuda", 0)).chunk == pb("zq", 60, 4144)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("split", ["1", "3", "4"])
 def test_4s_rows_kernel_band_splits(split, monkeypatch):
     """4s row-sweep kernel: `split` CTAs share a scenario's band chunks (2 by default; 3 or 4 on deep canopies, where
