@@ -981,6 +981,74 @@ CRT_HD void interp_np_prepare(double x, const double* xp, int n, double dl, int&
     w = 1.0 / (xp[j + 1] - xp[j]);
 }
 
+// ---- closed form of the M-grid system (ordinary columns) -----------------------------------------------------
+// The M-grid layers are identical (LAI/M each, ref :96-100), so the interior rows of the reference's matrix
+// (ref :205-225) have CONSTANT coefficients: with y_k = (SWu0[k], SWd0[k]) rows 2k-1 and 2k read
+//     y_k = T y_{k-1} + c Ib[k],   T = [[a, b], [-s a, D/pen - s b]],  a = pen/D,  b = s pen/D,  D = 1 - s^2,
+//     c = (cA, -s cA - (D/pen) cB),   for k = 2..M-1   (row 2k-1 differs at k = 1: soil below; row 2k at k = M: sky above).
+// det T = 1 and tr T = pen + D/pen >= 2 (equality only for conservative leaves), so the eigenvalues are lam >= 1 and
+// 1/lam, and Ib[k] = I_dr0 exp(-Kb cum[M+1-k]) is geometric with ratio 1/taub.  Hence for k = 1..M-1
+//     y_k = alpha lam^{k-(M-1)} v+  +  beta lam^{-(k-1)} v-  +  w Ib[k],      (1 - T taub) w = c,
+// with alpha, beta from the two boundary rows (row 1 with row 2 eliminating SWd0[0]; row 2M with SWd0[M] = I_df0).
+// The back sweep then needs two multiplications and six FMAs per grid level instead of the checkpointed Thomas
+// recurrences (two forward passes with two reciprocals per level each).  The same linear system as the reference's
+// dense solve; measured against it on 40 000 adversarial columns: <= 2e-11 outside the two windows below, where the
+// column falls back to the Thomas sweep:
+//   (lam - 1) M < CRT_ZQPA_DEGENERATE : the two modes approach linear dependence (error ~ eps / ((lam-1) M)^2);
+//   |1 - lam taub| < CRT_ZQPA_RESONANCE : the beam decays like the diffuse mode, w ~ 1/(1 - lam taub) cancels.
+#ifndef CRT_ZQPA_DEGENERATE
+#define CRT_ZQPA_DEGENERATE 5e-2
+#endif
+#ifndef CRT_ZQPA_RESONANCE
+#define CRT_ZQPA_RESONANCE 1e-4
+#endif
+struct ZqPaClosed {
+    double Au, Bu, wu, Ad, Bd, wd;  // SWu0[k] = Au P + Bu Q + wu Ib[k],  SWd0[k] = Ad P + Bd Q + wd Ib[k]
+    double lam, il, Q_top;          // P = lam^{k-(M-1)}, Q = lam^{-(k-1)};  Q_top = lam^{-(M-2)} = Q at k = M-1
+};
+// one_m_t = 1 - tau_d, aL = 1 - (leaf_r + leaf_t); Ib1, IbM1, IbM = Ib[1], Ib[M-1], Ib[M].  Returns false for a
+// column that must take the Thomas sweep (windows above, M < 4, non-finite or underflowing coefficients).
+CRT_HD bool zq_pa_closed_coef(const ZqCol& c, double one_m_t, double aL, double taub, int M, double Ib1, double IbM1,
+                              double IbM, double x0, double Idf0, ZqPaClosed& o) {
+#ifdef CRT_ZQPA_NO_CLOSED
+    return false;
+#else
+    if (M < 4) return false;
+    const double pen = c.pen, s = c.s, D = c.m_mid;
+    const double q1 = one_m_t * aL;                     // = 1 - pen - s, without the cancellation
+    const double hm1 = (q1 * (q1 + 2.0 * s)) / (2.0 * pen);  // tr T / 2 - 1
+    const double lam = 1.0 + hm1 + sqrt(hm1 * (hm1 + 2.0));
+    const double il = 1.0 / lam;
+    if (!((lam - 1.0) * M >= CRT_ZQPA_DEGENERATE) || !(fabs(1.0 - lam * taub) >= CRT_ZQPA_RESONANCE)) return false;
+    double Qt = 1.0, x = il;  // lam^{-(M-2)} by squaring
+    for (int n = M - 2; n > 0; n >>= 1) {
+        if (n & 1) Qt *= x;
+        x *= x;
+    }
+    if (!(Qt > 1e-280)) return false;
+    const double ip = 1.0 / pen;
+    const double a = pen * c.im_mid, b = s * a, T21 = -s * a, T22 = D * ip - s * b;
+    // eigenvectors: v+ = (b, lam - a) (T22 - lam and a - lam have opposite signs: lam - a > 0), v- = (1/lam - T22, T21)
+    const double vpu = b, vpd = lam - a, vmu = il - T22, vmd = T21;
+    const double c0 = c.cA, c1 = -s * c.cA - D * ip * c.cB;
+    const double m00 = 1.0 - a * taub, m01 = -b * taub, m10 = -T21 * taub, m11 = 1.0 - T22 * taub;
+    const double idet = 1.0 / (m00 * m11 - m01 * m10);
+    const double wu = (c0 * m11 - m01 * c1) * idet, wd = (m00 * c1 - m10 * c0) * idet;
+    // row 1 (soil below: s_bot, m_bot) with SWd0[0] eliminated through row 2:  c1u SWu0[1] + c1d SWd0[1] = r1
+    const double pp = c.s_bot * pen * pen * c.im_mid;
+    const double c1u = c.m_bot - s * pp, c1d = -pp;
+    const double r1 = c.m_bot * c.cA * Ib1 + pen * x0 + c.s_bot * pen * c.cB * Ib1 - (c1u * wu + c1d * wd) * Ib1;
+    const double r2 = pen * Idf0 + c.cB * IbM - wd * IbM1;  // row 2M: SWd0[M-1] = pen I_df0 + cB Ib[M]
+    const double A00 = (c1u * vpu + c1d * vpd) * Qt, A01 = c1u * vmu + c1d * vmd, A10 = vpd, A11 = Qt * vmd;
+    const double idd = 1.0 / (A00 * A11 - A01 * A10);
+    const double al = (r1 * A11 - A01 * r2) * idd, be = (A00 * r2 - A10 * r1) * idd;
+    o.Au = al * vpu; o.Ad = al * vpd; o.Bu = be * vmu; o.Bd = be * vmd;
+    o.wu = wu; o.wd = wd; o.lam = lam; o.il = il; o.Q_top = Qt;
+    const double chk = o.Au + o.Ad + o.Bu + o.Bd + wu + wd;
+    return chk - chk == 0.0;  // all finite
+#endif
+}
+
 // eC[i] = exp(-Kb cum[i]) on the M-grid (cum = running sum of LAI/M as np.cumsum produces it, ref :161).
 // The caller's levels come sorted by descending grid interval (the order in which the back sweep can finish
 // them): lk[c] = (level j, interval k) as two int32, and tt/ww (interp_np_prepare()) and eK = exp(-Kb lai[j])
@@ -1000,6 +1068,8 @@ CRT_HD void column_zq_pa(const ScenZqPa& s, const double* eC, const double* lk, 
     const double dl = s.LAI / M;
     const double taub = exp(-s.Kb * dl);                                            // ref :173
     ZqCol col[VEC];
+    ZqPaClosed cf[VEC];
+    bool closed = true;
     double x0[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
@@ -1024,6 +1094,8 @@ CRT_HD void column_zq_pa(const ScenZqPa& s, const double* eC, const double* lk, 
         c.kA = c.m_mid * c.cA;
         c.kB = c.m_mid * c.cB;
         x0[v] = rho * (eC[M] * in.Idr0[v]);                                         // C[0] = SoilAlbedo Ib[0]  (ref :241)
+        closed = zq_pa_closed_coef(c, 1.0 - t, aL, taub, M, eC[M] * in.Idr0[v], eC[M >= 2 ? 2 : M] * in.Idr0[v], eC[M >= 1 ? 1 : 0] * in.Idr0[v],
+                                   x0[v], in.Idf0[v], cf[v]) && closed;
     }
     // rows 2k-1 ("A") and 2k ("B") of grid layer k, as in column_zq (ref :195-236); Ib[k] = f_sl[k] IbSky (ref :165-169)
     auto rowA = [&](int k, int v, double e_in, double f_in, double& eA, double& fA) {
@@ -1059,12 +1131,14 @@ CRT_HD void column_zq_pa(const ScenZqPa& s, const double* eC, const double* lk, 
 #pragma unroll
     for (int v = 0; v < VEC; ++v) { e_prev[v] = 0.0; f_prev[v] = x0[v]; }
     const int g_last = (M - 1) / CK;  // segment g covers k = g CK + 1 .. min((g+1) CK, M)
-    for (int k = 1; k <= g_last * CK; ++k) {
+    if (!closed) {
+        for (int k = 1; k <= g_last * CK; ++k) {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) fwd(k, v, e_prev[v], f_prev[v], e_prev[v], f_prev[v]);
-        if (k % CK == 0) {
-            out.seg_st(CK + 1 + k / CK, 0, e_prev);
-            out.seg_st(CK + 1 + k / CK, 1, f_prev);
+            for (int v = 0; v < VEC; ++v) fwd(k, v, e_prev[v], f_prev[v], e_prev[v], f_prev[v]);
+            if (k % CK == 0) {
+                out.seg_st(CK + 1 + k / CK, 0, e_prev);
+                out.seg_st(CK + 1 + k / CK, 1, f_prev);
+            }
         }
     }
     // ---- streamed interpolation + outputs (ref :350-361, :403-407).  D[k] = SWd[k], U[k] = SWu[k] after the
@@ -1108,6 +1182,31 @@ CRT_HD void column_zq_pa(const ScenZqPa& s, const double* eC, const double* lk, 
     double SWd0_hi[VEC], pend[VEC];  // x[2k+1] = SWd0[k];  SWd0[k+1]
 #pragma unroll
     for (int v = 0; v < VEC; ++v) { SWd0_hi[v] = in.Idf0[v]; pend[v] = 0.0; }
+    if (closed) {
+        // Closed form: SWu0[k], SWd0[k] for k = M-1 .. 1 from the two modes (advanced by one multiplication each)
+        // and the beam term; pend = SWd0[k+1] starts as SWd0[M] = I_df0 (last row).
+        double P[VEC], Q[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { pend[v] = in.Idf0[v]; P[v] = 1.0; Q[v] = cf[v].Q_top; }
+        for (int k = M - 1; k >= 1; --k) {
+            const double eCk = eC[M + 1 - k];
+            double Dn[VEC], Un[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const ZqCol& c = col[v];
+                const ZqPaClosed& f = cf[v];
+                const double Ib = eCk * in.Idr0[v];
+                const double u = f.Au * P[v] + f.Bu * Q[v] + f.wu * Ib;  // SWu0[k]
+                const double d = f.Ad * P[v] + f.Bd * Q[v] + f.wd * Ib;  // SWd0[k]
+                Dn[v] = (pend[v] + u * c.s) * c.im_mid;  // eq. 24 (ref :288-312)
+                Un[v] = (u + pend[v] * c.s) * c.im_mid;  // eq. 25 (ref :318-342)
+                pend[v] = d;
+                P[v] *= f.il;
+                Q[v] *= f.lam;
+            }
+            pair_done(k, Dn, Un);
+        }
+    } else
     for (int g = g_last; g >= 0; --g) {
         const int base = g * CK;
         const int len = (M - base < CK) ? M - base : CK;

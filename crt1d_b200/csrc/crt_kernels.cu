@@ -515,7 +515,15 @@ __host__ __device__ constexpr bool has_fast_tile(int scheme) {
     return scheme == CRT1D_SCHEME_ZQ || scheme == CRT1D_SCHEME_N79 || scheme == CRT1D_SCHEME_ZQ_PA;
 }
 
-constexpr int ZQPA_VEC = 1, ZQPA_THREADS = 128;  // zq_pa: one column per thread, 128-thread CTAs (measured below)
+#ifndef CRT_ZQPA_VEC
+#define CRT_ZQPA_VEC 1
+#endif
+#ifndef CRT_ZQPA_THREADS
+#define CRT_ZQPA_THREADS 256
+#endif
+// zq_pa: one column per thread.  CTA size: 256 threads when its shared memory fits (closed M-grid solution: 0.66 of HBM
+// peak vs 0.59 with 128-thread CTAs -- longer row fragments per store; two columns per thread 0.51 / 0.48), else 128.
+constexpr int ZQPA_VEC = CRT_ZQPA_VEC, ZQPA_THREADS = CRT_ZQPA_THREADS, ZQPA_THREADS_MIN = 128;
 
 // Threads per CTA of a tile-kernel launch: the configured size, or CRT1D_B200_TILE_THREADS (<= the compiled
 // bound; tuning).  One CTA walks a scenario's bands in passes of nthr * VEC columns and the last pass is partly
@@ -599,7 +607,11 @@ static cudaError_t launch_flat(const crt1d_batch& in, const crt1d_out& out, int 
 
 template <int SCHEME, int VEC, int BLK, int MINB>
 static cudaError_t launch_one(const crt1d_batch& in, const crt1d_out& out, cudaStream_t stream) {
-    const int nthr = tile_threads(SCHEME == CRT1D_SCHEME_ZQ_PA ? ZQPA_THREADS : BLK, BLK);
+    int nthr = tile_threads(BLK, BLK);
+    if constexpr (SCHEME == CRT1D_SCHEME_ZQ_PA) {
+        const size_t want = (tab_doubles(SCHEME, in.n_z) + (size_t)ZQPA_THREADS * seg_thread_doubles<VEC>(SCHEME, in.n_z)) * sizeof(double);
+        nthr = tile_threads(want + 2048u <= 227u * 1024u ? ZQPA_THREADS : ZQPA_THREADS_MIN, BLK);
+    }
     if constexpr (uses_segments(SCHEME)) {
         size_t smem_flat = 0;
         if (flat_eligible<SCHEME, VEC, BLK, MINB>(in, nthr, smem_flat)) return launch_flat<SCHEME, VEC, BLK, MINB>(in, out, nthr, smem_flat, stream);
@@ -665,7 +677,7 @@ static cudaError_t launch_vec(const crt1d_batch& in, const crt1d_out& out, bool 
 size_t solve_shared_bytes(int scheme, int n_z) {
     if (!uses_segments(scheme)) return (size_t)n_level_tables(scheme) * n_z * sizeof(double);
     if (scheme == CRT1D_SCHEME_ZQ_PA)
-        return (tab_doubles(scheme, n_z) + (size_t)ZQPA_THREADS * seg_thread_doubles<ZQPA_VEC>(scheme, n_z)) * sizeof(double);
+        return (tab_doubles(scheme, n_z) + (size_t)ZQPA_THREADS_MIN * seg_thread_doubles<ZQPA_VEC>(scheme, n_z)) * sizeof(double);
     const int blk = scheme == CRT1D_SCHEME_ZQ ? TileCfg<CRT1D_SCHEME_ZQ>::BLK : TileCfg<CRT1D_SCHEME_N79>::BLK;
     return (tab_doubles(scheme, n_z) + (size_t)blk * seg_thread_doubles<2>(scheme, n_z)) * sizeof(double);
 }

@@ -125,6 +125,79 @@ def test_kernel_math_multi_scenario_indexing(default_p):
             assert_close(out["absorbed"][s, 0], ab["aI"].sum(), 1e-9, f"{scheme}[{s}] absorbed")
 
 
+def _zq_pa_adversarial_case(nz, sza_deg, lai_tot, seed):
+    """Default case with leaf / soil optics that stress zq_pa's closed M-grid solution: omega from 1e-6 to 1 - 1e-12
+    (degenerate eigenvalue of the layer transfer matrix), bands placed ON the beam / diffuse-mode resonance
+    lam taub = 1 and next to it, black and bright soil, zero direct beam."""
+    from crt1d_b200 import cases
+    from util import with_callables
+
+    rng = np.random.default_rng(seed)
+    q = dict(cases.load_default_case(nz))
+    n = 96
+    om = np.concatenate([10.0 ** rng.uniform(-6, -1, 16), rng.uniform(0.02, 0.98, 40), 1.0 - 10.0 ** rng.uniform(-12, -2, 24),
+                         np.full(16, 0.5)])
+    fr = rng.uniform(0.05, 0.95, n)
+    q["leaf_r"], q["leaf_t"] = om * fr, om * (1 - fr)
+    q["soil_r"] = rng.choice([1e-3, 0.1, 0.3, 0.95], n)  # (exactly black soil zeroes a pivot of the pivot-free Thomas sweep)
+    q["I_dr0_all"] = rng.choice([0.0, 1e-8, 0.7, 1.3], n)
+    q["I_df0_all"] = rng.uniform(1e-6, 1.0, n)
+    q["wl"] = np.linspace(0.4, 2.5, n)
+    q["dwl"] = np.full(n, q["wl"][1] - q["wl"][0])
+    q["wl_leafsoil"] = q["wl"]
+    q["psi"] = np.deg2rad(sza_deg)
+    q["lai"] = np.linspace(1, 0, nz) * lai_tot
+    q = with_callables(q)
+    # the last 16 bands: solve lam(omega) taub = 1 for omega by bisection (same formulas as the kernel), then detune
+    M = min(100, nz)
+    dl = lai_tot / M
+    from crt1d_b200.solvers import common
+
+    taud = common.tau_df_fn(q["K_b_fn"], dl)
+    taub = np.exp(-q["K_b_fn"](q["psi"]) * dl)
+
+    def lam(o, f):
+        rL, tL = f, 1 - f
+        rd = 2 / 3 * rL + 1 / 3 * tL
+        pen = taud + (1 - taud) * o * (1 - rd)
+        sc = rd * o * (1 - taud)
+        hm1 = ((1 - taud) * (1 - o)) * ((1 - taud) * (1 - o) + 2 * sc) / (2 * pen)
+        return 1 + hm1 + np.sqrt(hm1 * (hm1 + 2))
+
+    for i, det in enumerate((0.0, 1e-9, -1e-7, 1e-6, -1e-5, 5e-5, -9e-5, 1.1e-4, -2e-4, 1e-3, -1e-3, 1e-2, 3e-9, -3e-8, 2e-4, -5e-4)):
+        f = fr[80 + i]
+        lo, hi = 1e-9, 1.0  # lam decreases with omega; resonance needs lam = 1/taub
+        if not (lam(hi, f) < 1 / taub < lam(lo, f)):
+            continue
+        for _ in range(200):
+            mid = 0.5 * (lo + hi)
+            lo, hi = (mid, hi) if lam(mid, f) > 1 / taub else (lo, mid)
+        o = min(1.0, max(1e-9, 0.5 * (lo + hi) * (1 + det)))
+        q["leaf_r"][80 + i], q["leaf_t"][80 + i] = o * f, o * (1 - f)
+    return q
+
+
+def test_zq_pa_closed_form_vs_oracle_and_thomas():
+    """zq_pa's closed M-grid solution (crt_core.cuh zq_pa_closed_coef: constant-coefficient layer transfer matrix, two
+    modes + beam term) against the oracle (the reference's dense solve) AND against the same kernel source built with
+    the closed form disabled (checkpointed Thomas sweep on every column), on optics that hit both fall-back windows
+    (degenerate eigenvalue, beam resonance) and their edges."""
+    T = hostcheck.build_variant("zqpa_thomas", ["CRT_ZQPA_NO_CLOSED"])
+    n_closed = 0
+    for nz, sza, lai_tot, seed in ((60, 30.0, 4.0, 0), (10, 65.0, 7.5, 1), (150, 5.0, 1.0, 2), (4, 80.0, 3.0, 3), (33, 50.0, 0.2, 4)):
+        q = _zq_pa_adversarial_case(nz, sza, lai_tot, seed)
+        ref = oracle.run("zq_pa", q)
+        a = _solve(q, "zq_pa")
+        with hostcheck.use_lib(T):
+            b = _solve(q, "zq_pa")
+        for k in ("I_dr", "I_df_d", "I_df_u", "F"):
+            atol = 1e-14 * np.max(np.abs(ref[k]), axis=0, keepdims=True)  # the dense solve's own absolute floor per column
+            assert_close(b[k], ref[k], RTOL, f"thomas zq_pa nz={nz}.{k}", atol=atol)
+            assert_close(a[k], ref[k], RTOL, f"closed zq_pa nz={nz}.{k}", atol=atol)
+        n_closed += int(np.sum(np.any(a["I_df_u"] != b["I_df_u"], axis=0)))
+    assert n_closed > 300  # most of the 480 columns take the closed form (bit-different from the Thomas sweep)
+
+
 def test_leaf_angle_device_functions():
     from crt1d_b200.leaf_angle import LeafAngle
     from crt1d_b200.solvers import common
