@@ -996,6 +996,10 @@ CRT_HD void interp_np_prepare(double x, const double* xp, int n, double dl, int&
 // column falls back to the Thomas sweep:
 //   (lam - 1) M < CRT_ZQPA_DEGENERATE : the two modes approach linear dependence (error ~ eps / ((lam-1) M)^2);
 //   |1 - lam taub| < CRT_ZQPA_RESONANCE : the beam decays like the diffuse mode, w ~ 1/(1 - lam taub) cancels.
+// (zq's system has the same constant-coefficient structure on equally spaced level axes.  The closed form was built and
+// measured there too and DROPPED: 141 -> 61 instructions per unit, but 0.86 -> 0.73 of HBM peak (n_z = 1000: 0.66 -> 0.52).
+// zq's flat kernel is bound by how the column store pattern reaches DRAM, and the Thomas sweep's store-free forward phases
+// halve the number of concurrently open row fragments; see profiles/r02_zq_closed_form_persistent_DROPPED.txt.)
 #ifndef CRT_ZQPA_DEGENERATE
 #define CRT_ZQPA_DEGENERATE 5e-2
 #endif
@@ -1185,24 +1189,29 @@ CRT_HD void column_zq_pa(const ScenZqPa& s, const double* eC, const double* lk, 
     if (closed) {
         // Closed form: SWu0[k], SWd0[k] for k = M-1 .. 1 from the two modes (advanced by one multiplication each)
         // and the beam term; pend = SWd0[k+1] starts as SWd0[M] = I_df0 (last row).
-        double P[VEC], Q[VEC];
+        // The mode amplitudes are carried pre-multiplied (pu = Au P, qu = Bu Q, ...): four multiplications per grid level
+        // and four live values instead of P, Q and four coefficients.
+        double pu[VEC], pd[VEC], qu[VEC], qd[VEC], wuI[VEC], wdI[VEC];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) { pend[v] = in.Idf0[v]; P[v] = 1.0; Q[v] = cf[v].Q_top; }
+        for (int v = 0; v < VEC; ++v) {
+            pend[v] = in.Idf0[v];
+            pu[v] = cf[v].Au; pd[v] = cf[v].Ad;
+            qu[v] = cf[v].Bu * cf[v].Q_top; qd[v] = cf[v].Bd * cf[v].Q_top;
+            wuI[v] = cf[v].wu * in.Idr0[v]; wdI[v] = cf[v].wd * in.Idr0[v];
+        }
         for (int k = M - 1; k >= 1; --k) {
             const double eCk = eC[M + 1 - k];
             double Dn[VEC], Un[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 const ZqCol& c = col[v];
-                const ZqPaClosed& f = cf[v];
-                const double Ib = eCk * in.Idr0[v];
-                const double u = f.Au * P[v] + f.Bu * Q[v] + f.wu * Ib;  // SWu0[k]
-                const double d = f.Ad * P[v] + f.Bd * Q[v] + f.wd * Ib;  // SWd0[k]
+                const double u = (pu[v] + qu[v]) + wuI[v] * eCk;  // SWu0[k];  Ib[k] = I_dr0 eC[M+1-k]
+                const double d = (pd[v] + qd[v]) + wdI[v] * eCk;  // SWd0[k]
                 Dn[v] = (pend[v] + u * c.s) * c.im_mid;  // eq. 24 (ref :288-312)
                 Un[v] = (u + pend[v] * c.s) * c.im_mid;  // eq. 25 (ref :318-342)
                 pend[v] = d;
-                P[v] *= f.il;
-                Q[v] *= f.lam;
+                pu[v] *= cf[v].il; pd[v] *= cf[v].il;
+                qu[v] *= cf[v].lam; qd[v] *= cf[v].lam;
             }
             pair_done(k, Dn, Un);
         }
