@@ -223,6 +223,8 @@ def _kernel_name(scheme, runner):
         return f"crt::solve_rows_kernel<{scheme}> (one CTA per scenario, row-major work items)"
     if scheme in ("zq", "n79") and not os.environ.get("CRT1D_B200_NO_FLAT"):
         return f"crt::solve_flat_kernel<{scheme}, VEC=2> (flat column mapping, checkpointed Thomas sweeps)"
+    if scheme == "zq_pa":
+        return "crt::solve_kernel<zq_pa, VEC=1, 256 threads> (band-tile kernel; closed M-grid solution + streamed interpolation)"
     return f"crt::solve_kernel<{scheme}, VEC=2> (band-tile kernel)"
 
 
