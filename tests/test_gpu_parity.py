@@ -1139,6 +1139,35 @@ def test_flat_column_mapping_equals_tile_mapping(scheme, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_zq_pa_closed_form_and_thomas_columns_on_device():
+    """zq_pa on the device with optics that put columns into both fall-back windows of the closed M-grid solution
+    (degenerate eigenvalue, beam resonance) and on their edges: closed-form and Thomas columns side by side in one warp,
+    with the fused absorbed sums (one CTA per scenario) and without (one CTA per band tile), vs the oracle."""
+    import torch
+
+    from crt1d_b200 import engine
+    from crt1d_b200.scenarios import ScenarioBatch
+    from util import zq_pa_adversarial_case
+
+    for nz, sza, lai_tot, seed in ((60, 30.0, 4.0, 0), (10, 65.0, 7.5, 1), (150, 5.0, 1.0, 2), (4, 80.0, 3.0, 3)):
+        q = zq_pa_adversarial_case(nz, sza, lai_tot, seed)
+        batch = ScenarioBatch.from_params(q)
+        bw = np.stack([np.ones(batch.n_wl), np.linspace(0, 1, batch.n_wl)])
+        ref = oracle.run("zq_pa", q)
+        pro = engine.host_prologue(batch, "zq_pa", K_b_fn=q["K_b_fn"], G_fn=q["G_fn"])  # the reference's own quad calls
+        res = []
+        for with_abs in (True, False):
+            r = engine.solve(batch, "zq_pa", prologue=pro, band_w=bw if with_abs else None)
+            torch.cuda.synchronize()
+            res.append({k: v.cpu().numpy() for k, v in r.items()})
+            for k in ("I_dr", "I_df_d", "I_df_u", "F"):
+                atol = 1e-14 * np.max(np.abs(ref[k]), axis=0, keepdims=True)  # the dense solve's own absolute floor per column
+                assert_close(res[-1][k][0], ref[k], RTOL, f"zq_pa abs={with_abs} nz={nz}.{k}", atol=atol)
+        for k in ("I_dr", "I_df_d", "I_df_u", "F"):
+            assert np.array_equal(res[0][k], res[1][k]), k
+
+
+@pytest.mark.gpu
 def test_preferred_batch_fills_whole_waves():
     """crt1d_preferred_batch: scenarios per launch that fill whole waves of resident CTAs for the kernel the library
     picks (row-sweep: one CTA per scenario and SM; flat tridiagonal kernels: ceil(n gps / 256) CTAs on 2 n_SM slots;

@@ -19,6 +19,7 @@ from util import edge_4s_fixture_cases
 from util import deep_case as _deep_case
 from util import golden
 from util import variant_case
+from util import zq_pa_adversarial_case as _zq_pa_adversarial_case
 
 SCHEMES = ("2s", "bf", "bl", "g77", "n79", "zq", "zq_pa")
 
@@ -123,58 +124,6 @@ def test_kernel_math_multi_scenario_indexing(default_p):
             ab = oracle.calc_absorption(lai=q["lai"], K_b=q["K_b"], leaf_r=q["leaf_r"], leaf_t=q["leaf_t"],
                                         I_dr=ref["I_dr"], I_df_d=ref["I_df_d"], I_df_u=ref["I_df_u"])
             assert_close(out["absorbed"][s, 0], ab["aI"].sum(), 1e-9, f"{scheme}[{s}] absorbed")
-
-
-def _zq_pa_adversarial_case(nz, sza_deg, lai_tot, seed):
-    """Default case with leaf / soil optics that stress zq_pa's closed M-grid solution: omega from 1e-6 to 1 - 1e-12
-    (degenerate eigenvalue of the layer transfer matrix), bands placed ON the beam / diffuse-mode resonance
-    lam taub = 1 and next to it, black and bright soil, zero direct beam."""
-    from crt1d_b200 import cases
-    from util import with_callables
-
-    rng = np.random.default_rng(seed)
-    q = dict(cases.load_default_case(nz))
-    n = 96
-    om = np.concatenate([10.0 ** rng.uniform(-6, -1, 16), rng.uniform(0.02, 0.98, 40), 1.0 - 10.0 ** rng.uniform(-12, -2, 24),
-                         np.full(16, 0.5)])
-    fr = rng.uniform(0.05, 0.95, n)
-    q["leaf_r"], q["leaf_t"] = om * fr, om * (1 - fr)
-    q["soil_r"] = rng.choice([1e-3, 0.1, 0.3, 0.95], n)  # (exactly black soil zeroes a pivot of the pivot-free Thomas sweep)
-    q["I_dr0_all"] = rng.choice([0.0, 1e-8, 0.7, 1.3], n)
-    q["I_df0_all"] = rng.uniform(1e-6, 1.0, n)
-    q["wl"] = np.linspace(0.4, 2.5, n)
-    q["dwl"] = np.full(n, q["wl"][1] - q["wl"][0])
-    q["wl_leafsoil"] = q["wl"]
-    q["psi"] = np.deg2rad(sza_deg)
-    q["lai"] = np.linspace(1, 0, nz) * lai_tot
-    q = with_callables(q)
-    # the last 16 bands: solve lam(omega) taub = 1 for omega by bisection (same formulas as the kernel), then detune
-    M = min(100, nz)
-    dl = lai_tot / M
-    from crt1d_b200.solvers import common
-
-    taud = common.tau_df_fn(q["K_b_fn"], dl)
-    taub = np.exp(-q["K_b_fn"](q["psi"]) * dl)
-
-    def lam(o, f):
-        rL, tL = f, 1 - f
-        rd = 2 / 3 * rL + 1 / 3 * tL
-        pen = taud + (1 - taud) * o * (1 - rd)
-        sc = rd * o * (1 - taud)
-        hm1 = ((1 - taud) * (1 - o)) * ((1 - taud) * (1 - o) + 2 * sc) / (2 * pen)
-        return 1 + hm1 + np.sqrt(hm1 * (hm1 + 2))
-
-    for i, det in enumerate((0.0, 1e-9, -1e-7, 1e-6, -1e-5, 5e-5, -9e-5, 1.1e-4, -2e-4, 1e-3, -1e-3, 1e-2, 3e-9, -3e-8, 2e-4, -5e-4)):
-        f = fr[80 + i]
-        lo, hi = 1e-9, 1.0  # lam decreases with omega; resonance needs lam = 1/taub
-        if not (lam(hi, f) < 1 / taub < lam(lo, f)):
-            continue
-        for _ in range(200):
-            mid = 0.5 * (lo + hi)
-            lo, hi = (mid, hi) if lam(mid, f) > 1 / taub else (lo, mid)
-        o = min(1.0, max(1e-9, 0.5 * (lo + hi) * (1 + det)))
-        q["leaf_r"][80 + i], q["leaf_t"][80 + i] = o * f, o * (1 - f)
-    return q
 
 
 def test_zq_pa_closed_form_vs_oracle_and_thomas():
