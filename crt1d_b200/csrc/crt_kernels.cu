@@ -42,6 +42,7 @@ struct Tuning {
     bool no_rows = false;        // CRT1D_B200_NO_ROWS
     int fixup_parts = 0;         // CRT1D_B200_FIXUP_PARTS (0 = by level count)
     bool no_flat = false;        // CRT1D_B200_NO_FLAT: tridiagonal schemes keep the (scenario, band tile) mapping
+    int smem_pad = 0;            // CRT1D_B200_SMEM_PAD: extra dynamic shared memory (bytes) for the tile / flat kernels (occupancy experiments)
 };
 static Tuning read_tuning() {
     Tuning t;
@@ -55,6 +56,7 @@ static Tuning read_tuning() {
     if (const char* e = getenv("CRT1D_B200_2S_KERNEL")) t.tile_2s = e[0] != 'r';
     t.no_rows = getenv("CRT1D_B200_NO_ROWS") != nullptr;
     t.no_flat = getenv("CRT1D_B200_NO_FLAT") != nullptr;
+    if (const char* e = getenv("CRT1D_B200_SMEM_PAD")) t.smem_pad = atoi(e);
     if (const char* e = getenv("CRT1D_B200_FIXUP_PARTS")) t.fixup_parts = atoi(e);
     return t;
 }
@@ -587,6 +589,7 @@ static cudaError_t launch_flat(const crt1d_batch& in, const crt1d_out& out, int 
     bool all = out.profile_f32 == 0;
     for (int q = 0; q < n_out_fields(SCHEME); ++q) all = all && f[q] != nullptr;
     if (all) kern = solve_flat_kernel<SCHEME, VEC, BLK, MINB, true>;
+    smem = std::min<size_t>(smem + (size_t)std::max(0, tuning().smem_pad), 227u * 1024u);
     if (cudaError_t e = ensure_smem(kern, smem); e != cudaSuccess) return e;
     double* partial = nullptr;
     if (out.absorbed) {
@@ -631,6 +634,7 @@ static cudaError_t launch_one(const crt1d_batch& in, const crt1d_out& out, cudaS
         for (int q = 0; q < n_out_fields(SCHEME); ++q) all = all && f[q] != nullptr;
         if (all) kern = solve_kernel<SCHEME, VEC, BLK, MINB, true>;
     }
+    smem = std::min<size_t>(smem + (size_t)std::max(0, tuning().smem_pad), 227u * 1024u);
     if (cudaError_t e = ensure_smem(kern, smem); e != cudaSuccess) return e;
     kern<<<(unsigned)grid, nthr, smem, stream>>>(in, out, tiles_per_scen, tiles_per_cta);
     return cudaGetLastError();
