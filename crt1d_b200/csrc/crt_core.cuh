@@ -759,7 +759,10 @@ CRT_HD void column_zq(const ScenZq& s, const double* eK, int n_z, const BandIn<V
         ZqCol& c = col[v];
         c.pen = t + (1.0 - t) * (1.0 - a) * (1.0 - r);
         c.s = r * (1.0 - a) * (1.0 - t);
-        c.s_bot = 1.0 * (1.0 - a0) * (1.0 - 0.0);
+        // (a perfectly black soil zeroes the main-diagonal entry -s_bot pen of row 1, a pivot of the pivot-free Thomas sweep;
+        // the reference's pivoting solver does not care.  1e-200 instead of 0 is the exact solution for a soil reflectance
+        // that differs from the caller's by 1e-200: every product below stays finite, x0 = rho S[0] stays exactly 0.)
+        c.s_bot = fmax(1.0 * (1.0 - a0) * (1.0 - 0.0), 1e-200);
         c.m_mid = 1.0 - c.s * c.s;
         c.m_bot = 1.0 - c.s_bot * c.s;
         c.im_mid = 1.0 / c.m_mid;
@@ -1087,7 +1090,7 @@ CRT_HD void column_zq_pa(const ScenZqPa& s, const double* eC, const double* lk, 
         ZqCol& c = col[v];
         c.pen = t + (1.0 - t) * (1.0 - aL) * (1.0 - rd);
         c.s = rd * (1.0 - aL) * (1.0 - t);
-        c.s_bot = 1.0 * (1.0 - a0) * (1.0 - 0.0);                                   // k = 1: soil below
+        c.s_bot = fmax(1.0 * (1.0 - a0) * (1.0 - 0.0), 1e-200);                     // k = 1: soil below (black soil: see column_zq)
         c.m_mid = 1.0 - c.s * c.s;
         c.m_bot = 1.0 - c.s_bot * c.s;
         c.im_mid = 1.0 / c.m_mid;

@@ -1168,6 +1168,22 @@ def test_zq_pa_closed_form_and_thomas_columns_on_device():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("scheme", ["zq", "zq_pa", "n79", "bf", "g77"])  # (2s: the reference itself divides by soil_r, _solve_2s.py:87)
+def test_black_soil_plugin_path(scheme):
+    """soil_r = 0 exactly (the classic black-soil problem): finite and within the common bar of the oracle for every scheme
+    with a soil boundary row; zq / zq_pa needed a pivot floor (the reference's solvers pivot)."""
+    import crt1d_b200 as crt
+
+    m = crt.Model(scheme, nlayers=60)
+    m.update_p(soil_r=np.zeros_like(m._p["soil_r"]))
+    m.run()
+    ref = oracle.run(scheme, m._p)
+    for k in ("I_dr", "I_df_d", "I_df_u", "F"):
+        atol = 1e-14 * np.max(np.abs(ref[k]), axis=0, keepdims=True)
+        assert_close(m.out[k], ref[k], RTOL, f"black soil {scheme}.{k}", atol=atol)
+
+
+@pytest.mark.gpu
 def test_preferred_batch_fills_whole_waves():
     """crt1d_preferred_batch: scenarios per launch that fill whole waves of resident CTAs for the kernel the library
     picks (row-sweep: one CTA per scenario and SM; flat tridiagonal kernels: ceil(n gps / 256) CTAs on 2 n_SM slots;

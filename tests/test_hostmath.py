@@ -147,6 +147,26 @@ def test_zq_pa_closed_form_vs_oracle_and_thomas():
     assert n_closed > 300  # most of the 480 columns take the closed form (bit-different from the Thomas sweep)
 
 
+@pytest.mark.parametrize("rho", [0.0, 1e-300, 1e-30])
+def test_black_soil_zq_family(rho, default_p):
+    """A perfectly black (or numerically black) soil zeroes the main-diagonal entry of row 1 of the zq / zq_pa system --
+    a pivot of the pivot-free Thomas sweep (NaN/Inf before the pivot floor), while the reference's pivoting solvers
+    (`spsolve`, `np.linalg.solve`: _solve_zq.py:147, _solve_zq_pa.py:278) return finite values.  Both builds (closed
+    M-grid solution and Thomas sweep) against the oracle."""
+    T = hostcheck.build_variant("zqpa_thomas", ["CRT_ZQPA_NO_CLOSED"])
+    q = dict(default_p)
+    q["soil_r"] = np.full_like(default_p["soil_r"], rho)
+    for scheme in ("zq", "zq_pa"):
+        ref = oracle.run(scheme, q)
+        a = _solve(q, scheme)
+        with hostcheck.use_lib(T):
+            b = _solve(q, scheme)
+        for k in ref:
+            atol = 1e-14 * np.max(np.abs(ref[k]), axis=0, keepdims=True)  # I_df_u at the ground is ~rho: the reference solve's absolute floor
+            assert_close(a[k], ref[k], RTOL, f"black soil {scheme}.{k}", atol=atol)
+            assert_close(b[k], ref[k], RTOL, f"black soil thomas {scheme}.{k}", atol=atol)
+
+
 def test_leaf_angle_device_functions():
     from crt1d_b200.leaf_angle import LeafAngle
     from crt1d_b200.solvers import common

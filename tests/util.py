@@ -329,7 +329,7 @@ def zq_pa_adversarial_case(nz, sza_deg, lai_tot, seed):
                          np.full(16, 0.5)])
     fr = rng.uniform(0.05, 0.95, n)
     q["leaf_r"], q["leaf_t"] = om * fr, om * (1 - fr)
-    q["soil_r"] = rng.choice([1e-3, 0.1, 0.3, 0.95], n)  # (exactly black soil zeroes a pivot of the pivot-free Thomas sweep)
+    q["soil_r"] = rng.choice([0.0, 0.1, 0.3, 0.95], n)  # incl. a perfectly black soil (zero pivot of a pivot-free sweep)
     q["I_dr0_all"] = rng.choice([0.0, 1e-8, 0.7, 1.3], n)
     q["I_df0_all"] = rng.uniform(1e-6, 1.0, n)
     q["wl"] = np.linspace(0.4, 2.5, n)
