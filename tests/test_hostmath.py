@@ -167,6 +167,51 @@ def test_black_soil_zq_family(rho, default_p):
             assert_close(b[k], ref[k], RTOL, f"black soil thomas {scheme}.{k}", atol=atol)
 
 
+def test_kernel_math_extreme_inputs_fuzz():
+    """Seeded fuzz over inputs no default case reaches: omega from 1e-6 to 1 - 1e-12, soil_r from 1e-12 to 1, zero / tiny /
+    huge sky irradiances, sun at the zenith and 0.1 degree above the horizon, LAI from 0.01 to 20, 3 to 130 levels on linear,
+    quadratic and clustered axes.  (Known limit, outside this range: for VANISHING layers -- total LAI 1e-6 on 130 quartic
+    levels, layer LAI ~1e-8 -- the pivot-free zq sweep is 1.4e-8 off where the reference's pivoting solver is exact to 1e-12.)  Wherever the reference (oracle) is finite the kernel arithmetic must be finite and
+    within the bar; the absolute floor is 1e-12 of the column's scale (its largest value or the sky irradiance): the
+    reference's own solvers do not resolve less.  2s gets 1e-9 / 1e-10 of the column scale: at omega -> 1 its closed form
+    (the reference's as well) loses digits like 1/h -- e.g. the upward flux over a soil of reflectance 1e-12 comes
+    out as 5.2e-10 here, 1.1e-9 in the reference and is 4.0e-10."""
+    from crt1d_b200 import cases
+    from util import with_callables
+
+    rng = np.random.default_rng(11)
+    for trial in range(16):
+        nz = int(rng.choice([3, 4, 7, 20, 60, 130]))
+        q = dict(cases.load_default_case(nz))
+        n = 24
+        om = np.concatenate([10.0 ** rng.uniform(-6, -1, 6), rng.uniform(0.02, 0.98, 10), 1.0 - 10.0 ** rng.uniform(-12, -2, 8)])
+        fr = rng.uniform(0.02, 0.98, n)
+        q["leaf_r"], q["leaf_t"] = om * fr, om * (1 - fr)
+        q["soil_r"] = rng.choice([1e-12, 1e-3, 0.1, 0.5, 1.0], n)
+        q["I_dr0_all"] = rng.choice([0.0, 1e-12, 0.7, 300.0], n)
+        q["I_df0_all"] = rng.choice([0.0, 1e-9, 0.5, 100.0], n)
+        q["wl"] = np.linspace(0.4, 2.5, n)
+        q["dwl"] = np.full(n, q["wl"][1] - q["wl"][0])
+        q["wl_leafsoil"] = q["wl"]
+        q["psi"] = np.deg2rad(rng.choice([0.0, 1e-6, 30.0, 60.0, 85.0, 89.0, 89.9]))
+        x = np.linspace(1, 0, nz)
+        q["lai"] = x ** int(rng.choice([1, 2, 4])) * float(rng.choice([1e-2, 0.5, 3.0, 8.0, 20.0]))
+        q = with_callables(q)
+        scale = (q["I_dr0_all"] + q["I_df0_all"])[None, :]
+        for scheme in SCHEMES:
+            kw = {"tau_d_method": "9sky"} if scheme == "n79" else {}
+            with np.errstate(all="ignore"):
+                ref = oracle.run(scheme, q, **kw)
+            sol = _solve(q, scheme, **kw)
+            for k in ("I_dr", "I_df_d", "I_df_u", "F"):
+                fin = np.isfinite(ref[k])
+                assert np.all(np.isfinite(sol[k][fin])), f"fuzz {trial} {scheme}.{k}: reference finite, kernel math not"
+                r, v = np.where(fin, ref[k], 0.0), np.where(fin, sol[k], 0.0)
+                atol = (1e-10 if scheme == "2s" else 1e-12) * np.maximum(np.max(np.abs(r), axis=0, keepdims=True),
+                                                                         scale * (4.0 if k == "F" else 1.0))
+                assert_close(v, r, 1e-9 if scheme == "2s" else RTOL, f"fuzz {trial} nz={nz} {scheme}.{k}", atol=atol)
+
+
 def test_leaf_angle_device_functions():
     from crt1d_b200.leaf_angle import LeafAngle
     from crt1d_b200.solvers import common
