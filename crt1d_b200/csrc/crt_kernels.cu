@@ -42,6 +42,7 @@ struct Tuning {
     bool no_rows = false;        // CRT1D_B200_NO_ROWS
     int fixup_parts = 0;         // CRT1D_B200_FIXUP_PARTS (0 = by level count)
     bool no_flat = false;        // CRT1D_B200_NO_FLAT: tridiagonal schemes keep the (scenario, band tile) mapping
+    bool no_wide_ck = false;     // CRT1D_B200_NO_WIDE_CK: deep zq keeps the checkpoint spacing of 10 levels
     int smem_pad = 0;            // CRT1D_B200_SMEM_PAD: extra dynamic shared memory (bytes) for the tile / flat kernels (occupancy experiments)
 };
 static Tuning read_tuning() {
@@ -56,6 +57,7 @@ static Tuning read_tuning() {
     if (const char* e = getenv("CRT1D_B200_2S_KERNEL")) t.tile_2s = e[0] != 'r';
     t.no_rows = getenv("CRT1D_B200_NO_ROWS") != nullptr;
     t.no_flat = getenv("CRT1D_B200_NO_FLAT") != nullptr;
+    t.no_wide_ck = getenv("CRT1D_B200_NO_WIDE_CK") != nullptr;
     if (const char* e = getenv("CRT1D_B200_SMEM_PAD")) t.smem_pad = atoi(e);
     if (const char* e = getenv("CRT1D_B200_FIXUP_PARTS")) t.fixup_parts = atoi(e);
     return t;
@@ -99,8 +101,8 @@ __host__ __device__ constexpr bool uses_segments(int scheme) {
     return scheme == CRT1D_SCHEME_ZQ || scheme == CRT1D_SCHEME_N79 || scheme == CRT1D_SCHEME_ZQ_PA;
 }
 // slots (levels) of the segment store: the segment itself, plus zq_pa's checkpoints (its M-grid is not the output grid)
-__host__ __device__ inline int seg_slots(int scheme, int n_z) {
-    if (scheme != CRT1D_SCHEME_ZQ_PA) return SEG_CK + 1;  // + the prefetch slot of the next checkpoint (pf_tmp / ld_pf)
+__host__ __device__ inline int seg_slots(int scheme, int n_z, int ck = SEG_CK) {
+    if (scheme != CRT1D_SCHEME_ZQ_PA) return ck + 1;  // + the prefetch slot of the next checkpoint (pf_tmp / ld_pf)
     const int M = n_z < ZQPA_MAX_M ? n_z : ZQPA_MAX_M;
     return SEG_CK + 1 + (M - 1) / SEG_CK + 1;  // segment slots 0..CK (slot 0 = the pair below the segment) + checkpoints
 }
@@ -109,8 +111,8 @@ __host__ __device__ inline size_t tab_doubles(int scheme, int n_z) { return ((si
 
 // doubles of segment store per thread (thread-major, one pad element: see GlobalOut)
 template <int VEC>
-__host__ __device__ inline int seg_thread_doubles(int scheme, int n_z) {
-    return uses_segments(scheme) ? (seg_slots(scheme, n_z) * 2 + 1) * VEC : 0;
+__host__ __device__ inline int seg_thread_doubles(int scheme, int n_z, int ck = SEG_CK) {
+    return uses_segments(scheme) ? (seg_slots(scheme, n_z, ck) * 2 + 1) * VEC : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -139,7 +141,7 @@ __device__ __forceinline__ void st_raw(float* q, const double (&x)[VEC]) {
 // (scenario, level 0, first band) -- `xoff` for the extra-output slots, whose row count can differ.
 // FAST = every field of the scheme requested and float64 storage: no null checks, no dtype switch
 // (15 -> 3 issue slots per store); the general path keeps both.
-template <int VEC, bool FAST>
+template <int VEC, bool FAST, int CK = SEG_CK>
 struct GlobalOut {
     double* base[N_FIELDS];
     int64_t off, xoff, stride;
@@ -204,7 +206,7 @@ struct GlobalOut {
     // (cp.async: no registers held while it is in flight); ld_pf waits for it and reads the slot.
     __device__ __forceinline__ void pf_tmp(int f, int j, int k) const {
         const double* q = base[f] + at(f, j);
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(seg + (SEG_CK * 2 + k) * VEC);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(seg + (CK * 2 + k) * VEC);
         if constexpr (VEC == 2) {
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(q) : "memory");
         } else {
@@ -213,13 +215,13 @@ struct GlobalOut {
     }
     __device__ __forceinline__ void ld_pf(int f, int j, int k, double (&x)[VEC]) const {
         asm volatile("cp.async.wait_all;" ::: "memory");
-        seg_ld(SEG_CK, k, x);
+        seg_ld(CK, k, x);
     }
     // segment store of the checkpointed Thomas sweeps: `slots` levels x 2 values x VEC columns per thread in
     // shared memory, thread-major with one pad element: thread stride (2 slots + 1) * VEC doubles is an odd
     // multiple of the access width, so a warp's 8/16-byte accesses are bank-conflict free for any CTA size
     double* seg;  // this thread's first element
-    __device__ __forceinline__ int seg_levels() const { return SEG_CK; }
+    __device__ __forceinline__ int seg_levels() const { return CK; }
     __device__ __forceinline__ void seg_st(int slot, int k, const double (&x)[VEC]) const {
         double* q = seg + (slot * 2 + k) * VEC;
         if constexpr (VEC == 2) {
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(BLK, MINB) solve_kernel(const crt1d_batch in, 
 // Canopy-absorbed sums: each CTA reduces its columns per spanned scenario in a fixed order into
 // partial[c][which][band group]; absorbed_flat_finish_kernel adds a scenario's partials in CTA order (deterministic).
 // ---------------------------------------------------------------------------------------------
-template <int SCHEME, int VEC, int BLK, int MINB, bool FAST>
+template <int SCHEME, int VEC, int BLK, int MINB, bool FAST, int CK = SEG_CK>
 __global__ void __launch_bounds__(BLK, MINB) solve_flat_kernel(const crt1d_batch in, const crt1d_out out, int gps,
                                                                double* __restrict__ partial) {
     extern __shared__ double tab[];
@@ -445,10 +447,10 @@ __global__ void __launch_bounds__(BLK, MINB) solve_flat_kernel(const crt1d_batch
         const int64_t prof = (int64_t)n_z * n_wl;                       // doubles per scenario in a profile
         const int64_t xprof = (int64_t)extra_rows(SCHEME, n_z) * n_wl;  // ... in an extra-output slot
         const BandIn<VEC> b = load_bands<VEC>(in, s, b0);
-        GlobalOut<VEC, FAST> o;
+        GlobalOut<VEC, FAST, CK> o;
         o.stride = n_wl;
         o.f32 = out.profile_f32 != 0;
-        o.seg = tab + 2 * td + (size_t)threadIdx.x * seg_thread_doubles<VEC>(SCHEME, n_z);
+        o.seg = tab + 2 * td + (size_t)threadIdx.x * seg_thread_doubles<VEC>(SCHEME, n_z, CK);
         o.off = s * prof + b0;
         o.xoff = s * xprof + b0;
         o.base[F_IDR] = out.I_dr;
@@ -559,7 +561,7 @@ static cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t stream) {
 // Flat mapping (solve_flat_kernel) when a CTA cannot span more than two scenarios and two sets of level tables leave
 // the shared memory for the same number of resident CTAs.
 template <int SCHEME, int VEC, int BLK, int MINB>
-static bool flat_eligible(const crt1d_batch& in, int nthr, size_t& smem) {
+static bool flat_eligible(const crt1d_batch& in, int nthr, size_t& smem, int ck = SEG_CK) {
     if constexpr (!uses_segments(SCHEME)) return false;
     // zq_pa keeps the (scenario, band tile) mapping: its three-pass scenario prologue (M-grid, interpolation tables,
     // emission order) is paid per CTA, and the flat mapping has 16 CTAs per scenario where the fused-absorbed tile
@@ -568,7 +570,8 @@ static bool flat_eligible(const crt1d_batch& in, int nthr, size_t& smem) {
     if (tuning().no_flat) return false;
     const int gps = in.n_wl / VEC;
     if (gps * VEC != in.n_wl || nthr > gps) return false;
-    smem = (2 * tab_doubles(SCHEME, in.n_z) + (size_t)nthr * seg_thread_doubles<VEC>(SCHEME, in.n_z)) * sizeof(double);
+    smem = (2 * tab_doubles(SCHEME, in.n_z) + (size_t)nthr * seg_thread_doubles<VEC>(SCHEME, in.n_z, ck)) * sizeof(double);
+    if (ck != SEG_CK) return smem <= 227u * 1024u - 2048u;  // the wide-spacing variant runs one CTA per SM by design
     const size_t old_smem = (tab_doubles(SCHEME, in.n_z) + (size_t)nthr * seg_thread_doubles<VEC>(SCHEME, in.n_z)) * sizeof(double);
     const size_t per_sm = 228u * 1024u, per_cta = 1024u + sizeof(double) * (BLK / 32) * 8;
     // resident CTAs the (scenario, band tile) mapping gets: the register bound (MINB CTAs of BLK threads) or its shared memory
@@ -579,16 +582,16 @@ static bool flat_eligible(const crt1d_batch& in, int nthr, size_t& smem) {
     return smem <= 227u * 1024u && per_sm / (smem + per_cta) >= want;
 }
 
-template <int SCHEME, int VEC, int BLK, int MINB>
+template <int SCHEME, int VEC, int BLK, int MINB, int CK = SEG_CK>
 static cudaError_t launch_flat(const crt1d_batch& in, const crt1d_out& out, int nthr, size_t smem, cudaStream_t stream) {
     const int gps = in.n_wl / VEC;
     const int64_t grid = (in.n_scen * gps + nthr - 1) / nthr;
     if (grid <= 0 || grid > 2147483647LL) return cudaErrorInvalidConfiguration;
-    auto kern = solve_flat_kernel<SCHEME, VEC, BLK, MINB, false>;
+    auto kern = solve_flat_kernel<SCHEME, VEC, BLK, MINB, false, CK>;
     double* const f[7] = {out.I_dr, out.I_df_d, out.I_df_u, out.F, out.x0, out.x1, out.x2};
     bool all = out.profile_f32 == 0;
     for (int q = 0; q < n_out_fields(SCHEME); ++q) all = all && f[q] != nullptr;
-    if (all) kern = solve_flat_kernel<SCHEME, VEC, BLK, MINB, true>;
+    if (all) kern = solve_flat_kernel<SCHEME, VEC, BLK, MINB, true, CK>;
     smem = std::min<size_t>(smem + (size_t)std::max(0, tuning().smem_pad), 227u * 1024u);
     if (cudaError_t e = ensure_smem(kern, smem); e != cudaSuccess) return e;
     double* partial = nullptr;
@@ -608,6 +611,20 @@ static cudaError_t launch_flat(const crt1d_batch& in, const crt1d_out& out, int 
     return e;
 }
 
+// Deep canopies, zq: the checkpoints parked by all resident columns -- n_SM x 512 threads x (n_z / CK) x 32 B at two CTAs per SM --
+// outgrow the 126 MB L2 near n_z = 520 at CK = 10, and every parked pair then makes a round trip to HBM.  From there on zq runs
+// the flat kernel with checkpoints every 20 levels (twice the segment store: ONE resident CTA, a quarter of the parked bytes in
+// flight).  Measured at n_z = 1000 (variant builds, one box): CK = 10 0.665 | 14 0.693 | 16 0.703 | 20 0.707 of HBM peak.
+// Same arithmetic in the same order: the profiles are bit-identical for any spacing.
+#ifndef CRT_ZQ_DEEP_CK
+#define CRT_ZQ_DEEP_CK 20
+#endif
+#ifndef CRT_ZQ_DEEP_NZ
+#define CRT_ZQ_DEEP_NZ 512
+#endif
+constexpr int ZQ_DEEP_CK = CRT_ZQ_DEEP_CK;
+static bool zq_wide_spacing(int n_z) { return ZQ_DEEP_CK != SEG_CK && n_z >= CRT_ZQ_DEEP_NZ && !tuning().no_flat && !tuning().no_wide_ck; }
+
 template <int SCHEME, int VEC, int BLK, int MINB>
 static cudaError_t launch_one(const crt1d_batch& in, const crt1d_out& out, cudaStream_t stream) {
     int nthr = tile_threads(BLK, BLK);
@@ -617,6 +634,10 @@ static cudaError_t launch_one(const crt1d_batch& in, const crt1d_out& out, cudaS
     }
     if constexpr (uses_segments(SCHEME)) {
         size_t smem_flat = 0;
+        if constexpr (SCHEME == CRT1D_SCHEME_ZQ) {
+            if (zq_wide_spacing(in.n_z) && flat_eligible<SCHEME, VEC, BLK, MINB>(in, nthr, smem_flat, ZQ_DEEP_CK))
+                return launch_flat<SCHEME, VEC, BLK, MINB, ZQ_DEEP_CK>(in, out, nthr, smem_flat, stream);
+        }
         if (flat_eligible<SCHEME, VEC, BLK, MINB>(in, nthr, smem_flat)) return launch_flat<SCHEME, VEC, BLK, MINB>(in, out, nthr, smem_flat, stream);
     }
     const int cols = nthr * VEC;
@@ -1730,8 +1751,12 @@ int64_t preferred_batch(int scheme, int n_z, int n_wl, int64_t max_scen, int n_s
         const int nthr = tile_threads(B, B);
         size_t smem = 0;
         bool flat;
-        if (scheme == CRT1D_SCHEME_ZQ)
-            flat = vec2 ? flat_eligible<CRT1D_SCHEME_ZQ, 2, B, M>(in, nthr, smem) : flat_eligible<CRT1D_SCHEME_ZQ, 1, B, M>(in, nthr, smem);
+        if (scheme == CRT1D_SCHEME_ZQ) {
+            flat = false;
+            if (zq_wide_spacing(n_z))  // deep canopies: one resident CTA (launch_one)
+                flat = vec2 ? flat_eligible<CRT1D_SCHEME_ZQ, 2, B, M>(in, nthr, smem, ZQ_DEEP_CK) : flat_eligible<CRT1D_SCHEME_ZQ, 1, B, M>(in, nthr, smem, ZQ_DEEP_CK);
+            if (!flat) flat = vec2 ? flat_eligible<CRT1D_SCHEME_ZQ, 2, B, M>(in, nthr, smem) : flat_eligible<CRT1D_SCHEME_ZQ, 1, B, M>(in, nthr, smem);
+        }
         else
             flat = vec2 ? flat_eligible<CRT1D_SCHEME_N79, 2, B, M>(in, nthr, smem) : flat_eligible<CRT1D_SCHEME_N79, 1, B, M>(in, nthr, smem);
         if (!flat) return max_scen;

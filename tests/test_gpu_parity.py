@@ -1184,6 +1184,44 @@ def test_black_soil_plugin_path(scheme):
 
 
 @pytest.mark.gpu
+def test_deep_zq_wide_checkpoint_spacing_is_bit_identical(monkeypatch):
+    """zq at n_z >= 512 runs the flat kernel with checkpoints every 20 levels (one resident CTA, a quarter of the parked
+    checkpoint bytes in flight) instead of every 10.  The back sweep re-runs the same expressions from the checkpoints, so
+    the profiles must be bit-identical for either spacing and for the band-tile kernel; also vs the oracle on one scenario.
+    Level counts around the threshold and not divisible by either spacing."""
+    import torch
+
+    from crt1d_b200 import engine
+    from crt1d_b200 import sweep
+
+    for n_z, lo, n in ((1000, 4321, 2), (515, 99, 3), (511, 99, 2), (531, 7, 2)):
+        spec = sweep.synthetic_sweep_spec(seed=0, n_z=n_z)
+        sub = spec.slice(lo, lo + n)
+        bw = np.stack([np.ones(spec.n_wl), np.linspace(0, 1, spec.n_wl)])
+        res = []
+        for env in ({}, {"CRT1D_B200_NO_WIDE_CK": "1"}, {"CRT1D_B200_NO_FLAT": "1"}):
+            for k in ("CRT1D_B200_NO_WIDE_CK", "CRT1D_B200_NO_FLAT"):
+                tune(monkeypatch, k, env.get(k))
+            res.append(engine.solve(sub, "zq", band_w=bw))
+            torch.cuda.synchronize()
+        for k in ("CRT1D_B200_NO_WIDE_CK", "CRT1D_B200_NO_FLAT"):
+            tune(monkeypatch, k, None)
+        for k in res[0]:
+            if k == "absorbed":
+                assert torch.equal(res[0][k], res[1][k]), f"wide vs standard spacing absorbed n_z={n_z}"
+                assert_close(res[0][k].cpu().numpy(), res[2][k].cpu().numpy(), 1e-12, f"flat vs tile absorbed n_z={n_z}")
+            else:
+                assert torch.equal(res[0][k], res[1][k]), f"wide vs standard spacing {k} n_z={n_z}"
+                assert torch.equal(res[0][k], res[2][k]), f"wide spacing vs tile kernel {k} n_z={n_z}"
+        if n_z == 515:  # vs the oracle at the common bar: host prologue (the reference's own quad calls for tau_i)
+            one = sub.slice(0, 1)
+            r = engine.solve(one, "zq", prologue=engine.host_prologue(one, "zq"))
+            ref = oracle.run("zq", one.scenario_params(0))
+            for k in ("I_dr", "I_df_d", "I_df_u", "F"):
+                assert_close(r[k][0].cpu().numpy(), ref[k], RTOL, f"deep zq n_z={n_z}.{k}", atol=1e-300)
+
+
+@pytest.mark.gpu
 def test_preferred_batch_fills_whole_waves():
     """crt1d_preferred_batch: scenarios per launch that fill whole waves of resident CTAs for the kernel the library
     picks (row-sweep: one CTA per scenario and SM; flat tridiagonal kernels: ceil(n gps / 256) CTAs on 2 n_SM slots;
