@@ -219,7 +219,9 @@ def _peak():
 def _kernel_name(scheme, runner):
     if scheme == "2s" and runner.chunk >= 148 and not os.environ.get("CRT1D_B200_2S_KERNEL"):
         return "crt::solve_2s_rows_kernel<VEC=2, LV=10, 512 threads, REC> (one CTA per scenario, row-major work items)"
-    if scheme in ("bl", "bf", "g77", "4s") and runner.chunk >= 148:
+    if scheme == "4s" and runner.chunk >= 148:
+        return "crt::solve_rows_kernel<4s> (four CTAs per scenario sharing its band chunks, row-major work items) + fixup_4s_kernel"
+    if scheme in ("bl", "bf", "g77") and runner.chunk >= 148:
         return f"crt::solve_rows_kernel<{scheme}> (one CTA per scenario, row-major work items)"
     if scheme in ("zq", "n79") and not os.environ.get("CRT1D_B200_NO_FLAT"):
         return f"crt::solve_flat_kernel<{scheme}, VEC=2> (flat column mapping, checkpointed Thomas sweeps)"

@@ -34,7 +34,7 @@ struct Tuning {
     int tile_threads = 0;        // CRT1D_B200_TILE_THREADS   (0 = per-scheme default)
     int diag_threads = 0;        // CRT1D_B200_DIAG_THREADS
     int rows_lv = 10, rows_th = 512, rows_rec = 1;  // CRT1D_B200_ROWS_CFG "LV,threads,rec"
-    int split_4s = 2;            // CRT1D_B200_4S_SPLIT
+    int split_4s = 4;            // CRT1D_B200_4S_SPLIT (measured: 2 -> 0.833, 3 -> 0.832, 4 -> 0.853 of HBM peak at 60 levels; n_z = 1000: 1 -> 0.795, 3 -> 0.776, 4 -> 0.815)
     int rows_threads = 0;        // CRT1D_B200_ROWS_THREADS
     long long scen_min = 148;    // CRT1D_B200_SCEN_MIN
     bool force_vec1 = false;     // CRT1D_B200_FORCE_VEC1
@@ -1618,10 +1618,10 @@ static cudaError_t launch_rows_t(const crt1d_batch& in, const crt1d_out& out, in
         return finish(cudaGetLastError());
     }
     if constexpr (IS4S) {
-        // Two CTAs per SM, each on half of the scenario's band chunks (half the coefficient array: 2 x ~106 KB):
-        // one CTA's store-free coefficient phase (~20 % of its life) overlaps the other's level sweeps.
-        // Deep canopies (n_z = 1000: 16 KB of level tables on top of the coefficients): the band chunks are split three
-        // or four ways instead, so that two CTAs still fit.
+        // Two resident CTAs per SM (register bound), each on a share of the scenario's band chunks: one CTA's store-free
+        // coefficient phase (~20 % of its life) overlaps the other's level sweeps.  First version: halves (2 x ~106 KB of
+        // coefficients); quarters are better at every depth (60 levels 0.833 -> 0.853, 1000 levels 0.776 (thirds) -> 0.815:
+        // shorter coefficient phases, finer interleaving) and leave room for the level tables of deep canopies.
         size_t smem2 = 0;
         const int split = split_4s_for(in.n_z, in.n_wl, VEC, smem2);
         if (split >= 2 && in.n_scen * split <= 2147483647LL) {

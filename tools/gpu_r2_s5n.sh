@@ -1,0 +1,25 @@
+#!/bin/bash
+# session 5, call N: 4s band split at 60 levels (2 = default, 3, 4) and at 300 levels
+O=$PWD/gpurun_out/s5n; mkdir -p $O
+line() { python - "$1" "$2" <<'PY'
+import json, sys
+l=[x for x in open(sys.argv[1]) if x.startswith("{")]
+if not l: print(sys.argv[2], "FAILED"); print(open(sys.argv[1]).read()[-600:]); sys.exit()
+d=json.loads(l[-1]); r=d["roofline"]; c=d["clocks"]
+print("%-34s value=%.4e frac=%.4f GB/s=%.0f kernel_ms=%.3f ms/step=%.2f sm_mhz=%s" % (sys.argv[2], d["value"], r["frac"], r["achieved"], r["kernel_ms"], d["ms_per_step"], c.get("sm_mhz")))
+PY
+}
+: > $O/summary.txt
+run() { name=$1; sch=$2; args=$3; shift 3
+  env "$@" timeout 300 python bench.py --scheme $sch $args > $O/v.json 2> $O/v.err; line $O/v.json "$name" | tee -a $O/summary.txt
+}
+S="--scenarios 66304 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-legs"
+M="--nz 300 --scenarios 3552 --chunk 888 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-legs"
+for rep in 1 2; do
+  run "4s n_z=60 split=2 (default)" 4s "$S" A=1
+  run "4s n_z=60 split=3" 4s "$S" CRT1D_B200_4S_SPLIT=3
+  run "4s n_z=60 split=4" 4s "$S" CRT1D_B200_4S_SPLIT=4
+  run "4s n_z=300 default" 4s "$M" A=1
+  run "4s n_z=300 split=3" 4s "$M" CRT1D_B200_4S_SPLIT=3
+  run "4s n_z=300 split=4" 4s "$M" CRT1D_B200_4S_SPLIT=4
+done
