@@ -212,6 +212,39 @@ def test_kernel_math_extreme_inputs_fuzz():
                 assert_close(v, r, 1e-9 if scheme == "2s" else RTOL, f"fuzz {trial} nz={nz} {scheme}.{k}", atol=atol)
 
 
+def test_kernel_math_4s_extreme_inputs_fuzz():
+    """The same kind of seeded fuzz for 4s against the reference run at tight `solve_bvp` tolerance (slow: three trials of
+    eight bands here; 12 trials were run when the test was written): omega from 1e-4 to 1 - 1e-9 (both sides of the vanishing
+    eigenvalue), black / bright soil, zero and huge irradiances, sun from the zenith to 1 degree above the horizon."""
+    from crt1d_b200 import cases
+    from util import with_callables
+
+    rng = np.random.default_rng(0)
+    for trial in range(3):
+        nz = int(rng.choice([3, 7, 20, 60]))
+        q = dict(cases.load_default_case(nz))
+        n = 8
+        om = np.concatenate([10.0 ** rng.uniform(-4, -1, 2), rng.uniform(0.02, 0.98, 3), 1.0 - 10.0 ** rng.uniform(-9, -2, 3)])
+        fr = rng.uniform(0.05, 0.95, n)
+        q["leaf_r"], q["leaf_t"] = om * fr, om * (1 - fr)
+        q["soil_r"] = rng.choice([0.0, 1e-6, 0.1, 0.5, 1.0], n)
+        q["I_dr0_all"] = rng.choice([0.0, 0.7, 300.0], n)
+        q["I_df0_all"] = rng.choice([0.0, 0.5, 100.0], n)
+        q["wl"] = np.linspace(0.4, 2.5, n)
+        q["dwl"] = np.full(n, q["wl"][1] - q["wl"][0])
+        q["wl_leafsoil"] = q["wl"]
+        q["psi"] = np.deg2rad(rng.choice([0.0, 30.0, 60.0, 85.0, 89.0]))
+        lai_tot = float(rng.choice([1e-2, 0.5, 3.0, 8.0, 15.0]))
+        q["lai"] = np.linspace(1, 0, nz) ** int(rng.choice([1, 2])) * lai_tot
+        q = with_callables(q)
+        with np.errstate(all="ignore"):
+            ref = oracle.solve_4s_tight(**{k: q[k] for k in oracle.ARGS["4s"]})
+        sol = _solve(q, "4s")
+        for k in ref:
+            assert np.all(np.isfinite(sol[k][np.isfinite(ref[k])])), f"4s fuzz {trial}.{k}: reference finite, kernel math not"
+            assert_close_4s(sol[k], ref[k], f"4s fuzz {trial} nz={nz}.{k}")
+
+
 def test_leaf_angle_device_functions():
     from crt1d_b200.leaf_angle import LeafAngle
     from crt1d_b200.solvers import common
